@@ -210,7 +210,7 @@ DVGO_API int dvgo_alpha2weight(const float* alpha, const int64_t* ray_id, int n_
   if (!alphainv_last || !i_start || !i_end) return DVGO_EINVAL;
   cudaStream_t s = as_stream(stream);
   a2w_init_kernel<<<blocks_for(n_rays, 256), 256, 0, s>>>(n_rays, alphainv_last, i_start, i_end);
-  if (n_pts == 0) return launch_status();  // :483-485
+  if (n_pts == 0) return launch_status(1);  // :483-485
   if (!alpha || !ray_id || !weight || !T) return DVGO_EINVAL;
   a2w_bounds_kernel<<<blocks_for(n_pts, 256), 256, 0, s>>>(ray_id, n_pts, i_start, i_end);
   const int wpb = 8;
@@ -218,7 +218,7 @@ DVGO_API int dvgo_alpha2weight(const float* alpha, const int64_t* ray_id, int n_
   const int blocks = static_cast<int>(want < kNumSMs * 16 ? want : kNumSMs * 16);
   alpha2weight_kernel<<<blocks, wpb * 32, 0, s>>>(alpha, n_rays, weight, T, alphainv_last, i_start,
                                                   i_end);
-  return launch_status();
+  return launch_status(3);
 }
 
 DVGO_API int dvgo_alpha2weight_backward(const float* alpha, const float* weight, const float* T,

@@ -15,8 +15,15 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 static inline cudaStream_t as_stream(dvgo_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// Launch-error check: cudaPeekAtLastError keeps the error sticky for the caller's own checks.
-static inline int launch_status() { return static_cast<int>(cudaGetLastError()); }
+// Number of kernels this library has launched (bench.py reports it as `gpu_launches`).
+extern unsigned long long g_launch_count;
+static inline void count_launches(int n) { __atomic_fetch_add(&g_launch_count, n, __ATOMIC_RELAXED); }
+
+// Launch-error check after the last of `n_kernels` launches of an entry point.
+static inline int launch_status(int n_kernels = 1) {
+  count_launches(n_kernels);
+  return static_cast<int>(cudaGetLastError());
+}
 
 static inline int blocks_for(int64_t n, int threads) {
   return static_cast<int>((n + threads - 1) / threads);

@@ -200,7 +200,12 @@ static inline int grid_for(int64_t n, int threads) {
 
 using namespace dvgo;
 
+namespace dvgo { unsigned long long g_launch_count = 0; }
+
 DVGO_API int dvgo_abi_version(void) { return DVGO_ABI_VERSION; }
+DVGO_API unsigned long long dvgo_launch_count(void) {
+  return __atomic_load_n(&dvgo::g_launch_count, __ATOMIC_RELAXED);
+}
 DVGO_API const char* dvgo_build_arch(void) { return "sm_100a"; }
 
 DVGO_API int dvgo_infer_t_minmax(const float* rays_o, const float* rays_d, const float* xyz_min,
@@ -250,7 +255,7 @@ DVGO_API int dvgo_sample_pts_count(const float* rays_o, const float* rays_d, con
                                                            far, stepdist, n_rays, t_min, t_max,
                                                            N_steps);
   inclusive_scan_i64_kernel<<<1, kScanThreads, 0, s>>>(N_steps, n_rays, N_steps_cumsum);
-  int err = launch_status();
+  int err = launch_status(2);
   if (err) return err;
   // The reference's single host sync (render_utils_kernel.cu:206): the caller must size outputs.
   err = static_cast<int>(cudaMemcpyAsync(total_host, N_steps_cumsum + (n_rays - 1), sizeof(int64_t),

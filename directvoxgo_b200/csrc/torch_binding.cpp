@@ -330,6 +330,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "directvoxgo_b200: sm_100a kernels behind the DirectVoxGO operator surface";
   m.def("abi_version", []() { return dvgo_abi_version(); });
   m.def("build_arch", []() { return std::string(dvgo_build_arch()); });
+  m.def("launch_count", []() { return dvgo_launch_count(); });
 
   auto ru = m.def_submodule("render_utils_cuda");
   ru.def("infer_t_minmax", &infer_t_minmax, "Inference t_min and t_max of ray-bbox intersection");

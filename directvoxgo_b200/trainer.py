@@ -1,0 +1,65 @@
+"""Training-step drivers for the hot path (what run.py:372-397 does once per iteration).
+
+`ModuleTrainer`  -- the op-by-op drop-in path: DirectVoxGO module on our kernels + torch autograd +
+                    TV + MaskedAdam, i.e. exactly the call sequence of the reference's loop body.
+`FusedTrainer`   -- (fused.py) the B200 fast path with its own grid layout; same step() contract.
+
+Both expose
+    step(rays_o, rays_d, viewdirs, target) -> loss tensor (0-dim, on device, no sync)
+and are what bench.py times and what the multi-GPU wrapper shards.
+"""
+import torch
+import torch.nn.functional as F
+
+from .masked_adam import create_optimizer_or_freeze_model
+
+
+def training_loss(ret, target, n_rays, weight_main=1.0, weight_entropy_last=0.0, weight_rgbper=0.0):
+    """Photometric + background-entropy + per-point colour loss (run.py:377-386)."""
+    loss = weight_main * F.mse_loss(ret["rgb_marched"], target)
+    if weight_entropy_last > 0:
+        pout = ret["alphainv_last"].clamp(1e-6, 1 - 1e-6)
+        entropy = -(pout * torch.log(pout) + (1 - pout) * torch.log(1 - pout)).mean()
+        loss = loss + weight_entropy_last * entropy
+    if weight_rgbper > 0:
+        rgbper = (ret["raw_rgb"] - target[ret["ray_id"]]).pow(2).sum(-1)
+        loss = loss + weight_rgbper * (rgbper * ret["weights"].detach()).sum() / n_rays
+    return loss
+
+
+class ModuleTrainer:
+    def __init__(self, model, cfg_train, render_kwargs, dist_group=None, world_size=1):
+        self.model = model
+        self.cfg = dict(cfg_train)
+        self.rk = dict(render_kwargs)
+        self.opt = create_optimizer_or_freeze_model(model, self.cfg, global_step=0)
+        self.global_step = 0
+        self.world_size = world_size
+        self.dist_group = dist_group
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        for p in self.model.parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.dist_group)
+
+    def step(self, rays_o, rays_d, viewdirs, target):
+        cfg, m = self.cfg, self.model
+        self.global_step += 1
+        n_global = len(rays_o) * self.world_size  # loss normalisers use the global batch
+        ret = m(rays_o, rays_d, viewdirs, global_step=self.global_step, **self.rk)
+        self.opt.zero_grad(set_to_none=True)
+        loss = training_loss(ret, target, len(rays_o), cfg.get("weight_main", 1.0),
+                             cfg.get("weight_entropy_last", 0.0), cfg.get("weight_rgbper", 0.0))
+        if self.world_size > 1:
+            loss = loss / self.world_size
+        loss.backward()
+        if self.world_size > 1:
+            self._allreduce_grads()
+        dense = cfg.get("tv_dense", True)
+        if cfg.get("weight_tv_density", 0) > 0:
+            m.density_total_variation_add_grad(cfg["weight_tv_density"] / n_global, dense)
+        if cfg.get("weight_tv_k0", 0) > 0:
+            m.k0_total_variation_add_grad(cfg["weight_tv_k0"] / n_global, dense)
+        self.opt.step()
+        return loss.detach()

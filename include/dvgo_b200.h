@@ -36,6 +36,8 @@ typedef void* dvgo_stream_t; /* cudaStream_t */
 int dvgo_abi_version(void);
 /* Name of the compiled architecture ("sm_100a"). */
 const char* dvgo_build_arch(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic counter). */
+unsigned long long dvgo_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * a1  render_utils_cuda.infer_t_minmax        lib/cuda/render_utils.cpp:44-52,

@@ -1,0 +1,169 @@
+"""GPU parity tests at the model level (row a14): DirectVoxGO / DirectMPIGO on the CUDA kernels
+against (i) the golden outputs of the reference's own Python (tests/golden/refpy_*.npz) and
+(ii) the CPU oracle model on bigger seeded inputs -- forward dict, gradients and two full training
+iterations (fwd + loss + bwd + TV + MaskedAdam)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_to_max, to_np
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RK = dict(near=0.2, far=6.0, bg=1.0, stepsize=0.5)
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _loss(ret, target, n, wm, we, wp):
+    loss = wm * F.mse_loss(ret["rgb_marched"], target)
+    if we > 0:
+        pout = ret["alphainv_last"].clamp(1e-6, 1 - 1e-6)
+        loss = loss + we * (-(pout * torch.log(pout) + (1 - pout) * torch.log(1 - pout)).mean())
+    if wp > 0:
+        rgbper = (ret["raw_rgb"] - target[ret["ray_id"]]).pow(2).sum(-1)
+        loss = loss + wp * (rgbper * ret["weights"].detach()).sum() / n
+    return loss
+
+
+def _build(g, stage):
+    from directvoxgo_b200.dvgo import DirectVoxGO
+    if stage == "fine":
+        kw = dict(num_voxels=18 ** 3, num_voxels_base=18 ** 3, alpha_init=1e-2, fast_color_thres=1e-4,
+                  rgbnet_dim=12, rgbnet_direct=True, rgbnet_depth=3, rgbnet_width=128, viewbase_pe=4)
+    else:
+        kw = dict(num_voxels=16 ** 3, num_voxels_base=16 ** 3, alpha_init=1e-6, fast_color_thres=1e-7, rgbnet_dim=0)
+    m = DirectVoxGO(xyz_min=g["xyz_min"], xyz_max=g["xyz_max"], **kw)
+    assert tuple(m.world_size.tolist()) == tuple(g["world_size"].tolist())
+    with torch.no_grad():
+        m.density.copy_(torch.tensor(g["density0"]))
+        m.k0.copy_(torch.tensor(g["k00"]))
+        m.mask_cache.mask.copy_(torch.tensor(g["mask"]))
+        if stage == "fine":
+            lin = [x for x in m.rgbnet.modules() if isinstance(x, torch.nn.Linear)]
+            for i, l in enumerate(lin):
+                l.weight.copy_(torch.tensor(g["rgbnet_w%d" % i]))
+                l.bias.copy_(torch.tensor(g["rgbnet_b%d" % i]))
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("stage", ["fine", "coarse"])
+def test_dvgo_forward_backward_step_vs_reference_python(golden_dir, stage):
+    from directvoxgo_b200.masked_adam import MaskedAdam
+    g = _load(golden_dir, "refpy_%s_small.npz" % stage)
+    m = _build(g, stage)
+    ro, rd, vd, tgt = (torch.tensor(g[k]).to(DEV) for k in ("rays_o", "rays_d", "viewdirs", "target"))
+    cfg = dict(fine=(1.0, 1e-3, 1e-2, 1e-5, ["density", "k0"]), coarse=(1.0, 1e-2, 0.1, 0.0, []))[stage]
+    groups = [{"params": m.density, "lr": 0.1, "skip_zero_grad": "density" in cfg[4]},
+              {"params": m.k0, "lr": 0.1, "skip_zero_grad": "k0" in cfg[4]}]
+    if m.rgbnet is not None:
+        groups.append({"params": m.rgbnet.parameters(), "lr": 1e-3, "skip_zero_grad": False})
+    opt = MaskedAdam(groups)
+    for it in range(2):
+        ret = m(ro, rd, vd, global_step=it, render_depth=True, **RK)
+        opt.zero_grad(set_to_none=True)
+        loss = _loss(ret, tgt, len(ro), cfg[0], cfg[1], cfg[2])
+        loss.backward()
+        if it == 0:
+            assert np.array_equal(to_np(ret["ray_id"]), g["out_ray_id"])          # bit-exact sample set
+            for k, tol in (("alphainv_last", 2e-6), ("weights", 2e-6), ("raw_alpha", 2e-6),
+                           ("raw_rgb", 1e-5), ("rgb_marched", 1e-5), ("depth", 1e-4)):
+                np.testing.assert_allclose(to_np(ret[k]), g["out_" + k], rtol=1e-5, atol=tol, err_msg=k)
+            assert abs(loss.item() - float(g["loss0"])) < 1e-6
+            assert rel_to_max(m.density.grad, g["grad_density0"]) < 1e-4    # atomics: rel 1e-4 of max-abs
+            assert rel_to_max(m.k0.grad, g["grad_k00"]) < 1e-4
+            if stage == "fine":
+                lin = [x for x in m.rgbnet.modules() if isinstance(x, torch.nn.Linear)]
+                for i, l in enumerate(lin):
+                    assert rel_to_max(l.weight.grad, g["grad_rgbnet_w%d" % i]) < 1e-4
+        if cfg[3] > 0:
+            m.density_total_variation_add_grad(cfg[3] / len(ro), True)
+            m.k0_total_variation_add_grad(cfg[3] / len(ro), True)
+        opt.step()
+    assert abs(loss.item() - float(g["loss1"])) < 2e-6
+    # Adam normalises the step, so tiny grad differences show up as ~lr-sized flips only where
+    # |grad| ~ 0; compare the bulk.
+    for got, ref in ((m.density, g["density2"]), (m.k0, g["k02"])):
+        d = np.abs(to_np(got) - ref)
+        assert np.quantile(d, 0.999) < 2e-3 and np.median(d) < 1e-5
+
+
+def test_dmpigo_forward_backward_vs_reference_python(golden_dir):
+    from directvoxgo_b200.dmpigo import DirectMPIGO
+    g = _load(golden_dir, "refpy_dmpigo_small.npz")
+    m = DirectMPIGO(xyz_min=g["xyz_min"], xyz_max=g["xyz_max"], num_voxels=20 * 18 * 16, mpi_depth=16,
+                    fast_color_thres=1e-3, rgbnet_dim=9, rgbnet_depth=3, rgbnet_width=64, viewbase_pe=0)
+    assert tuple(m.world_size.tolist()) == tuple(g["world_size"].tolist())
+    with torch.no_grad():
+        m.density.copy_(torch.tensor(g["density0"]))
+        m.k0.copy_(torch.tensor(g["k00"]))
+        lin = [x for x in m.rgbnet.modules() if isinstance(x, torch.nn.Linear)]
+        for i, l in enumerate(lin):
+            l.weight.copy_(torch.tensor(g["rgbnet_w%d" % i]))
+            l.bias.copy_(torch.tensor(g["rgbnet_b%d" % i]))
+    m = m.to(DEV)
+    ro, rd, vd = (torch.tensor(g[k]).to(DEV) for k in ("rays_o", "rays_d", "viewdirs"))
+    ret = m(ro, rd, vd, global_step=0, near=0, far=1, bg=0.0, stepsize=0.5, render_depth=True)
+    assert np.array_equal(to_np(ret["ray_id"]), g["out_ray_id"])
+    for k, tol in (("alphainv_last", 2e-6), ("weights", 2e-6), ("raw_alpha", 2e-6), ("raw_rgb", 1e-5),
+                   ("rgb_marched", 1e-5), ("depth", 1e-4)):
+        np.testing.assert_allclose(to_np(ret[k]), g["out_" + k], rtol=1e-5, atol=tol, err_msg=k)
+    loss = F.mse_loss(ret["rgb_marched"], torch.full((len(ro), 3), 0.5, device=DEV))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss0"])) < 1e-6
+    assert rel_to_max(m.density.grad, g["grad_density0"]) < 1e-4
+    assert rel_to_max(m.k0.grad, g["grad_k00"]) < 1e-4
+
+
+def test_dvgo_vs_oracle_model_bigger(golden_dir):
+    """40^3 fine grid, 2048 Blender-geometry rays: CUDA model vs the CPU oracle model."""
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.dvgo import DirectVoxGO
+    from oracle.model_ref import RefDVGO
+    lo, hi = syn.fine_bbox()
+    kw = dict(syn.FINE_MODEL, num_voxels=40 ** 3, num_voxels_base=40 ** 3)
+    torch.manual_seed(0)
+    m = DirectVoxGO(lo, hi, **kw)
+    syn.randomize_grids_(m, 1)
+    with torch.no_grad():
+        m.density.mul_(3.0)
+        m.mask_cache.mask.copy_(torch.rand(m.mask_cache.mask.shape) > 0.3)
+    ref = RefDVGO.from_module(m)
+    m = m.to(DEV)
+    ro, rd, vd, tgt = syn.random_training_rays(2048, n_views=20, seed=3)
+    rk = dict(near=2.0, far=6.0, bg=1.0, stepsize=0.5)
+    r_ref = ref.forward(ro, rd, vd, rk["near"], rk["far"], rk["stepsize"], rk["bg"], render_depth=True)
+    l_ref = ref.loss(r_ref, tgt, len(ro), 1.0, 1e-3, 1e-2)
+    l_ref.backward()
+    r = m(ro.to(DEV), rd.to(DEV), vd.to(DEV), global_step=0, render_depth=True, **rk)
+    loss = _loss(r, tgt.to(DEV), len(ro), 1.0, 1e-3, 1e-2)
+    loss.backward()
+    assert np.array_equal(to_np(r["ray_id"]), to_np(r_ref["ray_id"]))
+    for k in ("alphainv_last", "weights", "raw_alpha", "raw_rgb", "rgb_marched"):
+        np.testing.assert_allclose(to_np(r[k]), to_np(r_ref[k]), rtol=1e-5, atol=1e-5, err_msg=k)
+    assert abs(loss.item() - l_ref.item()) < 1e-6
+    assert rel_to_max(m.density.grad, ref.density.grad) < 1e-4
+    assert rel_to_max(m.k0.grad, ref.k0.grad) < 1e-4
+
+
+def test_unmodified_reference_surface_via_dropin():
+    """`dropin.install()` must serve the reference's load() names and torch_scatter from our build."""
+    import torch.utils.cpp_extension as cpp_ext
+    import directvoxgo_b200 as pkg
+    from directvoxgo_b200 import dropin
+    dropin.install()
+    try:
+        assert cpp_ext.load(name="render_utils_cuda", sources=["x"]) is pkg.render_utils_cuda
+        assert cpp_ext.load(name="total_variation_cuda", sources=["x"], verbose=True) is pkg.total_variation_cuda
+        assert cpp_ext.load(name="adam_upd_cuda", sources=["x"]) is pkg.adam_upd_cuda
+        from torch_scatter import segment_coo
+        out = segment_coo(src=torch.ones(4, 3, device=DEV), index=torch.tensor([0, 0, 2, 2], device=DEV),
+                          out=torch.zeros(3, 3, device=DEV), reduce="sum")
+        assert out.tolist() == [[2, 2, 2], [0, 0, 0], [2, 2, 2]]
+    finally:
+        dropin.uninstall()
