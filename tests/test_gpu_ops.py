@@ -100,8 +100,7 @@ def test_alpha2weight_and_backward(pkg, n_rays, n_pts, seed, amax):
     assert diff.mean() <= 0.01
     same = ~diff
     # tolerance: the scan re-associates the double product -> rel 2e-6 on T / w / alphainv_last
-    ok_rays = torch.tensor(same)
-    keep = ok_rays[rid]
+    keep = same[rid.numpy()]
     np.testing.assert_allclose(to_np(T)[keep], to_np(T_r)[keep], rtol=2e-6, atol=1e-9)
     np.testing.assert_allclose(to_np(w)[keep], to_np(w_r)[keep], rtol=2e-6, atol=1e-9)
     np.testing.assert_allclose(to_np(last)[same], to_np(last_r)[same], rtol=2e-6, atol=1e-9)
