@@ -1,5 +1,220 @@
-// fused_binding.cpp -- torch adaptor for the fused trainer / renderer entry points (filled in as
-// the fused kernels land; see include/dvgo_b200_fused.h).
+// fused_binding.cpp -- torch adaptor for the fused entry points of include/dvgo_b200_fused.h.
+// Every buffer is a preallocated torch tensor owned by the Python FusedTrainer / FusedRenderer; the
+// functions below only validate (CUDA, contiguous, dtype), pass raw pointers + the current stream
+// and turn non-zero return codes into RuntimeError.  No allocation, no synchronisation.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
-void dvgo_bind_fused(pybind11::module_& m) { (void)m; }
+#include "../../include/dvgo_b200_fused.h"
+
+namespace {
+
+using torch::Tensor;
+
+inline dvgo_stream_t cur_stream() {
+  return reinterpret_cast<dvgo_stream_t>(at::cuda::getCurrentCUDAStream().stream());
+}
+
+inline void chk(const Tensor& t, const char* name, c10::ScalarType st) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+  TORCH_CHECK(t.scalar_type() == st, name, " has the wrong dtype");
+}
+#define F32(t) chk(t, #t, torch::kFloat32)
+#define I32(t) chk(t, #t, torch::kInt32)
+
+inline void rc_check(int rc, const char* what) {
+  TORCH_CHECK(rc == 0, "dvgo_b200 fused: ", what, " failed with code ", rc,
+              rc > 0 ? (std::string(" (") + cudaGetErrorString(static_cast<cudaError_t>(rc)) + ")")
+                     : std::string(" (invalid argument)"));
+}
+
+inline const float* fp(const Tensor& t) { return t.data_ptr<float>(); }
+inline float* fpm(const Tensor& t) { return t.data_ptr<float>(); }
+inline int32_t* ipm(const Tensor& t) { return t.data_ptr<int32_t>(); }
+inline const float* fp_opt(const c10::optional<Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+
+// Scene constants + the tensors they point into (kept alive by the object).
+struct Scene {
+  dvgo_scene_t s;
+  Tensor xyz_min, xyz_max, mask, mask_scale, mask_shift;
+  Scene(int X, int Y, int Z, int C, Tensor xyz_min_, Tensor xyz_max_, c10::optional<Tensor> mask_,
+        c10::optional<Tensor> mask_scale_, c10::optional<Tensor> mask_shift_, double near, double far,
+        double stepdist, double act_shift, double interval, double thres, bool ndc, int ndc_samples)
+      : xyz_min(xyz_min_), xyz_max(xyz_max_) {
+    F32(xyz_min); F32(xyz_max);
+    s.X = X; s.Y = Y; s.Z = Z; s.C = C;
+    s.xyz_min = fp(xyz_min); s.xyz_max = fp(xyz_max);
+    s.mask = nullptr; s.mx = s.my = s.mz = 0; s.mask_scale = s.mask_shift = nullptr;
+    if (mask_.has_value()) {
+      mask = *mask_; mask_scale = *mask_scale_; mask_shift = *mask_shift_;
+      chk(mask, "mask", torch::kBool); F32(mask_scale); F32(mask_shift);
+      TORCH_CHECK(mask.dim() == 3, "mask must be [X,Y,Z]");
+      s.mask = reinterpret_cast<const uint8_t*>(mask.data_ptr<bool>());
+      s.mx = mask.size(0); s.my = mask.size(1); s.mz = mask.size(2);
+      s.mask_scale = fp(mask_scale); s.mask_shift = fp(mask_shift);
+    }
+    s.near = static_cast<float>(near); s.far = static_cast<float>(far);
+    s.stepdist = static_cast<float>(stepdist); s.act_shift = static_cast<float>(act_shift);
+    s.interval = static_cast<float>(interval); s.fast_color_thres = static_cast<float>(thres);
+    s.ndc = ndc ? 1 : 0; s.ndc_samples = ndc_samples;
+  }
+  int max_steps() const { return dvgo_fused_max_steps(&s); }
+};
+
+void ray_setup(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor t_min, Tensor n_steps, Tensor ray_off) {
+  F32(rays_o); F32(rays_d); F32(t_min); I32(n_steps); I32(ray_off);
+  const int n = rays_o.size(0);
+  TORCH_CHECK(ray_off.numel() >= n + 1 && t_min.numel() >= n && n_steps.numel() >= n, "workspace too small");
+  const c10::cuda::CUDAGuard guard(rays_o.device());
+  rc_check(dvgo_fused_ray_setup(fp(rays_o), fp(rays_d), &sc.s, n, fpm(t_min), ipm(n_steps), ipm(ray_off),
+                                cur_stream()), "ray_setup");
+}
+
+void march_fwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor density, c10::optional<Tensor> k0_cl,
+               Tensor t_min, Tensor n_steps, Tensor ray_off, Tensor slot_alpha, Tensor slot_T,
+               Tensor slot_expd, Tensor slot_code, Tensor feat, Tensor s_ray, Tensor s_slot, Tensor s_weight,
+               Tensor alphainv_last, Tensor counters) {
+  F32(rays_o); F32(rays_d); F32(density); F32(t_min); I32(n_steps); I32(ray_off); F32(slot_alpha);
+  F32(slot_T); F32(slot_expd); I32(slot_code); F32(feat); I32(s_ray); I32(s_slot); F32(s_weight);
+  F32(alphainv_last); I32(counters);
+  if (k0_cl.has_value()) { F32((*k0_cl)); TORCH_CHECK(k0_cl->numel() == density.numel() * sc.s.C, "k0_cl must be [X,Y,Z,C]"); }
+  TORCH_CHECK(density.numel() == (int64_t)sc.s.X * sc.s.Y * sc.s.Z, "density must be [X,Y,Z]");
+  const int n = rays_o.size(0);
+  const int64_t slot_cap = slot_code.numel(), surv_cap = s_ray.numel();
+  TORCH_CHECK(slot_alpha.numel() >= slot_cap && slot_T.numel() >= slot_cap && slot_expd.numel() >= slot_cap, "slot arrays");
+  TORCH_CHECK(s_slot.numel() >= surv_cap && s_weight.numel() >= surv_cap && feat.numel() >= surv_cap * sc.s.C, "survivor arrays");
+  TORCH_CHECK(alphainv_last.numel() >= n && counters.numel() >= 2, "per-ray arrays");
+  const c10::cuda::CUDAGuard guard(rays_o.device());
+  rc_check(dvgo_fused_march_fwd(fp(rays_o), fp(rays_d), &sc.s, fp(density), fp_opt(k0_cl), n, fp(t_min),
+                                ipm(n_steps), ipm(ray_off), slot_cap, surv_cap, fpm(slot_alpha), fpm(slot_T),
+                                fpm(slot_expd), ipm(slot_code), fpm(feat), ipm(s_ray), ipm(s_slot),
+                                fpm(s_weight), fpm(alphainv_last), ipm(counters), cur_stream()), "march_fwd");
+}
+
+void rgb_direct(Tensor feat, Tensor counters, Tensor rgb) {
+  F32(feat); I32(counters); F32(rgb);
+  const c10::cuda::CUDAGuard guard(feat.device());
+  rc_check(dvgo_fused_rgb_direct(fp(feat), ipm(counters), rgb.numel() / 3, fpm(rgb), cur_stream()), "rgb_direct");
+}
+
+void rgb_direct_bwd(Tensor rgb, Tensor d_rgb, Tensor counters, Tensor d_feat) {
+  F32(rgb); F32(d_rgb); I32(counters); F32(d_feat);
+  const c10::cuda::CUDAGuard guard(rgb.device());
+  rc_check(dvgo_fused_rgb_direct_bwd(fp(rgb), fp(d_rgb), ipm(counters), rgb.numel() / 3, fpm(d_feat), cur_stream()),
+           "rgb_direct_bwd");
+}
+
+void composite(Tensor rgb, Tensor s_weight, Tensor s_ray, Tensor s_slot, Tensor ray_off, Tensor counters,
+               Tensor rgb_acc, c10::optional<Tensor> depth_acc) {
+  F32(rgb); F32(s_weight); I32(s_ray); I32(s_slot); I32(ray_off); I32(counters); F32(rgb_acc);
+  if (depth_acc.has_value()) F32((*depth_acc));
+  const c10::cuda::CUDAGuard guard(rgb.device());
+  rc_check(dvgo_fused_composite(fp(rgb), fp(s_weight), ipm(s_ray), ipm(s_slot), ipm(ray_off), ipm(counters),
+                                rgb.numel() / 3, fpm(rgb_acc),
+                                depth_acc.has_value() ? depth_acc->data_ptr<float>() : nullptr, cur_stream()),
+           "composite");
+}
+
+void ray_finish(Tensor rgb_acc, Tensor alphainv_last, c10::optional<Tensor> target, double bg, int n_rays,
+                int n_global, double weight_main, double weight_entropy_last, c10::optional<Tensor> G,
+                c10::optional<Tensor> g_last, c10::optional<Tensor> loss_acc) {
+  F32(rgb_acc); F32(alphainv_last);
+  if (target.has_value()) { F32((*target)); F32((*G)); F32((*g_last)); }
+  const c10::cuda::CUDAGuard guard(rgb_acc.device());
+  rc_check(dvgo_fused_ray_finish(fpm(rgb_acc), fp(alphainv_last), fp_opt(target), static_cast<float>(bg), n_rays,
+                                 n_global, static_cast<float>(weight_main), static_cast<float>(weight_entropy_last),
+                                 G.has_value() ? G->data_ptr<float>() : nullptr,
+                                 g_last.has_value() ? g_last->data_ptr<float>() : nullptr,
+                                 loss_acc.has_value() ? loss_acc->data_ptr<float>() : nullptr, cur_stream()),
+           "ray_finish");
+}
+
+void sample_grad(Tensor rgb, Tensor s_weight, Tensor s_ray, Tensor G, Tensor target, Tensor counters, int n_global,
+                 double weight_rgbper, Tensor d_rgb, Tensor d_w, Tensor loss_acc) {
+  F32(rgb); F32(s_weight); I32(s_ray); F32(G); F32(target); I32(counters); F32(d_rgb); F32(d_w); F32(loss_acc);
+  const c10::cuda::CUDAGuard guard(rgb.device());
+  rc_check(dvgo_fused_sample_grad(fp(rgb), fp(s_weight), ipm(s_ray), fp(G), fp(target), ipm(counters),
+                                  rgb.numel() / 3, n_global, static_cast<float>(weight_rgbper), fpm(d_rgb), fpm(d_w),
+                                  fpm(loss_acc), cur_stream()), "sample_grad");
+}
+
+void march_bwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor t_min, Tensor n_steps, Tensor ray_off,
+               Tensor slot_alpha, Tensor slot_T, Tensor slot_expd, Tensor slot_code, Tensor d_feat, Tensor d_w,
+               Tensor alphainv_last, Tensor g_last, Tensor grad_density, c10::optional<Tensor> grad_k0_cl) {
+  F32(rays_o); F32(rays_d); F32(t_min); I32(n_steps); I32(ray_off); F32(slot_alpha); F32(slot_T); F32(slot_expd);
+  I32(slot_code); F32(d_feat); F32(d_w); F32(alphainv_last); F32(g_last); F32(grad_density);
+  if (grad_k0_cl.has_value()) F32((*grad_k0_cl));
+  const c10::cuda::CUDAGuard guard(rays_o.device());
+  rc_check(dvgo_fused_march_bwd(fp(rays_o), fp(rays_d), &sc.s, rays_o.size(0), fp(t_min), ipm(n_steps), ipm(ray_off),
+                                fp(slot_alpha), fp(slot_T), fp(slot_expd), ipm(slot_code), fp(d_feat), fp(d_w),
+                                fp(alphainv_last), fp(g_last), fpm(grad_density),
+                                grad_k0_cl.has_value() ? grad_k0_cl->data_ptr<float>() : nullptr, cur_stream()),
+           "march_bwd");
+}
+
+void sweep(Tensor param_in, Tensor param_out, Tensor grad, Tensor exp_avg, Tensor exp_avg_sq,
+           c10::optional<Tensor> perlr, int X, int Y, int Z, int C, bool tv, bool tv_dense, double wx, double wy,
+           double wz, bool masked, int step, double beta1, double beta2, double lr, double eps) {
+  F32(param_in); F32(param_out); F32(grad); F32(exp_avg); F32(exp_avg_sq);
+  const int64_t n = (int64_t)X * Y * Z * C;
+  TORCH_CHECK(param_in.numel() == n && param_out.numel() == n && grad.numel() == n && exp_avg.numel() == n &&
+                  exp_avg_sq.numel() == n, "sweep: all buffers must have X*Y*Z*C elements");
+  const c10::cuda::CUDAGuard guard(param_in.device());
+  rc_check(dvgo_fused_sweep(fp(param_in), fpm(param_out), fpm(grad), fpm(exp_avg), fpm(exp_avg_sq), fp_opt(perlr), X,
+                            Y, Z, C, tv, tv_dense, static_cast<float>(wx), static_cast<float>(wy),
+                            static_cast<float>(wz), masked, step, static_cast<float>(beta1),
+                            static_cast<float>(beta2), static_cast<float>(lr), static_cast<float>(eps), cur_stream()),
+           "sweep");
+}
+
+Tensor ncdhw_to_cl(Tensor src) {  // [1,C,X,Y,Z] -> [X,Y,Z,C]
+  F32(src);
+  TORCH_CHECK(src.dim() == 5 && src.size(0) == 1, "expected [1,C,X,Y,Z]");
+  const c10::cuda::CUDAGuard guard(src.device());
+  const int C = src.size(1);
+  auto dst = torch::empty({src.size(2), src.size(3), src.size(4), C}, src.options());
+  rc_check(dvgo_grid_ncdhw_to_cl(fp(src), fpm(dst), C, src.numel() / std::max(C, 1), cur_stream()), "ncdhw_to_cl");
+  return dst;
+}
+
+Tensor cl_to_ncdhw(Tensor src) {  // [X,Y,Z,C] -> [1,C,X,Y,Z]
+  F32(src);
+  TORCH_CHECK(src.dim() == 4, "expected [X,Y,Z,C]");
+  const c10::cuda::CUDAGuard guard(src.device());
+  const int C = src.size(3);
+  auto dst = torch::empty({1, C, src.size(0), src.size(1), src.size(2)}, src.options());
+  rc_check(dvgo_grid_cl_to_ncdhw(fp(src), fpm(dst), C, src.numel() / std::max(C, 1), cur_stream()), "cl_to_ncdhw");
+  return dst;
+}
+
+void zero_(Tensor t) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.element_size() == 4, "zero_: 4-byte contiguous CUDA tensor");
+  const c10::cuda::CUDAGuard guard(t.device());
+  rc_check(dvgo_fused_zero(t.data_ptr(), t.numel(), cur_stream()), "zero");
+}
+
+}  // namespace
+
+void dvgo_bind_mlp(pybind11::module_& m);  // mlp_binding.cpp
+
+void dvgo_bind_fused(pybind11::module_& m) {
+  pybind11::class_<Scene>(m, "Scene")
+      .def(pybind11::init<int, int, int, int, Tensor, Tensor, c10::optional<Tensor>, c10::optional<Tensor>,
+                          c10::optional<Tensor>, double, double, double, double, double, double, bool, int>())
+      .def("max_steps", &Scene::max_steps);
+  m.def("ray_setup", &ray_setup);
+  m.def("march_fwd", &march_fwd);
+  m.def("rgb_direct", &rgb_direct);
+  m.def("rgb_direct_bwd", &rgb_direct_bwd);
+  m.def("composite", &composite);
+  m.def("ray_finish", &ray_finish);
+  m.def("sample_grad", &sample_grad);
+  m.def("march_bwd", &march_bwd);
+  m.def("sweep", &sweep);
+  m.def("ncdhw_to_cl", &ncdhw_to_cl);
+  m.def("cl_to_ncdhw", &cl_to_ncdhw);
+  m.def("zero_", &zero_);
+  dvgo_bind_mlp(m);
+}

@@ -1,0 +1,503 @@
+// fused_march.cu -- the fused per-ray kernels: ray_setup, march_fwd, march_bwd.
+//
+// One WARP owns one ray and walks it in chunks of 32 consecutive steps (lane = step), so
+//   * every per-sample array is read / written coalesced (the reference's per-ray kernels stride by
+//     the ray length across a warp, render_utils_kernel.cu:447-455),
+//   * the transmittance product is a 5-step shuffle scan instead of a serial loop,
+//   * the four data-dependent masks of DirectVoxGO.forward (lib/dvgo.py:444-447, 469-473, 478-484,
+//     488-494: 16 boolean-index compactions, each a host sync) become lane predicates, and
+//   * 32 neighbouring samples of a ray touch a ~16-voxel-long tube of the grid: the 8 trilinear
+//     corner fetches of adjacent lanes hit the same L1 lines.
+// Grid layout: density [X,Y,Z]; k0 channel-last [X,Y,Z,C], so one corner is C contiguous floats
+// (48 B for C=12 = three 16-byte vector loads, the two z-corners are adjacent in memory) instead of
+// C loads from C planes 16 MB apart as in the reference's NCDHW layout.
+//
+// Arithmetic follows the reference expression trees exactly where integer / boolean results depend
+// on it (common.cuh); see include/dvgo_b200_fused.h for the data layout.
+#include "common.cuh"
+#include "../../include/dvgo_b200_fused.h"
+
+namespace dvgo {
+
+struct SceneDev {
+  int X, Y, Z, C;
+  float lo[3], hi[3];
+  const uint8_t* mask;
+  int mx, my, mz;
+  float mscale[3], mshift[3];
+  float near, far, stepdist, act_shift, interval, thres;
+  int ndc, ndc_samples;
+};
+
+// The three [3] vectors live in device memory (they are torch buffers); fetch them once per thread.
+struct SceneArgs {
+  int X, Y, Z, C;
+  const float* xyz_min;
+  const float* xyz_max;
+  const uint8_t* mask;
+  int mx, my, mz;
+  const float* mask_scale;
+  const float* mask_shift;
+  float near, far, stepdist, act_shift, interval, thres;
+  int ndc, ndc_samples;
+};
+
+static inline SceneArgs to_args(const dvgo_scene_t* s) {
+  SceneArgs a;
+  a.X = s->X; a.Y = s->Y; a.Z = s->Z; a.C = s->C;
+  a.xyz_min = s->xyz_min; a.xyz_max = s->xyz_max;
+  a.mask = s->mask; a.mx = s->mx; a.my = s->my; a.mz = s->mz;
+  a.mask_scale = s->mask_scale; a.mask_shift = s->mask_shift;
+  a.near = s->near; a.far = s->far; a.stepdist = s->stepdist; a.act_shift = s->act_shift;
+  a.interval = s->interval; a.thres = s->fast_color_thres;
+  a.ndc = s->ndc; a.ndc_samples = s->ndc_samples;
+  return a;
+}
+
+__device__ __forceinline__ SceneDev load_scene(const SceneArgs& a) {
+  SceneDev s;
+  s.X = a.X; s.Y = a.Y; s.Z = a.Z; s.C = a.C;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.lo[i] = __ldg(a.xyz_min + i);
+    s.hi[i] = __ldg(a.xyz_max + i);
+    s.mscale[i] = a.mask ? __ldg(a.mask_scale + i) : 0.f;
+    s.mshift[i] = a.mask ? __ldg(a.mask_shift + i) : 0.f;
+  }
+  s.mask = a.mask; s.mx = a.mx; s.my = a.my; s.mz = a.mz;
+  s.near = a.near; s.far = a.far; s.stepdist = a.stepdist; s.act_shift = a.act_shift;
+  s.interval = a.interval; s.thres = a.thres; s.ndc = a.ndc; s.ndc_samples = a.ndc_samples;
+  return s;
+}
+
+// Per-ray constants: where sample i of the ray lies.
+struct RayGeom {
+  float sx, sy, sz, ux, uy, uz;  // p_i = s + u * dist_i
+  float inv_ndc;                 // ndc: dist_i = i / (N-1)
+};
+
+__device__ __forceinline__ RayGeom ray_geom(const SceneDev& sc, const float* __restrict__ rays_o,
+                                            const float* __restrict__ rays_d, int r, float t_min) {
+  RayGeom g;
+  const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+  const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+  if (sc.ndc) {  // lib/cuda/render_utils_kernel.cu:254-257: p = o + d * (i/(N-1))
+    g.sx = ox; g.sy = oy; g.sz = oz; g.ux = dx; g.uy = dy; g.uz = dz;
+    g.inv_ndc = static_cast<float>(sc.ndc_samples - 1);
+  } else {       // :62-71, :178-181: p = (o + d*t_min) + (d/|d|) * (stepdist*i)
+    const StartDir s = ray_start_dir(ox, oy, oz, dx, dy, dz, t_min);
+    g.sx = s.sx; g.sy = s.sy; g.sz = s.sz; g.ux = s.ux; g.uy = s.uy; g.uz = s.uz;
+    g.inv_ndc = 0.f;
+  }
+  return g;
+}
+
+__device__ __forceinline__ void sample_point(const SceneDev& sc, const RayGeom& g, int i, float& px,
+                                             float& py, float& pz) {
+  const float dist = sc.ndc ? fdiv(static_cast<float>(i), g.inv_ndc)
+                            : fmul(sc.stepdist, static_cast<float>(i));
+  px = fma_(g.ux, dist, g.sx);
+  py = fma_(g.uy, dist, g.sy);
+  pz = fma_(g.uz, dist, g.sz);
+}
+
+__device__ __forceinline__ bool occupancy(const SceneDev& sc, float px, float py, float pz) {
+  if (!sc.mask) return true;
+  const int i = static_cast<int>(roundf(fma_(px, sc.mscale[0], sc.mshift[0])));
+  const int j = static_cast<int>(roundf(fma_(py, sc.mscale[1], sc.mshift[1])));
+  const int k = static_cast<int>(roundf(fma_(pz, sc.mscale[2], sc.mshift[2])));
+  if ((0 <= i) & (i < sc.mx) & (0 <= j) & (j < sc.my) & (0 <= k) & (k < sc.mz))
+    return sc.mask[(static_cast<int64_t>(i) * sc.my + j) * sc.mz + k] != 0;
+  return false;
+}
+
+// 8-corner geometry (ATen order x0y0z0, x0y0z1, x0y1z0, ... ; weight = (wz*wy)*wx; zero padding).
+struct Corner8 {
+  int64_t off[8];  // voxel index (x*Y+y)*Z+z, or -1 when padded
+  float w[8];
+};
+__device__ __forceinline__ Corner8 corner8(const SceneDev& sc, float px, float py, float pz) {
+  const Tri t = tri_setup(px, py, pz, sc.lo, sc.hi, sc.X, sc.Y, sc.Z);
+  Corner8 c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;
+    const int xi = t.x0 + dx, yi = t.y0 + dy, zi = t.z0 + dz;
+    const bool in = (xi >= 0) & (xi < sc.X) & (yi >= 0) & (yi < sc.Y) & (zi >= 0) & (zi < sc.Z);
+    c.off[k] = in ? (static_cast<int64_t>(xi) * sc.Y + yi) * sc.Z + zi : -1;
+    c.w[k] = fmul(fmul(dz ? t.wz1 : t.wz0, dy ? t.wy1 : t.wy0), dx ? t.wx1 : t.wx0);
+  }
+  return c;
+}
+
+// ---- ray_setup -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fused_count_kernel(const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d,
+                                                          SceneArgs a, int n_rays,
+                                                          float* __restrict__ t_min,
+                                                          int32_t* __restrict__ n_steps) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  if (a.ndc) { t_min[r] = 0.f; n_steps[r] = a.ndc_samples; return; }
+  const TMinMax t = slab_test(rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2], rays_d[3 * r],
+                              rays_d[3 * r + 1], rays_d[3 * r + 2], a.xyz_min, a.xyz_max, a.near,
+                              a.far);
+  t_min[r] = t.t_min;
+  n_steps[r] = static_cast<int32_t>(n_samples_of(t.t_min, t.t_max, a.stepdist));
+}
+
+// Single-CTA exclusive scan of int32 counts into ray_off[0..n] (ray_off[n] = total).
+__global__ void __launch_bounds__(1024) fused_scan_kernel(const int32_t* __restrict__ in, int n,
+                                                          int32_t* __restrict__ out) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  constexpr int kItems = 4;
+  for (int base = 0; base < n; base += 1024 * kItems) {
+    int32_t v[kItems];
+    int32_t local = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+      const int i = base + tid * kItems + k;
+      v[k] = (i < n) ? in[i] : 0;
+      local += v[k];
+    }
+    int32_t incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += up;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int32_t ws = warp_sums[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int32_t up = __shfl_up_sync(0xffffffffu, ws, off);
+        if (lane >= off) ws += up;
+      }
+      warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    int32_t run = carry_s + (wid ? warp_sums[wid - 1] : 0) + (incl - local);  // exclusive prefix
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) {
+      const int i = base + tid * kItems + k;
+      if (i < n) out[i] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = run;
+    __syncthreads();
+  }
+  if (tid == 0) out[n] = carry_s;
+}
+
+// ---- march_fwd -------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void gather_k0(const float* __restrict__ k0, const Corner8& cn,
+                                          float* __restrict__ out) {
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (cn.off[k] < 0) continue;
+    const float* __restrict__ v = k0 + cn.off[k] * C;
+    if (C % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(v) + q);
+        acc[4 * q + 0] = fma_(f.x, cn.w[k], acc[4 * q + 0]);
+        acc[4 * q + 1] = fma_(f.y, cn.w[k], acc[4 * q + 1]);
+        acc[4 * q + 2] = fma_(f.z, cn.w[k], acc[4 * q + 2]);
+        acc[4 * q + 3] = fma_(f.w, cn.w[k], acc[4 * q + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fma_(__ldg(v + c), cn.w[k], acc[c]);
+    }
+  }
+  if (C % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q)
+      reinterpret_cast<float4*>(out)[q] =
+          make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[c] = acc[c];
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) march_fwd_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
+    const float* __restrict__ density, const float* __restrict__ k0, int n_rays,
+    const float* __restrict__ t_min, const int32_t* __restrict__ n_steps,
+    const int32_t* __restrict__ ray_off, int64_t slot_cap, int64_t surv_cap,
+    float* __restrict__ slot_alpha, float* __restrict__ slot_T, float* __restrict__ slot_expd,
+    int32_t* __restrict__ slot_code, float* __restrict__ feat, int32_t* __restrict__ s_ray,
+    int32_t* __restrict__ s_slot, float* __restrict__ s_weight, float* __restrict__ alphainv_last,
+    int32_t* __restrict__ counters) {
+  const SceneDev sc = load_scene(a);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const bool use_thres = sc.thres > 0.f;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * wpb) {
+    const int n = n_steps[r];
+    const int64_t off = ray_off[r];
+    const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
+    double carry = 1.0;
+    float last_T = 1.f;
+    bool stopped = false;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < n;
+      const int64_t slot = off + i;
+      float px, py, pz;
+      sample_point(sc, g, i, px, py, pz);
+      bool live = valid && !stopped && !out_of_bbox(px, py, pz, sc.lo, sc.hi);  // lib/dvgo.py:444-447
+      live = live && occupancy(sc, px, py, pz);                                  // :469-473
+      float alpha = 0.f, e = 0.f;
+      Corner8 cn;
+      if (live) {
+        cn = corner8(sc, px, py, pz);
+        float dens = 0.f;  // :476 trilinear density (ATen accumulation order)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (cn.off[k] >= 0) dens = fma_(__ldg(density + cn.off[k]), cn.w[k], dens);
+        e = expf(fadd(dens, sc.act_shift));                     // render_utils_kernel.cu:366
+        alpha = fsub(1.f, powf(fadd(1.f, e), -sc.interval));    // :368
+        if (use_thres) live = alpha > sc.thres;                 // lib/dvgo.py:478-484
+      }
+      // transmittance: exclusive product of (1 - alpha + 1e-10) over the samples still alive
+      const double f = live ? ((1.0 - static_cast<double>(alpha)) + 1e-10) : 1.0;
+      double incl = f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl *= up;
+      }
+      double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0;
+      const float T_before = static_cast<float>(carry * excl);
+      const float T_after = static_cast<float>(carry * incl);
+      const bool hit = live && (static_cast<double>(T_after) < 1e-3);  // render_utils_kernel.cu:451
+      const unsigned hits = __ballot_sync(0xffffffffu, hit);
+      const int first = hits ? (__ffs(hits) - 1) : 32;
+      const bool in_scan = live && lane <= first;            // inside [i_start, i_end)
+      const float w = fmul(T_before, alpha);                  // :449
+      const bool surv = in_scan && (!use_thres || w > sc.thres);  // lib/dvgo.py:488-494
+      const unsigned smask = __ballot_sync(0xffffffffu, surv);
+      int idx4 = -1;
+      if (smask) {
+        int base4 = 0;
+        if (lane == 0) base4 = atomicAdd(counters, __popc(smask));
+        base4 = __shfl_sync(0xffffffffu, base4, 0);
+        if (surv) idx4 = base4 + __popc(smask & ((1u << lane) - 1u));
+      }
+      if (valid && slot < slot_cap) {
+        slot_code[slot] = surv ? idx4 : (in_scan ? -1 : -2);
+        if (in_scan) { slot_alpha[slot] = alpha; slot_T[slot] = T_before; slot_expd[slot] = e; }
+      } else if (valid) {
+        counters[1] = 1;  // capacity overflow (cannot happen with dvgo_fused_max_steps sizing)
+      }
+      if (surv) {
+        if (idx4 < surv_cap) {
+          s_ray[idx4] = r;
+          s_slot[idx4] = static_cast<int32_t>(slot);
+          s_weight[idx4] = w;
+          if (k0) gather_k0<C>(k0, cn, feat + static_cast<int64_t>(idx4) * C);  // lib/dvgo.py:509
+        } else {
+          counters[1] = 1;
+        }
+      }
+      if (hits) {
+        stopped = true;
+        last_T = __shfl_sync(0xffffffffu, T_after, first);
+      } else {
+        carry = carry * __shfl_sync(0xffffffffu, incl, 31);
+        last_T = static_cast<float>(carry);
+      }
+    }
+    if (lane == 0) alphainv_last[r] = last_T;  // render_utils_kernel.cu:457
+  }
+}
+
+// ---- march_bwd -------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void scatter_k0(float* __restrict__ gk0, const Corner8& cn,
+                                           const float* __restrict__ df) {
+  float d[C];
+  if (C % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(df) + q);
+      d[4 * q] = f.x; d[4 * q + 1] = f.y; d[4 * q + 2] = f.z; d[4 * q + 3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[c] = __ldg(df + c);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (cn.off[k] < 0) continue;
+    float* __restrict__ dst = gk0 + cn.off[k] * C;
+    const float w = cn.w[k];
+    if (C % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q) {
+        // one 16-byte vector reduction (red.global.add.v4.f32, sm_90+) instead of four scalar atomics
+        atomicAdd(reinterpret_cast<float4*>(dst) + q,
+                  make_float4(fmul(w, d[4 * q]), fmul(w, d[4 * q + 1]), fmul(w, d[4 * q + 2]),
+                              fmul(w, d[4 * q + 3])));
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) atomicAdd(dst + c, fmul(w, d[c]));
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) march_bwd_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a, int n_rays,
+    const float* __restrict__ t_min, const int32_t* __restrict__ n_steps,
+    const int32_t* __restrict__ ray_off, const float* __restrict__ slot_alpha,
+    const float* __restrict__ slot_T, const float* __restrict__ slot_expd,
+    const int32_t* __restrict__ slot_code, const float* __restrict__ d_feat,
+    const float* __restrict__ d_w, const float* __restrict__ alphainv_last,
+    const float* __restrict__ g_last, float* __restrict__ grad_density,
+    float* __restrict__ grad_k0) {
+  const SceneDev sc = load_scene(a);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * wpb) {
+    const int n = n_steps[r];
+    const int64_t off = ray_off[r];
+    const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
+    float back = fmul(g_last[r], alphainv_last[r]);  // render_utils_kernel.cu:525
+    // far to near; lane 0 = farthest sample of the chunk
+    for (int hi = n; hi > 0; hi -= 32) {
+      const int i = hi - 1 - lane;
+      const bool valid = i >= 0;
+      const int64_t slot = off + i;
+      const int code = valid ? slot_code[slot] : -2;
+      const bool in_scan = code >= -1;
+      float alpha = 0.f, T = 0.f, e = 0.f, gw = 0.f;
+      if (in_scan) {
+        alpha = slot_alpha[slot]; T = slot_T[slot]; e = slot_expd[slot];
+        if (code >= 0) gw = d_w[code];  // samples dropped by the weight mask carry dL/dw = 0
+      }
+      const float term = in_scan ? fmul(gw, fmul(T, alpha)) : 0.f;  // gw * weight, :528
+      float incl = term;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 0.f;
+      const float back_i = back + excl;
+      back += __shfl_sync(0xffffffffu, incl, 31);
+      if (!in_scan) continue;
+      // alpha2weight backward (:527) then raw2alpha backward (:404)
+      const float g_alpha = static_cast<float>(
+          static_cast<double>(fmul(gw, T)) -
+          static_cast<double>(back_i) / (static_cast<double>(fsub(1.f, alpha)) + 1e-10));
+      const double mm = fmin(static_cast<double>(e), 1e10);
+      const double pw = static_cast<double>(powf(fadd(1.f, e), fsub(-sc.interval, 1.f)));
+      const float g_dens = static_cast<float>(mm * pw * static_cast<double>(sc.interval) *
+                                              static_cast<double>(g_alpha));
+      float px, py, pz;
+      sample_point(sc, g, i, px, py, pz);
+      const Corner8 cn = corner8(sc, px, py, pz);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (cn.off[k] >= 0) atomicAdd(grad_density + cn.off[k], fmul(cn.w[k], g_dens));
+      if (code >= 0 && grad_k0) scatter_k0<C>(grad_k0, cn, d_feat + static_cast<int64_t>(code) * C);
+    }
+  }
+}
+
+static inline int ray_blocks(int n_rays, int wpb) {
+  const int64_t want = (static_cast<int64_t>(n_rays) + wpb - 1) / wpb;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 32;
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace dvgo
+
+using namespace dvgo;
+
+DVGO_API int dvgo_fused_max_steps(const dvgo_scene_t* s) {
+  if (!s) return DVGO_EINVAL;
+  if (s->ndc) return s->ndc_samples;
+  const float c = ceilf((s->far - s->near) / s->stepdist);
+  return c > 1.f ? static_cast<int>(c) : 1;
+}
+
+DVGO_API int dvgo_fused_ray_setup(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                                  int n_rays, float* t_min, int32_t* n_steps, int32_t* ray_off,
+                                  dvgo_stream_t stream) {
+  if (n_rays < 0 || !scene || !ray_off) return DVGO_EINVAL;
+  if (n_rays > 0 && (!rays_o || !rays_d || !t_min || !n_steps)) return DVGO_EINVAL;
+  cudaStream_t s = as_stream(stream);
+  if (n_rays > 0)
+    fused_count_kernel<<<blocks_for(n_rays, 256), 256, 0, s>>>(rays_o, rays_d, to_args(scene), n_rays,
+                                                               t_min, n_steps);
+  fused_scan_kernel<<<1, 1024, 0, s>>>(n_steps, n_rays, ray_off);
+  return launch_status(n_rays > 0 ? 2 : 1);
+}
+
+#define DVGO_DISPATCH_C(Cval, ...)                       \
+  switch (Cval) {                                        \
+    case 3: { constexpr int kC = 3; __VA_ARGS__; } break;   \
+    case 9: { constexpr int kC = 9; __VA_ARGS__; } break;   \
+    case 12: { constexpr int kC = 12; __VA_ARGS__; } break; \
+    default: return DVGO_EINVAL;                         \
+  }
+
+DVGO_API int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                                  const float* density, const float* k0_cl, int n_rays,
+                                  const float* t_min, const int32_t* n_steps, const int32_t* ray_off,
+                                  int64_t slot_cap, int64_t surv_cap, float* slot_alpha, float* slot_T,
+                                  float* slot_expd, int32_t* slot_code, float* feat, int32_t* s_ray,
+                                  int32_t* s_slot, float* s_weight, float* alphainv_last,
+                                  int32_t* counters, dvgo_stream_t stream) {
+  if (n_rays < 0 || !scene) return DVGO_EINVAL;
+  if (n_rays == 0) return 0;
+  if (!rays_o || !rays_d || !density || !t_min || !n_steps || !ray_off || !slot_alpha || !slot_T ||
+      !slot_expd || !slot_code || !s_ray || !s_slot || !s_weight || !alphainv_last || !counters ||
+      (k0_cl && !feat))
+    return DVGO_EINVAL;
+  const int wpb = 8;
+  DVGO_DISPATCH_C(scene->C, (march_fwd_kernel<kC><<<ray_blocks(n_rays, wpb), wpb * 32, 0,
+                                                    as_stream(stream)>>>(
+      rays_o, rays_d, to_args(scene), density, k0_cl, n_rays, t_min, n_steps, ray_off, slot_cap,
+      surv_cap, slot_alpha, slot_T, slot_expd, slot_code, feat, s_ray, s_slot, s_weight,
+      alphainv_last, counters)));
+  return launch_status();
+}
+
+DVGO_API int dvgo_fused_march_bwd(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                                  int n_rays, const float* t_min, const int32_t* n_steps,
+                                  const int32_t* ray_off, const float* slot_alpha, const float* slot_T,
+                                  const float* slot_expd, const int32_t* slot_code, const float* d_feat,
+                                  const float* d_w, const float* alphainv_last, const float* g_last,
+                                  float* grad_density, float* grad_k0_cl, dvgo_stream_t stream) {
+  if (n_rays < 0 || !scene) return DVGO_EINVAL;
+  if (n_rays == 0) return 0;
+  if (!rays_o || !rays_d || !t_min || !n_steps || !ray_off || !slot_alpha || !slot_T || !slot_expd ||
+      !slot_code || !d_w || !alphainv_last || !g_last || !grad_density || (grad_k0_cl && !d_feat))
+    return DVGO_EINVAL;
+  const int wpb = 8;
+  DVGO_DISPATCH_C(scene->C, (march_bwd_kernel<kC><<<ray_blocks(n_rays, wpb), wpb * 32, 0,
+                                                    as_stream(stream)>>>(
+      rays_o, rays_d, to_args(scene), n_rays, t_min, n_steps, ray_off, slot_alpha, slot_T, slot_expd,
+      slot_code, d_feat, d_w, alphainv_last, g_last, grad_density, grad_k0_cl)));
+  return launch_status();
+}

@@ -1,0 +1,226 @@
+// fused_sweep.cu -- ONE pass over each grid per step: total-variation gradient + (masked) Adam +
+// gradient re-zeroing, on the trainer's layouts (density [X,Y,Z], k0 channel-last [X,Y,Z,C]).
+//
+// Reference sequence (run.py:389-397): total_variation_add_grad (read p + 6 neighbours, RMW grad:
+// 12 B/elem of HBM) -> masked_adam_upd (read g,p,m,v, write p,m,v: 28 B/elem) -> next step's
+// zero_grad/backward re-materialise grad (4 B/elem) = 44 B/elem in 2 launches + allocator traffic.
+// Here: read p,g,m,v (16 B) + write p',m,v,g=0 (16 B) = 32 B/elem in one launch; the six TV
+// neighbours are L1/L2 hits (z +-1: same/adjacent line; y +-1: Z*C*4 B away; x +-1: Y*Z*C*4 B away,
+// re-used within ~2.5 MB of streaming, far below the 126 MB L2).
+//
+// Stencil-then-write hazard: TV must read the OLD neighbours (total_variation_kernel.cu:27-32), so
+// with TV on, new parameters go to a second buffer (ping-pong, no extra traffic); without TV the
+// update is in place.  Semantics kept from the reference: weights /6, wx unused and the x axis
+// uses wz (:31-32, :45-47), term order k-,k+,j-,j+,i-,i+, sparse TV gates on grad != 0 BEFORE the
+// add (:21), masked Adam gates on grad != 0 AFTER it (adam_upd_kernel.cu:35).
+#include "common.cuh"
+#include "../../include/dvgo_b200_fused.h"
+
+namespace dvgo {
+
+__device__ __forceinline__ float clamp1f(float v) { return fminf(fmaxf(v, -1.f), 1.f); }
+__device__ __forceinline__ float tvt(float w, float p, float pn) { return fmul(w, clamp1f(fsub(p, pn))); }
+
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float lrs,
+                                          float step_size, float beta1, float beta2, float eps) {
+  m = fma_(beta1, m, fmul(fsub(1.f, beta1), g));
+  v = fma_(beta2, v, fmul(fmul(fsub(1.f, beta2), g), g));
+  p = fsub(p, fdiv(fmul(fmul(step_size, lrs), m), fadd(sqrtf(v), eps)));
+}
+__device__ __forceinline__ void adam_elem_nolr(float& p, float g, float& m, float& v, float step_size,
+                                               float beta1, float beta2, float eps) {
+  m = fma_(beta1, m, fmul(fsub(1.f, beta1), g));
+  v = fma_(beta2, v, fmul(fmul(fsub(1.f, beta2), g), g));
+  p = fsub(p, fdiv(fmul(step_size, m), fadd(sqrtf(v), eps)));
+}
+
+// VEC = 4: C % 4 == 0, each thread owns one float4 = 4 channels of one voxel.
+// VEC = 1: generic (density: C == 1; C == 3 or 9 grids).
+template <int VEC, bool kTV>
+__global__ void __launch_bounds__(256) sweep_kernel(
+    const float* __restrict__ pin, float* __restrict__ pout, float* __restrict__ grad,
+    float* __restrict__ m_, float* __restrict__ v_, const float* __restrict__ perlr, int X, int Y,
+    int Z, int C, int tv_dense, float wy, float wz, int masked, float step_size, float beta1,
+    float beta2, float eps) {
+  const int64_t n_elem = static_cast<int64_t>(X) * Y * Z * C;
+  const int64_t n_work = n_elem / VEC;
+  const int64_t sz = C;                                // element stride of z +- 1
+  const int64_t sy = static_cast<int64_t>(Z) * C;      // y +- 1
+  const int64_t sx = static_cast<int64_t>(Y) * Z * C;  // x +- 1
+  for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < n_work;
+       q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e0 = q * VEC;
+    float p[VEC], g[VEC], pn[VEC];
+    if constexpr (VEC == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(pin + e0);
+      const float4 b = *reinterpret_cast<const float4*>(grad + e0);
+      p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;
+      g[0] = b.x; g[1] = b.y; g[2] = b.z; g[3] = b.w;
+    } else {
+      p[0] = pin[e0];
+      g[0] = grad[e0];
+    }
+    bool dirty = false;  // original gradient non-zero somewhere -> must be re-zeroed
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) dirty = dirty || (g[k] != 0.f);
+    if (kTV) {
+      bool any = tv_dense != 0;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) any = any || (g[k] != 0.f);
+      if (any) {
+        const int64_t vox = e0 / C;
+        const int z = static_cast<int>(vox % Z);
+        const int y = static_cast<int>((vox / Z) % Y);
+        const int x = static_cast<int>(vox / (static_cast<int64_t>(Z) * Y));
+        float add[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) add[k] = 0.f;
+        auto axis = [&](bool ok, int64_t stride, float w) {
+          if (ok) {
+            if constexpr (VEC == 4) {
+              const float4 nb = __ldg(reinterpret_cast<const float4*>(pin + e0 + stride));
+              pn[0] = nb.x; pn[1] = nb.y; pn[2] = nb.z; pn[3] = nb.w;
+            } else {
+              pn[0] = __ldg(pin + e0 + stride);
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) add[k] = fadd(add[k], tvt(w, p[k], pn[k]));
+          }
+        };
+        axis(z > 0, -sz, wz);
+        axis(z < Z - 1, sz, wz);
+        axis(y > 0, -sy, wy);
+        axis(y < Y - 1, sy, wy);
+        axis(x > 0, -sx, wz);      // reference quirk: the x axis uses wz
+        axis(x < X - 1, sx, wz);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          if (tv_dense || g[k] != 0.f) g[k] = fadd(g[k], add[k]);
+      }
+    }
+    bool upd = !masked;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) upd = upd || (g[k] != 0.f);
+    if (upd) {
+      float m[VEC], v[VEC], l[VEC];
+      if constexpr (VEC == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(m_ + e0);
+        const float4 b = *reinterpret_cast<const float4*>(v_ + e0);
+        m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
+        v[0] = b.x; v[1] = b.y; v[2] = b.z; v[3] = b.w;
+        if (perlr) {
+          const float4 c = __ldg(reinterpret_cast<const float4*>(perlr + e0));
+          l[0] = c.x; l[1] = c.y; l[2] = c.z; l[3] = c.w;
+        }
+      } else {
+        m[0] = m_[e0];
+        v[0] = v_[e0];
+        if (perlr) l[0] = __ldg(perlr + e0);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        if (masked && g[k] == 0.f) continue;  // adam_upd_kernel.cu:35
+        if (perlr) adam_elem(p[k], g[k], m[k], v[k], l[k], step_size, beta1, beta2, eps);
+        else adam_elem_nolr(p[k], g[k], m[k], v[k], step_size, beta1, beta2, eps);
+      }
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(m_ + e0) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(v_ + e0) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        m_[e0] = m[0];
+        v_[e0] = v[0];
+      }
+    }
+    // new parameters: always written when ping-ponging (pout != pin), only when changed in place
+    if (upd || pout != pin) {
+      if constexpr (VEC == 4) *reinterpret_cast<float4*>(pout + e0) = make_float4(p[0], p[1], p[2], p[3]);
+      else pout[e0] = p[0];
+    }
+    // re-zero the gradient accumulator for the next step (only where it was non-zero)
+    if (dirty) {
+      if constexpr (VEC == 4) *reinterpret_cast<float4*>(grad + e0) = make_float4(0.f, 0.f, 0.f, 0.f);
+      else grad[e0] = 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ncdhw_to_cl_kernel(const float* __restrict__ src,
+                                                          float* __restrict__ dst, int C, int64_t G) {
+  const int64_t n = G * C;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t vox = i / C;
+    const int c = static_cast<int>(i - vox * C);
+    dst[i] = src[c * G + vox];
+  }
+}
+
+__global__ void __launch_bounds__(256) cl_to_ncdhw_kernel(const float* __restrict__ src,
+                                                          float* __restrict__ dst, int C, int64_t G) {
+  const int64_t n = G * C;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i / G);
+    const int64_t vox = i - c * G;
+    dst[i] = src[vox * C + c];
+  }
+}
+
+static inline int sweep_grid(int64_t n, int threads) {
+  const int64_t want = (n + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 16;
+  return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace dvgo
+
+using namespace dvgo;
+
+DVGO_API int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float* exp_avg,
+                              float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C,
+                              int tv, int tv_dense, float wx, float wy, float wz, int masked, int step,
+                              float beta1, float beta2, float lr, float eps, dvgo_stream_t stream) {
+  (void)wx;
+  if (X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || step <= 0) return DVGO_EINVAL;
+  if (!param_in || !param_out || !grad || !exp_avg || !exp_avg_sq) return DVGO_EINVAL;
+  if (tv && param_in == param_out) return DVGO_EINVAL;  // TV needs the old neighbours
+  const float step_size = lr * sqrtf(1.f - powf(beta2, static_cast<float>(step))) /
+                          (1.f - powf(beta1, static_cast<float>(step)));  // adam_upd_kernel.cu:72
+  wy /= 6;  // total_variation_kernel.cu:45-47
+  wz /= 6;
+  const int64_t n = static_cast<int64_t>(X) * Y * Z * C;
+  const bool vec = (C % 4 == 0) && al16(param_in) && al16(param_out) && al16(grad) && al16(exp_avg) &&
+                   al16(exp_avg_sq) && (!perlr || al16(perlr));
+  cudaStream_t s = as_stream(stream);
+#define SWEEP_ARGS param_in, param_out, grad, exp_avg, exp_avg_sq, perlr, X, Y, Z, C, tv_dense, wy, wz, \
+                   masked, step_size, beta1, beta2, eps
+  if (vec) {
+    const int blocks = sweep_grid(n / 4, 256);
+    if (tv) sweep_kernel<4, true><<<blocks, 256, 0, s>>>(SWEEP_ARGS);
+    else sweep_kernel<4, false><<<blocks, 256, 0, s>>>(SWEEP_ARGS);
+  } else {
+    const int blocks = sweep_grid(n, 256);
+    if (tv) sweep_kernel<1, true><<<blocks, 256, 0, s>>>(SWEEP_ARGS);
+    else sweep_kernel<1, false><<<blocks, 256, 0, s>>>(SWEEP_ARGS);
+  }
+#undef SWEEP_ARGS
+  return launch_status();
+}
+
+DVGO_API int dvgo_grid_ncdhw_to_cl(const float* src, float* dst, int C, int64_t G,
+                                   dvgo_stream_t stream) {
+  if (C <= 0 || G < 0 || !src || !dst) return DVGO_EINVAL;
+  if (G == 0) return 0;
+  ncdhw_to_cl_kernel<<<sweep_grid(G * C, 256), 256, 0, as_stream(stream)>>>(src, dst, C, G);
+  return launch_status();
+}
+
+DVGO_API int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G,
+                                   dvgo_stream_t stream) {
+  if (C <= 0 || G < 0 || !src || !dst) return DVGO_EINVAL;
+  if (G == 0) return 0;
+  cl_to_ncdhw_kernel<<<sweep_grid(G * C, 256), 256, 0, as_stream(stream)>>>(src, dst, C, G);
+  return launch_status();
+}

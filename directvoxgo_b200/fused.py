@@ -1,0 +1,321 @@
+"""The fused B200 path: FusedTrainer (one training iteration of run.py:372-397) and FusedRenderer
+(one chunk of run.py:91-98), built on include/dvgo_b200_fused.h.
+
+Per step the trainer launches ~12 kernels and never synchronises with the host (the reference's
+forward alone does ~120 launches and 17 syncs):
+
+    ray_setup(2) -> march_fwd -> rgb (rgbnet) -> composite -> ray_finish -> sample_grad
+      -> rgbnet backward -> march_bwd -> [NCCL all-reduce of grid grads when ray-sharded]
+      -> sweep(density) -> sweep(k0) -> Adam(rgbnet)
+
+State lives in the trainer's own buffers: density [X,Y,Z], k0 channel-last [X,Y,Z,C] (two copies,
+ping-ponged by the TV sweep), persistent zero-initialised gradient accumulators (re-zeroed inside
+the sweep), Adam moments in the same layouts.  `sync_to_model()` converts back to the reference's
+[1,C,X,Y,Z] parameters so checkpoints / state_dicts stay interchangeable (run.py:420-437).
+
+rgbnet modes
+    'torch'  the MLP runs as plain cuBLAS fp32 GEMMs through torch autograd (exact-fp32 parity mode;
+             needs one host read of the survivor count per step)
+    'tc'     hand-written tcgen05 (TF32 tensor-core, fp32 accumulate) forward+backward kernels with
+             in-TMEM weight-gradient accumulation; no host sync   [fused_mlp.cu]
+"""
+import math
+
+import torch
+
+from . import adam_upd_cuda, ext
+
+
+def _scene_of(model, rk, ndc=False, ndc_samples=0):
+    X, Y, Z = (int(s) for s in model.density.shape[2:])
+    C = int(model.k0.shape[1])
+    mc = model.mask_cache
+    stepdist = 0.0 if ndc else float(rk["stepsize"] * model.voxel_size)
+    return ext.Scene(X, Y, Z, C, model.xyz_min.contiguous(), model.xyz_max.contiguous(),
+                     mc.mask if mc is not None else None,
+                     mc.xyz2ijk_scale if mc is not None else None,
+                     mc.xyz2ijk_shift if mc is not None else None,
+                     float(rk["near"]), float(rk["far"]), stepdist, float(model.act_shift),
+                     float(rk["stepsize"] * model.voxel_size_ratio), float(model.fast_color_thres),
+                     bool(ndc), int(ndc_samples))
+
+
+class _Workspace:
+    """Preallocated per-call buffers for N rays (capacities from the scene's max steps per ray)."""
+
+    def __init__(self, scene, n_rays, C, device, train):
+        f32 = dict(dtype=torch.float32, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        cap = n_rays * scene.max_steps()
+        self.n_rays, self.cap = n_rays, cap
+        self.t_min = torch.empty(n_rays, **f32)
+        self.n_steps = torch.empty(n_rays, **i32)
+        self.ray_off = torch.empty(n_rays + 1, **i32)
+        self.slot_alpha = torch.empty(cap, **f32)
+        self.slot_T = torch.empty(cap, **f32)
+        self.slot_expd = torch.empty(cap, **f32)
+        self.slot_code = torch.empty(cap, **i32)
+        self.feat = torch.empty(cap, C, **f32)
+        self.s_ray = torch.empty(cap, **i32)
+        self.s_slot = torch.empty(cap, **i32)
+        self.s_weight = torch.empty(cap, **f32)
+        self.rgb = torch.empty(cap, 3, **f32)
+        self.alphainv_last = torch.empty(n_rays, **f32)
+        # one zero-able block: counters(2) | loss(2) | rgb_acc(3N) | depth_acc(N)
+        self.zblock = torch.zeros(4 + 4 * n_rays, **f32)
+        self.counters = self.zblock[0:2].view(torch.int32)
+        self.loss_acc = self.zblock[2:4]
+        self.rgb_acc = self.zblock[4:4 + 3 * n_rays].view(n_rays, 3)
+        self.depth_acc = self.zblock[4 + 3 * n_rays:4 + 4 * n_rays]
+        if train:
+            self.G = torch.empty(n_rays, 3, **f32)
+            self.g_last = torch.empty(n_rays, **f32)
+            self.d_rgb = torch.empty(cap, 3, **f32)
+            self.d_w = torch.empty(cap, **f32)
+            self.d_feat = torch.empty(cap, C, **f32)
+
+
+def view_embedding(viewdirs, viewfreq):
+    """[N, 3 + 6*len(viewfreq)] = cat(viewdirs, sin(v*f), cos(v*f)) (lib/dvgo.py:524-525)."""
+    emb = (viewdirs.unsqueeze(-1) * viewfreq).flatten(-2)
+    return torch.cat([viewdirs, emb.sin(), emb.cos()], -1)
+
+
+class _FusedBase:
+    def __init__(self, model, render_kwargs, mlp="auto"):
+        self.model = model
+        self.rk = dict(render_kwargs)
+        self.device = model.density.device
+        self.ndc = hasattr(model, "mpi_depth")
+        ndc_samples = int((model.mpi_depth - 1) / self.rk["stepsize"]) + 1 if self.ndc else 0
+        self.scene = _scene_of(model, self.rk, self.ndc, ndc_samples)
+        self.X, self.Y, self.Z = (int(s) for s in model.density.shape[2:])
+        self.C = int(model.k0.shape[1])
+        if mlp == "auto":
+            mlp = "tc" if (model.rgbnet is not None and hasattr(ext, "mlp_fwd")) else "torch"
+        if mlp == "tc" and not hasattr(ext, "mlp_fwd"):
+            raise ImportError("tensor-core rgbnet kernels are not built")
+        self.mlp_mode = mlp
+        if model.rgbnet is not None and not getattr(model, "rgbnet_direct", True):
+            if mlp == "tc":
+                raise NotImplementedError("tc rgbnet implements rgbnet_direct=True (the configs' default)")
+        self.density = model.density.detach().reshape(self.X, self.Y, self.Z).contiguous().clone()
+        self.k0 = ext.ncdhw_to_cl(model.k0.detach().contiguous())
+        self._ws = {}
+
+    def _workspace(self, n_rays, train):
+        key = (n_rays, train)
+        if key not in self._ws:
+            self._ws[key] = _Workspace(self.scene, n_rays, self.C, self.device, train)
+        return self._ws[key]
+
+    def _march(self, ws, rays_o, rays_d):
+        ext.zero_(ws.zblock)
+        ext.ray_setup(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off)
+        ext.march_fwd(self.scene, rays_o, rays_d, self.density, self.k0, ws.t_min, ws.n_steps, ws.ray_off,
+                      ws.slot_alpha, ws.slot_T, ws.slot_expd, ws.slot_code, ws.feat, ws.s_ray, ws.s_slot,
+                      ws.s_weight, ws.alphainv_last, ws.counters)
+
+    def _rgb_torch(self, ws, viewdirs, m4, grad):
+        """rgbnet through torch/cuBLAS fp32 on the first m4 survivors; returns (rgb, feat leaf)."""
+        model = self.model
+        feat = ws.feat[:m4].detach()
+        if grad:
+            feat.requires_grad_(True)
+        pe = view_embedding(viewdirs, model.viewfreq)[ws.s_ray[:m4].long()]
+        if getattr(model, "rgbnet_direct", True):
+            rgb = torch.sigmoid(model.rgbnet(torch.cat([feat, pe], -1)))
+        else:
+            rgb = torch.sigmoid(model.rgbnet(torch.cat([feat[:, 3:], pe], -1)) + feat[:, :3])
+        return rgb, feat
+
+    @torch.no_grad()
+    def sync_to_model(self):
+        self.model.density.data.copy_(self.density.reshape(self.model.density.shape))
+        self.model.k0.data.copy_(ext.cl_to_ncdhw(self.k0))
+        return self.model
+
+
+class FusedRenderer(_FusedBase):
+    """Forward-only rendering of a chunk of rays: rgb_marched [N,3], depth [N], alphainv_last [N]
+    (the keys run.py:89,98-99 keeps)."""
+
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, viewdirs, render_depth=True):
+        n = rays_o.shape[0]
+        ws = self._workspace(n, False)
+        self._march(ws, rays_o.contiguous(), rays_d.contiguous())
+        if self.model.rgbnet is None:
+            ext.rgb_direct(ws.feat, ws.counters, ws.rgb)
+        elif self.mlp_mode == "tc":
+            self._tc_forward(ws, viewdirs)
+        else:
+            m4 = int(ws.counters[0].item())
+            if m4:
+                rgb, _ = self._rgb_torch(ws, viewdirs, m4, False)
+                ws.rgb[:m4].copy_(rgb)
+        ext.composite(ws.rgb, ws.s_weight, ws.s_ray, ws.s_slot, ws.ray_off, ws.counters, ws.rgb_acc,
+                      ws.depth_acc if render_depth else None)
+        ext.ray_finish(ws.rgb_acc, ws.alphainv_last, None, float(self.rk["bg"]), n, n, 1.0, 0.0, None, None, None)
+        out = {"rgb_marched": ws.rgb_acc.clone(), "alphainv_last": ws.alphainv_last.clone()}
+        if render_depth:
+            out["depth"] = ws.depth_acc.clone()
+        return out
+
+    def _tc_forward(self, ws, viewdirs):
+        from .fused_mlp import TensorCoreMLP
+        if not hasattr(self, "_tc"):
+            self._tc = TensorCoreMLP(self.model.rgbnet, self.device)
+        pe = view_embedding(viewdirs, self.model.viewfreq).contiguous()
+        self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
+
+
+class FusedTrainer(_FusedBase):
+    def __init__(self, model, cfg_train, render_kwargs, world_size=1, dist_group=None, mlp="auto",
+                 betas=(0.9, 0.99), eps=1e-8):
+        super().__init__(model, render_kwargs, mlp)
+        self.cfg = dict(cfg_train)
+        self.world_size = world_size
+        self.dist_group = dist_group
+        self.betas, self.eps = betas, eps
+        self.global_step = 0
+        self.opt_step = 0
+        z = torch.zeros_like
+        self.density_next = torch.empty_like(self.density)
+        self.k0_next = torch.empty_like(self.k0)
+        self.g_density, self.m_density, self.v_density = z(self.density), z(self.density), z(self.density)
+        self.g_k0, self.m_k0, self.v_k0 = z(self.k0), z(self.k0), z(self.k0)
+        self.per_lr = None
+        self.lr = {k: float(self.cfg.get("lrate_" + k, 0.0)) for k in ("density", "k0", "rgbnet")}
+        decay_steps = self.cfg.get("lrate_decay", 20) * 1000
+        self.decay = 0.1 ** (1.0 / decay_steps)
+        skip = self.cfg.get("skip_zero_grad_fields", []) or []
+        self.masked = {k: (k in skip) for k in ("density", "k0")}
+        self.rgbnet_state = {}
+        if model.rgbnet is not None and self.mlp_mode == "tc":
+            from .fused_mlp import TensorCoreMLP
+            self._tc = TensorCoreMLP(model.rgbnet, self.device, train=True)
+
+    def set_pervoxel_lr(self, count):
+        """View-count learning-rate table for the density grid (lib/masked_adam.py:35-37)."""
+        self.per_lr = (count.float() / count.max()).reshape(self.X, self.Y, self.Z).contiguous()
+
+    # -- the step -----------------------------------------------------------------------------------
+    def step(self, rays_o, rays_d, viewdirs, target):
+        cfg, model = self.cfg, self.model
+        n = rays_o.shape[0]
+        n_global = n * self.world_size
+        self.global_step += 1
+        ws = self._workspace(n, True)
+        rays_o, rays_d, target = rays_o.contiguous(), rays_d.contiguous(), target.contiguous()
+        self._march(ws, rays_o, rays_d)
+
+        w_main = float(cfg.get("weight_main", 1.0))
+        w_ent = float(cfg.get("weight_entropy_last", 0.0))
+        w_per = float(cfg.get("weight_rgbper", 0.0))
+        bg = float(self.rk["bg"])
+
+        def after_rgb():
+            ext.composite(ws.rgb, ws.s_weight, ws.s_ray, ws.s_slot, ws.ray_off, ws.counters, ws.rgb_acc, None)
+            ext.ray_finish(ws.rgb_acc, ws.alphainv_last, target, bg, n, n_global, w_main, w_ent, ws.G, ws.g_last,
+                           ws.loss_acc)
+            ext.sample_grad(ws.rgb, ws.s_weight, ws.s_ray, ws.G, target, ws.counters, n_global, w_per, ws.d_rgb,
+                            ws.d_w, ws.loss_acc)
+
+        if model.rgbnet is None:
+            ext.rgb_direct(ws.feat, ws.counters, ws.rgb)
+            after_rgb()
+            ext.rgb_direct_bwd(ws.rgb, ws.d_rgb, ws.counters, ws.d_feat)
+        elif self.mlp_mode == "tc":
+            pe = view_embedding(viewdirs, model.viewfreq).contiguous()
+            self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
+            after_rgb()
+            self._tc.backward(ws.feat, ws.s_ray, pe, ws.counters, ws.d_rgb, ws.d_feat)
+        else:
+            m4 = int(ws.counters[0].item())  # parity mode: one host read of the survivor count
+            for p in model.rgbnet.parameters():
+                p.grad = None
+            if m4:
+                rgb, feat = self._rgb_torch(ws, viewdirs, m4, True)
+                ws.rgb[:m4].copy_(rgb.detach())
+            after_rgb()
+            if m4:
+                rgb.backward(ws.d_rgb[:m4])
+                ws.d_feat[:m4].copy_(feat.grad)
+
+        ext.march_bwd(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T,
+                      ws.slot_expd, ws.slot_code, ws.d_feat, ws.d_w, ws.alphainv_last, ws.g_last, self.g_density,
+                      self.g_k0)
+        if self.world_size > 1:
+            self._allreduce()
+        self._optimise(n_global)
+        return ws.loss_acc[0].clone()
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.g_density, group=self.dist_group)
+        dist.all_reduce(self.g_k0, group=self.dist_group)
+        if self.model.rgbnet is not None:
+            if self.mlp_mode == "tc":
+                dist.all_reduce(self._tc.grad_flat, group=self.dist_group)
+            else:
+                for p in self.model.rgbnet.parameters():
+                    if p.grad is not None:
+                        dist.all_reduce(p.grad, group=self.dist_group)
+
+    def _tv_now(self):
+        cfg, gs = self.cfg, self.global_step
+        if "tv_before" in cfg or "tv_after" in cfg:  # run.py:389 schedule
+            on = gs < cfg.get("tv_before", 0) and gs > cfg.get("tv_after", 0) and gs % cfg.get("tv_every", 1) == 0
+            dense = gs < cfg.get("tv_dense_before", 0)
+        else:
+            on, dense = True, bool(cfg.get("tv_dense", True))
+        return on, dense
+
+    def _optimise(self, n_global):
+        cfg = self.cfg
+        self.opt_step += 1
+        b1, b2 = self.betas
+        tv_on, tv_dense = self._tv_now()
+        wmax = float(max(self.X, self.Y, self.Z))
+        if self.ndc:  # lib/dmpigo.py:147-157 anisotropic weights
+            wxy_s, wz_s = float(max(self.X, self.Y)) / 128, float(self.Z) / 128
+        for name, C in (("density", 1), ("k0", self.C)):
+            lr = self.lr[name]
+            if lr <= 0:
+                continue
+            wt = float(cfg.get("weight_tv_" + name, 0.0))
+            tv = tv_on and wt > 0
+            if self.ndc:
+                wx = wy = wt / n_global * wxy_s
+                wz = wt / n_global * wz_s
+            else:
+                wx = wy = wz = wt / n_global * wmax / 128  # lib/dvgo.py:297-305, run.py:392
+            cur = getattr(self, name)
+            nxt = getattr(self, name + "_next") if tv else cur
+            per_lr = self.per_lr if (name == "density" and self.per_lr is not None) else None
+            masked = self.masked[name] and per_lr is None  # dispatch of lib/masked_adam.py:60-71
+            ext.sweep(cur, nxt, getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
+                      per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, self.opt_step,
+                      b1, b2, lr, self.eps)
+            if tv:
+                setattr(self, name, nxt)
+                setattr(self, name + "_next", cur)
+        if self.model.rgbnet is not None and self.lr["rgbnet"] > 0:
+            if self.mlp_mode == "tc":
+                self._tc.adam_step(self.opt_step, b1, b2, self.lr["rgbnet"], self.eps)
+            else:
+                for p in self.model.rgbnet.parameters():
+                    if p.grad is None:
+                        continue
+                    st = self.rgbnet_state.setdefault(p, {"exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)})
+                    adam_upd_cuda.adam_upd(p.data, p.grad, st["exp_avg"], st["exp_avg_sq"], self.opt_step, b1, b2,
+                                           self.lr["rgbnet"], self.eps)
+        for k in self.lr:  # run.py:401-406
+            self.lr[k] *= self.decay
+
+    @torch.no_grad()
+    def sync_to_model(self):
+        if self.model.rgbnet is not None and self.mlp_mode == "tc":
+            self._tc.sync_to_module(self.model.rgbnet)
+        return super().sync_to_model()

@@ -1,0 +1,155 @@
+/*
+ * dvgo_b200_fused.h -- C ABI of the FUSED B200 path of libdvgo_b200.so.
+ *
+ * The op-by-op entry points of dvgo_b200.h reproduce the reference's extension surface one call at
+ * a time.  The entry points here implement the same mathematics as the model-level hot path
+ *     DirectVoxGO.forward            lib/dvgo.py:450-577   (sample_ray :425-448, mask cascade :469-494,
+ *                                    grid_sampler :312-328, compositing :554-576)
+ *     loss                           run.py:377-386
+ *     backward of all of the above   (autograd in the reference)
+ *     TV + MaskedAdam                run.py:389-397, lib/cuda/total_variation_kernel.cu:13-67,
+ *                                    lib/cuda/adam_upd_kernel.cu:8-58
+ * in a handful of kernels with no host synchronisation and no boolean-mask compaction passes:
+ *
+ *   ray_setup     per-ray slab test + step count + exclusive scan -> slot offsets (M0 layout)
+ *   march_fwd     ONE WARP PER RAY: points, bbox + occupancy cull, density trilinear, alpha, alpha
+ *                 threshold, shuffle-scan transmittance with early stop, weight threshold, k0 trilinear
+ *                 (channel-last grid: one corner = C contiguous floats), compacted survivor stream
+ *   rgb           rgbnet on the survivor stream (tcgen05 kernel, fused_mlp.cu) or sigmoid(k0)
+ *   composite     segmented (per-ray) sums of w*rgb and w*step
+ *   ray_loss      per-ray loss terms and dL/d(rgb_marched), dL/d(alphainv_last)
+ *   sample_grad   per-survivor dL/d(rgb), dL/d(weight)
+ *   march_bwd     ONE WARP PER RAY, far to near: alpha2weight + raw2alpha backward, trilinear scatter
+ *                 of density and k0 gradients
+ *   sweep         TV gradient + (masked) Adam + gradient re-zeroing in one pass over each grid
+ *
+ * Data layout in HBM
+ *   density          [X,Y,Z] fp32          (identical to the reference's [1,1,X,Y,Z])
+ *   k0 (channel-last)[X,Y,Z,C] fp32        (the reference keeps [1,C,X,Y,Z]; convert with
+ *                                           dvgo_grid_ncdhw_to_cl / dvgo_grid_cl_to_ncdhw at the
+ *                                           state_dict boundary)
+ *   "slot" arrays    indexed by s = ray_off[r] + step, s < M0 = sum of N_steps: alpha, T, exp_d, code
+ *                    code: >= 0 index into the survivor stream; -1 in the transmittance scan but below
+ *                    the weight threshold; -2 culled (outside bbox / free space / alpha threshold /
+ *                    after the early stop)
+ *   survivor stream  compacted, warp-chunk order: feat [M4,C], ray [M4], slot [M4], weight [M4]
+ *
+ * All pointers are device pointers; conventions as in dvgo_b200.h.
+ */
+#ifndef DVGO_B200_FUSED_H_
+#define DVGO_B200_FUSED_H_
+
+#include <stdint.h>
+
+#include "dvgo_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Scene + render constants shared by the fused kernels (host struct, device pointers inside). */
+typedef struct dvgo_scene {
+  int X, Y, Z;               /* density / k0 grid size */
+  int C;                     /* k0 channels (3, 9 or 12) */
+  const float* xyz_min;      /* [3] */
+  const float* xyz_max;      /* [3] */
+  const uint8_t* mask;       /* occupancy grid [mx,my,mz] bool (lib/dvgo.py:583-613) */
+  int mx, my, mz;
+  const float* mask_scale;   /* [3] xyz2ijk_scale */
+  const float* mask_shift;   /* [3] xyz2ijk_shift */
+  float near, far;           /* render_kwargs near / far */
+  float stepdist;            /* stepsize * voxel_size (lib/dvgo.py:439) */
+  float act_shift;           /* density bias (lib/dvgo.py:61) */
+  float interval;            /* stepsize * voxel_size_ratio (lib/dvgo.py:466) */
+  float fast_color_thres;    /* alpha / weight threshold (lib/dvgo.py:478,488); 0 disables both masks */
+  int ndc;                   /* 0: sample_pts_on_rays sampler; 1: NDC fixed-count sampler (dmpigo) */
+  int ndc_samples;           /* N_samples of the NDC sampler (lib/dmpigo.py:188) */
+} dvgo_scene_t;
+
+/* Upper bound of samples per ray: ceil((far-near)/stepdist), at least 1 (t is clamped to [near,far],
+ * render_utils_kernel.cu:32-33,47); ndc: ndc_samples.  Host-side helper for sizing the workspace. */
+int dvgo_fused_max_steps(const dvgo_scene_t* scene);
+
+/* ray_setup: t_min [N], n_steps [N] (int32), ray_off [N+1] (int32 exclusive scan; ray_off[N] = M0).
+ * Replaces infer_t_minmax + infer_n_samples + cumsum + the .item() sync of sample_pts_on_rays
+ * (render_utils_kernel.cu:190-213). */
+int dvgo_fused_ray_setup(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                         int n_rays, float* t_min, int32_t* n_steps, int32_t* ray_off,
+                         dvgo_stream_t stream);
+
+/* march_fwd.  Slot arrays [slot_cap], survivor arrays [surv_cap] (feat [surv_cap, C]); per ray
+ * alphainv_last [N]; counters[0] = number of survivors M4 (must be zeroed by the caller, e.g. with
+ * dvgo_fused_zero), counters[1] = overflow flag (set if a capacity was too small).
+ * want_k0 = 0 skips the k0 gather (render of alpha only). */
+int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                         const float* density, const float* k0_cl, int n_rays, const float* t_min,
+                         const int32_t* n_steps, const int32_t* ray_off, int64_t slot_cap,
+                         int64_t surv_cap, float* slot_alpha, float* slot_T, float* slot_expd,
+                         int32_t* slot_code, float* feat, int32_t* s_ray, int32_t* s_slot,
+                         float* s_weight, float* alphainv_last, int32_t* counters,
+                         dvgo_stream_t stream);
+
+/* rgb = sigmoid(feat) for models without rgbnet (lib/dvgo.py:512-514); rgb [M4,3], C must be 3. */
+int dvgo_fused_rgb_direct(const float* feat, const int32_t* counters, int64_t surv_cap, float* rgb,
+                          dvgo_stream_t stream);
+/* backward of the above: d_feat = d_rgb * rgb * (1 - rgb). */
+int dvgo_fused_rgb_direct_bwd(const float* rgb, const float* d_rgb, const int32_t* counters,
+                              int64_t surv_cap, float* d_feat, dvgo_stream_t stream);
+
+/* composite: rgb_acc[ray] += w*rgb (3), depth_acc[ray] += w*step (lib/dvgo.py:554-558,571-575).
+ * rgb_acc [N,3], depth_acc [N] must be zeroed by the caller; depth_acc may be NULL. */
+int dvgo_fused_composite(const float* rgb, const float* s_weight, const int32_t* s_ray,
+                         const int32_t* s_slot, const int32_t* ray_off, const int32_t* counters,
+                         int64_t surv_cap, float* rgb_acc, float* depth_acc, dvgo_stream_t stream);
+
+/* ray_finish: rgb_marched = rgb_acc + alphainv_last*bg (lib/dvgo.py:559) in place in rgb_acc.
+ * With target != NULL also the training loss pieces of run.py:377-382:
+ *   G [N,3]       = dL/d rgb_marched = weight_main * 2 (rgb_marched - target) / (3 n_global)
+ *   g_last [N]    = dL/d alphainv_last = bg * sum_c G + weight_entropy_last * dEntropy/dp / n_global
+ *   loss_acc[0]  += weight_main * mse  + weight_entropy_last * entropy   (this rank's share)
+ * n_global = number of rays in the GLOBAL batch (ray-sharded data parallel divides by it). */
+int dvgo_fused_ray_finish(float* rgb_acc, const float* alphainv_last, const float* target, float bg,
+                          int n_rays, int n_global, float weight_main, float weight_entropy_last,
+                          float* G, float* g_last, float* loss_acc, dvgo_stream_t stream);
+
+/* sample_grad: per survivor i of ray r (run.py:383-386 and SURVEY.md appendix C):
+ *   d_rgb[i] = w_i*G[r] + weight_rgbper * 2 w_i (rgb_i - target[r]) / n_global
+ *   d_w[i]   = sum_c G[r,c]*rgb_i,c                       (weights are detached in the rgbper term)
+ *   loss_acc[0] += weight_rgbper * w_i * |rgb_i - target[r]|^2 / n_global */
+int dvgo_fused_sample_grad(const float* rgb, const float* s_weight, const int32_t* s_ray,
+                           const float* G, const float* target, const int32_t* counters,
+                           int64_t surv_cap, int n_global, float weight_rgbper, float* d_rgb,
+                           float* d_w, float* loss_acc, dvgo_stream_t stream);
+
+/* march_bwd: accumulates into grad_density [X,Y,Z] and grad_k0_cl [X,Y,Z,C] (fp32 atomics).
+ * d_feat [M4,C] = dL/d(k0 features), d_w [M4] = dL/d(weights), g_last [N] = dL/d(alphainv_last). */
+int dvgo_fused_march_bwd(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                         int n_rays, const float* t_min, const int32_t* n_steps,
+                         const int32_t* ray_off, const float* slot_alpha, const float* slot_T,
+                         const float* slot_expd, const int32_t* slot_code, const float* d_feat,
+                         const float* d_w, const float* alphainv_last, const float* g_last,
+                         float* grad_density, float* grad_k0_cl, dvgo_stream_t stream);
+
+/* sweep: for every element  g = grad; if (tv && (tv_dense || g != 0)) g += TV(param_in);
+ *        if (!masked || g != 0) Adam(param, g, m, v);  grad = 0.
+ * `param_in` and `param_out` may alias ONLY when tv == 0 (TV reads neighbours of the old values, so
+ * with TV the new parameters go to a second buffer and the caller swaps -- no extra HBM traffic).
+ * layout: channels = C innermost for k0 (pass C), 1 for density.  wy/wz as in total_variation_add_grad
+ * (the caller passes the un-divided weights; /6 and the wx->wz quirk are applied inside).
+ * perlr (may be NULL): per-element learning-rate scale (adam_upd_with_perlr). */
+int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float* exp_avg,
+                     float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C, int tv,
+                     int tv_dense, float wx, float wy, float wz, int masked, int step, float beta1,
+                     float beta2, float lr, float eps, dvgo_stream_t stream);
+
+/* Layout converters at the state_dict boundary: [C,X,Y,Z] <-> [X,Y,Z,C]. */
+int dvgo_grid_ncdhw_to_cl(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);
+int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);
+
+/* Zero `n` 4-byte words (counters, accumulators) on the stream. */
+int dvgo_fused_zero(void* ptr, int64_t n_words, dvgo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVGO_B200_FUSED_H_ */

@@ -1,0 +1,206 @@
+"""GPU parity tests of the FUSED path (include/dvgo_b200_fused.h) against the CPU oracle model, the
+golden outputs of the reference's own Python, and our own op-by-op path (itself parity-green
+against the reference's CUDA kernels)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import rel_to_max, to_np, ulp_diff
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _fine_model(grid, seed=1, dens_scale=3.0, mask_p=0.3):
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.dvgo import DirectVoxGO
+    lo, hi = syn.fine_bbox()
+    kw = dict(syn.FINE_MODEL, num_voxels=grid ** 3, num_voxels_base=grid ** 3)
+    torch.manual_seed(0)
+    m = DirectVoxGO(lo, hi, **kw)
+    syn.randomize_grids_(m, seed)
+    with torch.no_grad():
+        m.density.mul_(dens_scale)
+        if mask_p > 0:
+            m.mask_cache.mask.copy_(torch.rand(m.mask_cache.mask.shape) > mask_p)
+    return m
+
+
+def test_layout_converters_roundtrip():
+    from directvoxgo_b200 import ext
+    g = torch.randn(1, 12, 9, 7, 5, device=DEV)
+    cl = ext.ncdhw_to_cl(g)
+    assert cl.shape == (9, 7, 5, 12)
+    assert torch.equal(cl, g[0].permute(1, 2, 3, 0).contiguous())
+    assert torch.equal(ext.cl_to_ncdhw(cl), g)
+
+
+@pytest.mark.parametrize("C,tv,tv_dense,masked,perlr", [
+    (12, True, True, True, False), (12, True, False, True, False), (12, False, False, True, False),
+    (12, False, False, False, False), (1, True, True, True, False), (1, False, False, False, True),
+    (3, True, True, False, False), (9, True, False, True, False)])
+def test_sweep_matches_oracle_tv_plus_adam(C, tv, tv_dense, masked, perlr):
+    """The fused TV+Adam sweep on channel-last buffers == total_variation_add_grad followed by the
+    matching Adam kernel on the reference's [1,C,X,Y,Z] layout (oracle), 3 consecutive steps."""
+    from directvoxgo_b200 import ext
+    from oracle import oracle as orc
+    X, Y, Z = 11, 9, 13
+    g = torch.Generator().manual_seed(C * 7 + tv)
+    p = torch.randn(1, C, X, Y, Z, generator=g) * 1.5
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    pl = torch.rand(1, C, X, Y, Z, generator=g) if perlr else None
+    to_cl = lambda t: t[0].permute(1, 2, 3, 0).contiguous().to(DEV)
+    pc, pn, mc, vc = to_cl(p), torch.empty_like(to_cl(p)), to_cl(m), to_cl(v)
+    plc = to_cl(pl) if perlr else None
+    wx, wy, wz = 0.3, 0.7, 1.3
+    for step in (1, 2, 3):
+        grad = torch.randn(1, C, X, Y, Z, generator=g)
+        grad[torch.rand(grad.shape, generator=g) < 0.5] = 0
+        gc = to_cl(grad)
+        # oracle
+        if tv:
+            orc.total_variation_add_grad(p, grad, wx, wy, wz, tv_dense)
+        if perlr:
+            orc.adam_upd_with_perlr(p, grad, m, v, pl, step, 0.9, 0.99, 0.1, 1e-8)
+        elif masked:
+            orc.masked_adam_upd(p, grad, m, v, step, 0.9, 0.99, 0.1, 1e-8)
+        else:
+            orc.adam_upd(p, grad, m, v, step, 0.9, 0.99, 0.1, 1e-8)
+        # product
+        out = pn if tv else pc
+        ext.sweep(pc, out, gc, mc, vc, plc, X, Y, Z, C, tv, tv_dense, wx, wy, wz, masked and not perlr, step,
+                  0.9, 0.99, 0.1, 1e-8)
+        if tv:
+            pc, pn = pn, pc
+        assert torch.count_nonzero(gc) == 0            # gradient accumulator re-zeroed
+        back = lambda t: t.permute(3, 0, 1, 2)[None].cpu()
+        assert ulp_diff(to_np(back(mc)), to_np(m)).max() <= 1
+        assert ulp_diff(to_np(back(vc)), to_np(v)).max() <= 1
+        np.testing.assert_allclose(to_np(back(pc)), to_np(p), rtol=2e-6, atol=2e-7)
+
+
+def _render_both(m, n_rays, seed):
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedRenderer
+    ro, rd, vd, _ = syn.random_training_rays(n_rays, n_views=20, seed=seed, device=DEV)
+    rk = dict(syn.RENDER_KWARGS)
+    with torch.no_grad():
+        ref = m(ro, rd, vd, global_step=0, render_depth=True, **rk)
+    out = FusedRenderer(m, rk, mlp="torch").render(ro, rd, vd, render_depth=True)
+    return ref, out
+
+
+@pytest.mark.parametrize("grid,n_rays,dens,maskp", [(32, 1024, 3.0, 0.3), (48, 4096, 1.0, 0.0), (40, 2048, 6.0, 0.5)])
+def test_fused_render_matches_module_forward(grid, n_rays, dens, maskp):
+    m = _fine_model(grid, dens_scale=dens, mask_p=maskp).to(DEV)
+    ref, out = _render_both(m, n_rays, 3)
+    # tolerances: T re-association 2e-6 rel; compositing order (atomics) 1e-5 abs on O(1) sums
+    np.testing.assert_allclose(to_np(out["alphainv_last"]), to_np(ref["alphainv_last"]), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(to_np(out["rgb_marched"]), to_np(ref["rgb_marched"]), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(to_np(out["depth"]), to_np(ref["depth"]), rtol=1e-5, atol=2e-3)
+
+
+def test_fused_survivor_set_is_the_reference_sample_set():
+    """The survivor stream (unordered) must be exactly the reference's M4 sample set: compare the
+    multiset of (ray, step) and the per-sample weights."""
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedRenderer
+    m = _fine_model(36, dens_scale=4.0, mask_p=0.4).to(DEV)
+    ro, rd, vd, _ = syn.random_training_rays(1500, n_views=20, seed=9, device=DEV)
+    rk = dict(syn.RENDER_KWARGS)
+    with torch.no_grad():
+        ref = m(ro, rd, vd, global_step=0, **rk)
+        pts, ray_id, step_id = m.sample_ray(ro, rd, **rk)
+    fr = FusedRenderer(m, rk, mlp="torch")
+    fr.render(ro, rd, vd)
+    ws = fr._workspace(1500, False)
+    m4 = int(ws.counters[0])
+    assert m4 == ref["ray_id"].numel()
+    assert int(ws.counters[1]) == 0
+    ray = ws.s_ray[:m4].long()
+    step = ws.s_slot[:m4].long() - ws.ray_off[:-1].long()[ray]
+    key = ray * 100000 + step
+    order = torch.argsort(key)
+    assert torch.equal(ray[order], ref["ray_id"])                      # bit-exact set, ray-major order
+    np.testing.assert_allclose(to_np(ws.s_weight[:m4][order]), to_np(ref["weights"]), rtol=5e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("stage", ["fine", "coarse"])
+def test_fused_trainer_vs_reference_python_golden(golden_dir, stage):
+    from directvoxgo_b200.fused import FusedTrainer
+    from tests.test_gpu_model import RK, _build
+    g = np.load(os.path.join(golden_dir, "refpy_%s_small.npz" % stage), allow_pickle=False)
+    m = _build(g, stage)
+    ro, rd, vd, tgt = (torch.tensor(g[k]).to(DEV) for k in ("rays_o", "rays_d", "viewdirs", "target"))
+    cfg = dict(fine=dict(weight_main=1.0, weight_entropy_last=1e-3, weight_rgbper=1e-2, lrate_density=0.1,
+                         lrate_k0=0.1, lrate_rgbnet=1e-3, lrate_decay=1e9, skip_zero_grad_fields=["density", "k0"],
+                         weight_tv_density=1e-5, weight_tv_k0=1e-5, tv_dense=True),
+               coarse=dict(weight_main=1.0, weight_entropy_last=1e-2, weight_rgbper=0.1, lrate_density=0.1,
+                           lrate_k0=0.1, lrate_rgbnet=0.0, lrate_decay=1e9, skip_zero_grad_fields=[]))[stage]
+    tr = FusedTrainer(m, cfg, RK, mlp="torch")
+    grads = {}
+    orig = tr._optimise
+
+    def capture(n_global):
+        if not grads:
+            grads["density"] = tr.g_density.clone()
+            grads["k0"] = tr.g_k0.clone()
+        orig(n_global)
+    tr._optimise = capture
+    l0 = float(tr.step(ro, rd, vd, tgt))
+    l1 = float(tr.step(ro, rd, vd, tgt))
+    assert abs(l0 - float(g["loss0"])) < 2e-6 and abs(l1 - float(g["loss1"])) < 5e-6
+    gd = grads["density"].reshape(g["grad_density0"].shape)
+    gk = grads["k0"].permute(3, 0, 1, 2)[None]
+    assert rel_to_max(gd, g["grad_density0"]) < 1e-4          # atomics: rel 1e-4 of max-abs
+    assert rel_to_max(gk, g["grad_k00"]) < 5e-4               # + cuBLAS-vs-MKL rgbnet backward
+    tr.sync_to_model()
+    for got, ref in ((m.density, g["density2"]), (m.k0, g["k02"])):
+        d = np.abs(to_np(got) - ref)
+        assert np.quantile(d, 0.999) < 2e-3 and np.median(d) < 1e-5
+
+
+def test_fused_trainer_vs_module_trainer_bigger():
+    """48^3 fine grid, 4096 Blender rays, 3 steps: fused (torch-MLP mode) vs the op-by-op path."""
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedTrainer
+    from directvoxgo_b200.trainer import ModuleTrainer
+    m1 = _fine_model(48, dens_scale=2.0, mask_p=0.2).to(DEV)
+    m2 = copy.deepcopy(m1)
+    cfg, rk = dict(syn.FINE_TRAIN), dict(syn.RENDER_KWARGS)
+    t1, t2 = ModuleTrainer(m1, cfg, rk), FusedTrainer(m2, cfg, rk, mlp="torch")
+    for it in range(3):
+        ro, rd, vd, tgt = syn.random_training_rays(4096, n_views=20, seed=50 + it, device=DEV)
+        la, lb = float(t1.step(ro, rd, vd, tgt)), float(t2.step(ro, rd, vd, tgt))
+        assert abs(la - lb) < 1e-5 * max(1.0, abs(la)), (it, la, lb)
+    t2.sync_to_model()
+    for a, b in ((m1.density, m2.density), (m1.k0, m2.k0)):
+        d = np.abs(to_np(a) - to_np(b))
+        assert np.median(d) < 1e-5 and np.quantile(d, 0.999) < 5e-3
+    for pa, pb in zip(m1.rgbnet.parameters(), m2.rgbnet.parameters()):
+        assert rel_to_max(pa, pb) < 1e-3
+
+
+def test_fused_dmpigo_render_and_step(golden_dir):
+    from directvoxgo_b200.dmpigo import DirectMPIGO
+    from directvoxgo_b200.fused import FusedRenderer
+    g = np.load(os.path.join(golden_dir, "refpy_dmpigo_small.npz"), allow_pickle=False)
+    m = DirectMPIGO(xyz_min=g["xyz_min"], xyz_max=g["xyz_max"], num_voxels=20 * 18 * 16, mpi_depth=16,
+                    fast_color_thres=1e-3, rgbnet_dim=9, rgbnet_depth=3, rgbnet_width=64, viewbase_pe=0)
+    with torch.no_grad():
+        m.density.copy_(torch.tensor(g["density0"]))
+        m.k0.copy_(torch.tensor(g["k00"]))
+        lin = [x for x in m.rgbnet.modules() if isinstance(x, torch.nn.Linear)]
+        for i, l in enumerate(lin):
+            l.weight.copy_(torch.tensor(g["rgbnet_w%d" % i]))
+            l.bias.copy_(torch.tensor(g["rgbnet_b%d" % i]))
+    m = m.to(DEV)
+    ro, rd, vd = (torch.tensor(g[k]).to(DEV) for k in ("rays_o", "rays_d", "viewdirs"))
+    out = FusedRenderer(m, dict(near=0, far=1, bg=0.0, stepsize=0.5), mlp="torch").render(ro, rd, vd)
+    np.testing.assert_allclose(to_np(out["rgb_marched"]), g["out_rgb_marched"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(to_np(out["alphainv_last"]), g["out_alphainv_last"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(to_np(out["depth"]), g["out_depth"], rtol=1e-5, atol=1e-3)
