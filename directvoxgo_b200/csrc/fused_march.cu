@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(256) march_fwd_kernel(
         }
       }
       if (hits) {
-        stopped = true;
+        stopped = true;  // later chunks only mark their slots as culled
         last_T = __shfl_sync(0xffffffffu, T_after, first);
-      } else {
+      } else if (!stopped) {
         carry = carry * __shfl_sync(0xffffffffu, incl, 31);
         last_T = static_cast<float>(carry);
       }

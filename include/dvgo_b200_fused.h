@@ -146,6 +146,17 @@ int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float
 int dvgo_grid_ncdhw_to_cl(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);
 int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);
 
+/* Tensor-core self test (one CTA): D[128,N] = A * B^T with tcgen05.mma kind::f16 (fp16 operands), for each operand
+ * orientation the rgbnet kernels use.  a_mn=0: A is [128][K]; a_mn=1: A is [K][128]; b_mn=0: B is
+ * [N][K]; b_mn=1: B is [K][N].  N % 16 == 0, N <= 256, K % 16 == 0, K <= 128.  D is [128][N]. */
+int dvgo_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn,
+                     dvgo_stream_t stream);
+
+/* Descriptor probe (debug aid for the kernel author): A [128][K] K-major, the B operand region is
+ * filled verbatim from Braw [nwords] and described with the given LBO/SBO/k-step (bytes). */
+int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, int K, int b_mn, int lbo, int sbo,
+                  int kstep, int nwords, dvgo_stream_t stream);
+
 /* Zero `n` 4-byte words (counters, accumulators) on the stream. */
 int dvgo_fused_zero(void* ptr, int64_t n_words, dvgo_stream_t stream);
 
