@@ -37,9 +37,58 @@ Tensor tc_probe(Tensor A, Tensor Braw, int N, int K, bool b_mn, int lbo, int sbo
                          kstep, static_cast<int>(Braw.numel()), cur_stream()), "tc_probe");
   return D;
 }
+
+inline void chki(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == torch::kInt32, name,
+              " must be a contiguous int32 CUDA tensor");
+}
+
+// params / grads: flat fp32 buffers laid out [W1 (width*d_in) | b1 | W2 | b2 | W3 (3*width) | b3]
+struct Offsets { int64_t W1, b1, W2, b2, W3, b3, total; };
+inline Offsets offsets(int d_in, int width) {
+  Offsets o;
+  o.W1 = 0; o.b1 = o.W1 + (int64_t)width * d_in; o.W2 = o.b1 + width; o.b2 = o.W2 + (int64_t)width * width;
+  o.W3 = o.b2 + width; o.b3 = o.W3 + 3 * width; o.total = o.b3 + 3;
+  return o;
+}
+
+void mlp_fwd(Tensor feat, Tensor s_ray, Tensor pe, Tensor counters, Tensor params, int width, Tensor rgb) {
+  chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
+  chkf(rgb, "rgb");
+  const int C = feat.size(1), P = pe.size(1);
+  const Offsets o = offsets(C + P, width);
+  TORCH_CHECK(params.numel() == o.total, "params has the wrong size");
+  const int64_t cap = s_ray.numel();
+  TORCH_CHECK(feat.size(0) >= cap && rgb.numel() >= cap * 3, "stream buffers too small");
+  const c10::cuda::CUDAGuard guard(feat.device());
+  const float* p = params.data_ptr<float>();
+  rc_check(dvgo_mlp_fwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P,
+                        counters.data_ptr<int32_t>(), cap, p + o.W1, p + o.b1, p + o.W2, p + o.b2, p + o.W3, p + o.b3,
+                        width, rgb.data_ptr<float>(), cur_stream()), "mlp_fwd");
+}
+
+void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, Tensor counters, Tensor params, int width, Tensor rgb, Tensor d_rgb,
+             double grad_scale, Tensor d_feat, Tensor grads) {
+  chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
+  chkf(rgb, "rgb"); chkf(d_rgb, "d_rgb"); chkf(d_feat, "d_feat"); chkf(grads, "grads");
+  const int C = feat.size(1), P = pe.size(1);
+  const Offsets o = offsets(C + P, width);
+  TORCH_CHECK(params.numel() == o.total && grads.numel() == o.total, "params/grads have the wrong size");
+  const int64_t cap = s_ray.numel();
+  const c10::cuda::CUDAGuard guard(feat.device());
+  const float* p = params.data_ptr<float>();
+  float* g = grads.data_ptr<float>();
+  rc_check(dvgo_mlp_bwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P,
+                        counters.data_ptr<int32_t>(), cap, p + o.W1, p + o.b1, p + o.W2, p + o.b2, p + o.W3, p + o.b3,
+                        width, rgb.data_ptr<float>(), d_rgb.data_ptr<float>(), static_cast<float>(grad_scale),
+                        d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3,
+                        cur_stream()), "mlp_bwd");
+}
 }  // namespace
 
 void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("tc_selftest", &tc_selftest);
   m.def("tc_probe", &tc_probe);
+  m.def("mlp_fwd", &mlp_fwd);
+  m.def("mlp_bwd", &mlp_bwd);
 }

@@ -92,7 +92,7 @@ class _FusedBase:
         self.X, self.Y, self.Z = (int(s) for s in model.density.shape[2:])
         self.C = int(model.k0.shape[1])
         if mlp == "auto":
-            mlp = "tc" if (model.rgbnet is not None and hasattr(ext, "mlp_fwd")) else "torch"
+            mlp = "tc" if (model.rgbnet is not None and hasattr(ext, "mlp_fwd") and self._tc_supported(model)) else "torch"
         if mlp == "tc" and not hasattr(ext, "mlp_fwd"):
             raise ImportError("tensor-core rgbnet kernels are not built")
         self.mlp_mode = mlp
@@ -102,6 +102,12 @@ class _FusedBase:
         self.density = model.density.detach().reshape(self.X, self.Y, self.Z).contiguous().clone()
         self.k0 = ext.ncdhw_to_cl(model.k0.detach().contiguous())
         self._ws = {}
+
+    @staticmethod
+    def _tc_supported(model):
+        lin = [m for m in model.rgbnet.modules() if isinstance(m, torch.nn.Linear)]
+        return (len(lin) == 3 and lin[0].out_features == 128 and lin[1].out_features == 128 and
+                getattr(model, "rgbnet_direct", True) and getattr(model, "posbase_pe", 0) == 0)
 
     def _workspace(self, n_rays, train):
         key = (n_rays, train)
@@ -230,7 +236,7 @@ class FusedTrainer(_FusedBase):
             pe = view_embedding(viewdirs, model.viewfreq).contiguous()
             self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
             after_rgb()
-            self._tc.backward(ws.feat, ws.s_ray, pe, ws.counters, ws.d_rgb, ws.d_feat)
+            self._tc.backward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb, ws.d_rgb, ws.d_feat, n_global)
         else:
             m4 = int(ws.counters[0].item())  # parity mode: one host read of the survivor count
             for p in model.rgbnet.parameters():

@@ -1,0 +1,58 @@
+"""Host side of the tensor-core rgbnet (csrc/fused_mlp.cu): flat fp32 master parameters, gradient and
+Adam buffers for the 39 -> 128 -> 128 -> 3 MLP of lib/dvgo.py:123-131, and the forward / backward /
+optimiser-step calls the FusedTrainer / FusedRenderer make."""
+import math
+
+import torch
+
+from . import adam_upd_cuda, ext
+
+
+class TensorCoreMLP:
+    WIDTH = 128
+
+    def __init__(self, rgbnet, device, train=False):
+        lin = [m for m in rgbnet.modules() if isinstance(m, torch.nn.Linear)]
+        if len(lin) != 3 or lin[0].out_features != self.WIDTH or lin[1].in_features != self.WIDTH or \
+                lin[1].out_features != self.WIDTH or lin[2].out_features != 3:
+            raise NotImplementedError("tensor-core rgbnet: depth 3, width 128, 3 outputs (the configs' default)")
+        self.d_in = lin[0].in_features
+        self.lin = lin
+        flat = [t.detach().reshape(-1) for l in lin for t in (l.weight, l.bias)]
+        self.params = torch.cat(flat).to(device=device, dtype=torch.float32).contiguous()
+        self.train = train
+        if train:
+            self.grad_flat = torch.zeros_like(self.params)
+            self.exp_avg = torch.zeros_like(self.params)
+            self.exp_avg_sq = torch.zeros_like(self.params)
+
+    def refresh_from_module(self):
+        flat = [t.detach().reshape(-1) for l in self.lin for t in (l.weight, l.bias)]
+        self.params.copy_(torch.cat(flat))
+
+    def forward(self, feat, s_ray, pe, counters, rgb):
+        ext.mlp_fwd(feat, s_ray, pe, counters, self.params, self.WIDTH, rgb)
+
+    def backward(self, feat, s_ray, pe, counters, rgb, d_rgb, d_feat, n_global):
+        """Accumulates weight gradients into self.grad_flat (zeroed here) and writes d_feat."""
+        ext.zero_(self.grad_flat)
+        # d_rgb <= ~2/(3 n_global): scale so that the largest FP16 backward operand is O(100)
+        scale = 2.0 ** math.floor(math.log2(256.0 * n_global))
+        ext.mlp_bwd(feat, s_ray, pe, counters, self.params, self.WIDTH, rgb, d_rgb, scale, d_feat, self.grad_flat)
+
+    def adam_step(self, step, beta1, beta2, lr, eps):
+        adam_upd_cuda.adam_upd(self.params, self.grad_flat, self.exp_avg, self.exp_avg_sq, step, beta1, beta2, lr, eps)
+
+    def unflatten(self, flat):
+        out, o = [], 0
+        for l in self.lin:
+            for t in (l.weight, l.bias):
+                n = t.numel()
+                out.append(flat[o:o + n].view_as(t))
+                o += n
+        return out
+
+    @torch.no_grad()
+    def sync_to_module(self, rgbnet=None):
+        for dst, src in zip([t for l in self.lin for t in (l.weight, l.bias)], self.unflatten(self.params)):
+            dst.data.copy_(src)

@@ -146,6 +146,26 @@ int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float
 int dvgo_grid_ncdhw_to_cl(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);
 int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);
 
+/* rgbnet on the tensor cores (fused_mlp.cu): x = [feat (C) | pe[s_ray] (P)] -> Linear(C+P, 128) -> ReLU
+ * -> Linear(128,128) -> ReLU -> Linear(128,3) -> sigmoid   (lib/dvgo.py:123-131, :524-539 with
+ * rgbnet_direct=True, rgbnet_depth=3, rgbnet_width=128 -- the configs' default).
+ * feat [surv_cap,C], s_ray [surv_cap] int32, pe [n_rays,P] (per-ray view embedding), counters[0] = M4.
+ * Weights are fp32 in torch nn.Linear layout ([out][in]); GEMM operands are rounded to FP16, accumulation
+ * is fp32.  rgb [surv_cap,3].  width must be 128 (DVGO_EINVAL otherwise: the caller falls back). */
+int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P,
+                 const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
+                 const float* b2, const float* W3, const float* b3, int width, float* rgb,
+                 dvgo_stream_t stream);
+/* Backward with forward recompute: d_feat [surv_cap,C] = dL/dfeat, and gW*, gb* += weight gradients
+ * (accumulated in TMEM per CTA, flushed with atomics; the caller zeroes them).  d_rgb = dL/d(rgb) (after
+ * the sigmoid).  grad_scale: power of two applied to the FP16 backward operands and removed exactly in
+ * the fp32 epilogues. */
+int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P,
+                 const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
+                 const float* b2, const float* W3, const float* b3, int width, const float* rgb,
+                 const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
+                 float* gb2, float* gW3, float* gb3, dvgo_stream_t stream);
+
 /* Tensor-core self test (one CTA): D[128,N] = A * B^T with tcgen05.mma kind::f16 (fp16 operands), for each operand
  * orientation the rgbnet kernels use.  a_mn=0: A is [128][K]; a_mn=1: A is [K][128]; b_mn=0: B is
  * [N][K]; b_mn=1: B is [K][N].  N % 16 == 0, N <= 256, K % 16 == 0, K <= 128.  D is [128][N]. */

@@ -33,3 +33,108 @@ def test_tcgen05_descriptor_orientations(N, K, a_mn, b_mn):
     # fp16-rounded inputs, fp32 accumulation: agreement to fp32 summation error
     err = rel_to_max(D, ref)
     assert err < 2e-6, (N, K, a_mn, b_mn, err)
+
+
+def _make_mlp(seed, d_in=39):
+    torch.manual_seed(seed)
+    net = torch.nn.Sequential(
+        torch.nn.Linear(d_in, 128), torch.nn.ReLU(inplace=True),
+        torch.nn.Sequential(torch.nn.Linear(128, 128), torch.nn.ReLU(inplace=True)),
+        torch.nn.Linear(128, 3))
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.05)   # non-zero biases everywhere
+    return net.to(DEV)
+
+
+def _stream(M, n_rays, C, P, seed, cap_extra=77):
+    g = torch.Generator().manual_seed(seed)
+    cap = M + cap_extra
+    feat = torch.randn(cap, C, generator=g).to(DEV)
+    pe = (torch.rand(n_rays, P, generator=g) * 2 - 1).to(DEV)
+    s_ray = torch.randint(n_rays, (cap,), generator=g, dtype=torch.int32).to(DEV)
+    counters = torch.tensor([M, 0], dtype=torch.int32, device=DEV)
+    return feat, pe, s_ray, counters, cap
+
+
+@pytest.mark.parametrize("M,C,P", [(1, 12, 27), (128, 12, 27), (1000, 12, 27), (70001, 12, 27), (3000, 9, 3)])
+def test_tc_mlp_forward(M, C, P):
+    from directvoxgo_b200.fused_mlp import TensorCoreMLP
+    net = _make_mlp(M, C + P)
+    feat, pe, s_ray, counters, cap = _stream(M, 257, C, P, M)
+    tc = TensorCoreMLP(net, DEV)
+    rgb = torch.full((cap, 3), -7.0, device=DEV)
+    tc.forward(feat, s_ray, pe, counters, rgb)
+    torch.cuda.synchronize()
+    x = torch.cat([feat[:M], pe[s_ray[:M].long()]], -1)
+    with torch.no_grad():
+        ref = torch.sigmoid(net(x))
+        # emulation of the kernel's operand rounding: fp16 inputs / weights / hidden-1, fp32 accumulate
+        l = [m for m in net.modules() if isinstance(m, torch.nn.Linear)]
+        h1 = torch.relu(_h(x).double() @ _h(l[0].weight).double().t() + _h(l[0].bias).double())
+        h2 = torch.relu(_h(h1.float()).double() @ _h(l[1].weight).double().t() + l[1].bias.double())
+        emu = torch.sigmoid(h2 @ l[2].weight.double().t() + l[2].bias.double()).float()
+    assert torch.all(rgb[M:] == -7.0)                                    # nothing written past the count
+    np.testing.assert_allclose(to_np(rgb[:M]), to_np(emu), rtol=0, atol=2e-5)   # same rounding model
+    np.testing.assert_allclose(to_np(rgb[:M]), to_np(ref), rtol=0, atol=2e-3)   # stated tolerance vs exact fp32
+
+
+@pytest.mark.parametrize("M,n_global", [(1, 8192), (300, 8192), (9000, 8192), (40000, 65536)])
+def test_tc_mlp_backward(M, n_global):
+    from directvoxgo_b200.fused_mlp import TensorCoreMLP
+    C, P = 12, 27
+    net = _make_mlp(M + 5, C + P)
+    feat, pe, s_ray, counters, cap = _stream(M, 300, C, P, M + 1)
+    g = torch.Generator().manual_seed(M)
+    d_rgb = (torch.randn(cap, 3, generator=g) * (1.0 / (3 * n_global))).to(DEV)
+    tc = TensorCoreMLP(net, DEV, train=True)
+    rgb = torch.zeros(cap, 3, device=DEV)
+    d_feat = torch.full((cap, C), 3.0, device=DEV)
+    tc.forward(feat, s_ray, pe, counters, rgb)
+    tc.backward(feat, s_ray, pe, counters, rgb, d_rgb, d_feat, n_global)
+    torch.cuda.synchronize()
+    x = torch.cat([feat[:M], pe[s_ray[:M].long()]], -1).requires_grad_()
+    out = torch.sigmoid(net(x))
+    out.backward(d_rgb[:M])
+    assert torch.all(d_feat[M:] == 3.0)
+    # tolerance: fp16 operand rounding (2^-11 relative per operand) -> 5e-3 of max-abs on every gradient
+    assert rel_to_max(d_feat[:M], x.grad[:, :C]) < 5e-3
+    lin = [m for m in net.modules() if isinstance(m, torch.nn.Linear)]
+    got = tc.unflatten(tc.grad_flat)
+    names = ["W1", "b1", "W2", "b2", "W3", "b3"]
+    for name, gt, p in zip(names, got, [t for l in lin for t in (l.weight, l.bias)]):
+        assert rel_to_max(gt, p.grad) < 5e-3, (name, rel_to_max(gt, p.grad))
+
+
+def test_fused_trainer_tensor_core_mode_tracks_fp32_mode():
+    """Whole training steps: tcgen05 rgbnet vs the exact-fp32 (cuBLAS) rgbnet inside the same fused pipeline."""
+    import copy
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedTrainer
+    from tests.test_gpu_fused import _fine_model
+    m1 = _fine_model(48, dens_scale=2.0, mask_p=0.2).to(DEV)
+    m2 = copy.deepcopy(m1)
+    cfg, rk = dict(syn.FINE_TRAIN), dict(syn.RENDER_KWARGS)
+    t1, t2 = FusedTrainer(m1, cfg, rk, mlp="torch"), FusedTrainer(m2, cfg, rk, mlp="tc")
+    for it in range(3):
+        ro, rd, vd, tgt = syn.random_training_rays(4096, n_views=20, seed=70 + it, device=DEV)
+        la, lb = float(t1.step(ro, rd, vd, tgt)), float(t2.step(ro, rd, vd, tgt))
+        assert abs(la - lb) < 2e-3 * max(1.0, abs(la)), (it, la, lb)
+    t1.sync_to_model(); t2.sync_to_model()
+    for pa, pb in zip(m1.rgbnet.parameters(), m2.rgbnet.parameters()):
+        assert rel_to_max(pa, pb) < 2e-2
+    d = np.abs(to_np(m1.k0) - to_np(m2.k0))
+    assert np.median(d) < 2e-3
+
+
+def test_fused_renderer_tensor_core_mode():
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedRenderer
+    from tests.test_gpu_fused import _fine_model
+    m = _fine_model(48, dens_scale=2.0, mask_p=0.2).to(DEV)
+    ro, rd, vd, _ = syn.random_training_rays(4096, n_views=20, seed=3, device=DEV)
+    rk = dict(syn.RENDER_KWARGS)
+    a = FusedRenderer(m, rk, mlp="torch").render(ro, rd, vd)
+    b = FusedRenderer(m, rk, mlp="tc").render(ro, rd, vd)
+    np.testing.assert_allclose(to_np(b["rgb_marched"]), to_np(a["rgb_marched"]), rtol=0, atol=2e-3)
+    np.testing.assert_allclose(to_np(b["depth"]), to_np(a["depth"]), rtol=1e-5, atol=2e-3)
