@@ -111,22 +111,34 @@ __device__ __forceinline__ bool occupancy(const SceneDev& sc, float px, float py
   return false;
 }
 
-// 8-corner geometry (ATen order x0y0z0, x0y0z1, x0y1z0, ... ; weight = (wz*wy)*wx; zero padding).
+// 8-corner geometry (ATen order x0y0z0, x0y0z1, x0y1z0, ... ; weight = (wz*wy)*wx; zero padding),
+// kept compact (one base voxel index + validity bits + six axis weights) to save registers.
 struct Corner8 {
-  int64_t off[8];  // voxel index (x*Y+y)*Z+z, or -1 when padded
-  float w[8];
+  int base;        // voxel index of (x0,y0,z0) = (x0*Y + y0)*Z + z0 (may be "virtual" when padded)
+  int sy, sx;      // voxel-index strides of y+1 and x+1
+  unsigned valid;  // bit k set <=> corner k lies inside the grid
+  float wx0, wx1, wy0, wy1, wz0, wz1;
+  __device__ __forceinline__ bool ok(int k) const { return (valid >> k) & 1u; }
+  __device__ __forceinline__ int off(int k) const { return base + (k >> 2) * sx + ((k >> 1) & 1) * sy + (k & 1); }
+  __device__ __forceinline__ float w(int k) const {
+    return fmul(fmul((k & 1) ? wz1 : wz0, ((k >> 1) & 1) ? wy1 : wy0), (k >> 2) ? wx1 : wx0);
+  }
 };
 __device__ __forceinline__ Corner8 corner8(const SceneDev& sc, float px, float py, float pz) {
   const Tri t = tri_setup(px, py, pz, sc.lo, sc.hi, sc.X, sc.Y, sc.Z);
   Corner8 c;
+  c.sy = sc.Z;
+  c.sx = sc.Y * sc.Z;
+  c.base = (t.x0 * sc.Y + t.y0) * sc.Z + t.z0;
+  c.wx0 = t.wx0; c.wx1 = t.wx1; c.wy0 = t.wy0; c.wy1 = t.wy1; c.wz0 = t.wz0; c.wz1 = t.wz1;
+  const unsigned vx = (t.x0 >= 0 && t.x0 < sc.X ? 1u : 0u) | (t.x0 + 1 >= 0 && t.x0 + 1 < sc.X ? 2u : 0u);
+  const unsigned vy = (t.y0 >= 0 && t.y0 < sc.Y ? 1u : 0u) | (t.y0 + 1 >= 0 && t.y0 + 1 < sc.Y ? 2u : 0u);
+  const unsigned vz = (t.z0 >= 0 && t.z0 < sc.Z ? 1u : 0u) | (t.z0 + 1 >= 0 && t.z0 + 1 < sc.Z ? 2u : 0u);
+  unsigned v = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;
-    const int xi = t.x0 + dx, yi = t.y0 + dy, zi = t.z0 + dz;
-    const bool in = (xi >= 0) & (xi < sc.X) & (yi >= 0) & (yi < sc.Y) & (zi >= 0) & (zi < sc.Z);
-    c.off[k] = in ? (static_cast<int64_t>(xi) * sc.Y + yi) * sc.Z + zi : -1;
-    c.w[k] = fmul(fmul(dz ? t.wz1 : t.wz0, dy ? t.wy1 : t.wy0), dx ? t.wx1 : t.wx0);
-  }
+  for (int k = 0; k < 8; ++k)
+    if (((vx >> (k >> 2)) & 1u) & ((vy >> ((k >> 1) & 1)) & 1u) & ((vz >> (k & 1)) & 1u)) v |= 1u << k;
+  c.valid = v;
   return c;
 }
 
@@ -205,20 +217,21 @@ __device__ __forceinline__ void gather_k0(const float* __restrict__ k0, const Co
   for (int c = 0; c < C; ++c) acc[c] = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    if (cn.off[k] < 0) continue;
-    const float* __restrict__ v = k0 + cn.off[k] * C;
+    if (!cn.ok(k)) continue;
+    const float* __restrict__ v = k0 + static_cast<int64_t>(cn.off(k)) * C;
+    const float wk = cn.w(k);
     if (C % 4 == 0) {
 #pragma unroll
       for (int q = 0; q < C / 4; ++q) {
         const float4 f = __ldg(reinterpret_cast<const float4*>(v) + q);
-        acc[4 * q + 0] = fma_(f.x, cn.w[k], acc[4 * q + 0]);
-        acc[4 * q + 1] = fma_(f.y, cn.w[k], acc[4 * q + 1]);
-        acc[4 * q + 2] = fma_(f.z, cn.w[k], acc[4 * q + 2]);
-        acc[4 * q + 3] = fma_(f.w, cn.w[k], acc[4 * q + 3]);
+        acc[4 * q + 0] = fma_(f.x, wk, acc[4 * q + 0]);
+        acc[4 * q + 1] = fma_(f.y, wk, acc[4 * q + 1]);
+        acc[4 * q + 2] = fma_(f.z, wk, acc[4 * q + 2]);
+        acc[4 * q + 3] = fma_(f.w, wk, acc[4 * q + 3]);
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = fma_(__ldg(v + c), cn.w[k], acc[c]);
+      for (int c = 0; c < C; ++c) acc[c] = fma_(__ldg(v + c), wk, acc[c]);
     }
   }
   if (C % 4 == 0) {
@@ -233,7 +246,7 @@ __device__ __forceinline__ void gather_k0(const float* __restrict__ k0, const Co
 }
 
 template <int C>
-__global__ void __launch_bounds__(256) march_fwd_kernel(
+__global__ void __launch_bounds__(256, 3) march_fwd_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
     const float* __restrict__ density, const float* __restrict__ k0, int n_rays,
     const float* __restrict__ t_min, const int32_t* __restrict__ n_steps,
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__(256) march_fwd_kernel(
         float dens = 0.f;  // :476 trilinear density (ATen accumulation order)
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (cn.off[k] >= 0) dens = fma_(__ldg(density + cn.off[k]), cn.w[k], dens);
+          if (cn.ok(k)) dens = fma_(__ldg(density + cn.off(k)), cn.w(k), dens);
         e = expf(fadd(dens, sc.act_shift));                     // render_utils_kernel.cu:366
         alpha = fsub(1.f, powf(fadd(1.f, e), -sc.interval));    // :368
         if (use_thres) live = alpha > sc.thres;                 // lib/dvgo.py:478-484
@@ -344,9 +357,9 @@ __device__ __forceinline__ void scatter_k0(float* __restrict__ gk0, const Corner
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    if (cn.off[k] < 0) continue;
-    float* __restrict__ dst = gk0 + cn.off[k] * C;
-    const float w = cn.w[k];
+    if (!cn.ok(k)) continue;
+    float* __restrict__ dst = gk0 + static_cast<int64_t>(cn.off(k)) * C;
+    const float w = cn.w(k);
     if (C % 4 == 0) {
 #pragma unroll
       for (int q = 0; q < C / 4; ++q) {
@@ -363,7 +376,7 @@ __device__ __forceinline__ void scatter_k0(float* __restrict__ gk0, const Corner
 }
 
 template <int C>
-__global__ void __launch_bounds__(256) march_bwd_kernel(
+__global__ void __launch_bounds__(256, 3) march_bwd_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a, int n_rays,
     const float* __restrict__ t_min, const int32_t* __restrict__ n_steps,
     const int32_t* __restrict__ ray_off, const float* __restrict__ slot_alpha,
@@ -417,7 +430,7 @@ __global__ void __launch_bounds__(256) march_bwd_kernel(
       const Corner8 cn = corner8(sc, px, py, pz);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        if (cn.off[k] >= 0) atomicAdd(grad_density + cn.off[k], fmul(cn.w[k], g_dens));
+        if (cn.ok(k)) atomicAdd(grad_density + cn.off(k), fmul(cn.w(k), g_dens));
       if (code >= 0 && grad_k0) scatter_k0<C>(grad_k0, cn, d_feat + static_cast<int64_t>(code) * C);
     }
   }

@@ -65,24 +65,40 @@ __device__ void load_weights(const MlpW& w, int d_in, int K1, uint8_t* sW1, uint
   if (threadIdx.x < 3) sB3[threadIdx.x] = w.b3[threadIdx.x];
 }
 
-// Augmented input tile [128 x K1]: cols [0,C) k0 features, [C,C+P) view embedding of the sample's ray,
-// col C+P = 1 (bias), rest 0; rows past the survivor count are zero.
+// Augmented input tile [128 x K1]: cols [0,C) k0 features, [C,C+pe_stride) the ray's row of the padded
+// view-embedding table (P embedding values, then the constant 1 that carries b1, then zeros), rest 0;
+// rows past the survivor count are zero.  16-byte vector loads when C and pe_stride are multiples of 4.
 __device__ __forceinline__ void stage_x(uint8_t* sX, int K1, int64_t base, int64_t count,
                                         const float* __restrict__ feat, int C,
-                                        const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P) {
+                                        const int32_t* __restrict__ s_ray, const float* __restrict__ pe,
+                                        int pe_stride) {
   const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
   const int64_t s = base + r;
   const bool valid = s < count;
   const float* __restrict__ f = feat + s * C;
-  const float* __restrict__ e = pe + static_cast<int64_t>(valid ? s_ray[s] : 0) * P;
+  const float* __restrict__ e = pe + static_cast<int64_t>(valid ? s_ray[s] : 0) * pe_stride;
+  const bool vec = ((C | pe_stride) & 3) == 0;
   for (int ch = h; ch < K1 / 8; ch += 2) {
     float v[8];
+    if (vec) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = ch * 8 + j;
-      float x = 0.f;
-      if (valid) x = c < C ? __ldg(f + c) : (c < C + P ? __ldg(e + (c - C)) : (c == C + P ? 1.f : 0.f));
-      v[j] = x;
+      for (int g = 0; g < 2; ++g) {
+        const int c = ch * 8 + g * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          if (c < C) x = __ldg(reinterpret_cast<const float4*>(f + c));
+          else if (c < C + pe_stride) x = __ldg(reinterpret_cast<const float4*>(e + (c - C)));
+        }
+        v[g * 4] = x.x; v[g * 4 + 1] = x.y; v[g * 4 + 2] = x.z; v[g * 4 + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = ch * 8 + j;
+        float x = 0.f;
+        if (valid) x = c < C ? __ldg(f + c) : (c < C + pe_stride ? __ldg(e + (c - C)) : 0.f);
+        v[j] = x;
+      }
     }
     *reinterpret_cast<uint4*>(sX + tile_off(r, ch * 8, K1)) = pack8(v);
   }
@@ -127,19 +143,33 @@ __device__ __forceinline__ void gemm_mm(uint32_t d, uint32_t a, int a_cols, uint
             desc_mnmajor(b + k * 2u * group_stride(b_cols), b_cols), idesc, (accumulate || k) ? 1u : 0u);
 }
 
-// TMEM [this thread's row][c0, c0+64) -> act(v + bias) -> fp16 -> smem tile row.  bias may be null.
+// TMEM [this thread's row][c_begin, c_begin+64) -> relu(v + bias) -> fp16 -> smem tile row.  bias may be
+// null.  All four 16-column TMEM loads are issued before the single wait so their latencies overlap.
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) tmem_ld16(taddr + cc * 16, v + cc * 16);
+  tmem_ld_wait();
+}
 __device__ __forceinline__ void epi_relu_to_smem(uint32_t tmem_d, int q, int row, int c_begin, const float* sBias,
                                                  uint8_t* sOut) {
+  float v[64];
+  tmem_ld64(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + c_begin, v);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    const int c0 = c_begin + cc * 16;
-    float v[16];
-    tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-    tmem_ld_wait();
+  for (int cc = 0; cc < 8; ++cc) {
+    const int c0 = c_begin + cc * 8;
+    float o[8];
+    if (sBias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0);
+      const float4 b1 = *reinterpret_cast<const float4*>(sBias + c0 + 4);
+      o[0] = v[cc * 8 + 0] + b0.x; o[1] = v[cc * 8 + 1] + b0.y; o[2] = v[cc * 8 + 2] + b0.z; o[3] = v[cc * 8 + 3] + b0.w;
+      o[4] = v[cc * 8 + 4] + b1.x; o[5] = v[cc * 8 + 5] + b1.y; o[6] = v[cc * 8 + 6] + b1.z; o[7] = v[cc * 8 + 7] + b1.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + (sBias ? sBias[c0 + j] : 0.f), 0.f);
-    *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, kHid)) = pack8(v);
-    *reinterpret_cast<uint4*>(sOut + tile_off(row, c0 + 8, kHid)) = pack8(v + 8);
+      for (int j = 0; j < 8; ++j) o[j] = v[cc * 8 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, kHid)) = pack8(o);
   }
 }
 
@@ -148,7 +178,7 @@ __device__ __forceinline__ size_t align1k(size_t x) { return (x + 1023) & ~stati
 // ---- forward ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, float* __restrict__ rgb) {
+    const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride, float* __restrict__ rgb) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -169,10 +199,13 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
   float* sB2 = sW3 + 3 * kHid;
   float* sB3 = sB2 + kHid;
   float* sPart = sB3 + 4;  // [128][3] partial layer-3 sums of the upper column half
+  float4* sL3 = reinterpret_cast<float4*>(sPart + 3 * kTile);  // [128] {W3[0][j], W3[1][j], W3[2][j], b2[j]}
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
   if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init_fence(); }
   load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3);
+  for (int j = tid; j < kHid; j += blockDim.x)
+    sL3[j] = make_float4(w.W3[j], w.W3[kHid + j], w.W3[2 * kHid + j], w.b2[j]);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -182,7 +215,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t s0 = tile * kTile;
-    stage_x(sX, K1, s0, count, feat, C, s_ray, pe, P);
+    stage_x(sX, K1, s0, count, feat, C, s_ray, pe, pe_stride);
     sync_for_mma();
     if (tid == 0) {
       gemm_kk(tD1, smem_u32(sX), K1, smem_u32(sW1), K1, kHid, K1, false);
@@ -198,18 +231,16 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     mma_wait(ctx);
     // layer-2 epilogue fused with layer 3 (fp32 SIMT): acc_c = sum_j relu(z2_j + b2_j) * W3[c][j]
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    {
+      float v[64];
+      tmem_ld64(tD2 + (static_cast<uint32_t>(q * 32) << 16) + half * 64, v);
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c0 = half * 64 + cc * 16;
-      float v[16];
-      tmem_ld16(tD2 + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float hv = fmaxf(v[j] + sB2[c0 + j], 0.f);
-        a0 = fmaf(hv, sW3[c0 + j], a0);
-        a1 = fmaf(hv, sW3[kHid + c0 + j], a1);
-        a2 = fmaf(hv, sW3[2 * kHid + c0 + j], a2);
+      for (int j = 0; j < 64; ++j) {
+        const float4 t = sL3[half * 64 + j];  // one broadcast 16-byte load per hidden unit
+        const float hv = fmaxf(v[j] + t.w, 0.f);
+        a0 = fmaf(hv, t.x, a0);
+        a1 = fmaf(hv, t.y, a1);
+        a2 = fmaf(hv, t.z, a2);
       }
     }
     if (half == 1) { sPart[row * 3] = a0; sPart[row * 3 + 1] = a1; sPart[row * 3 + 2] = a2; }
@@ -242,35 +273,54 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
 // The four weight-gradient accumulators stay in TMEM across all tiles of the CTA and are flushed to
 // global memory with atomics once at the end.  S = grad_scale (a power of two) keeps the FP16
 // operands of the backward GEMMs in normal range.
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_kernel(
+//
+// Pipelining: the five MMA batches of a tile are separated by SIMT epilogues that depend on them, so a
+// single tile leaves the tensor pipe idle ~85% of the time (measured, profiles/r01_*).  Each CTA
+// therefore works on TWO tiles (contexts A and B, each with its own activation buffers, TMEM work
+// columns and mbarrier) in an interleaved schedule: while all 512 threads run the epilogue of one
+// context, the MMA batch of the other is in flight.  One thread issues every MMA in program order, so
+// both contexts can accumulate into the same TMEM weight-gradient columns.
+constexpr int kBwdThreads = 512;
+
+struct TileCtx {
+  uint8_t* sX; uint8_t* sH1; uint8_t* sH2; uint8_t* sdZ3;
+  uint32_t tWork;
+  MmaCtx bar;
+  int64_t s0;
+  float dz[3];
+  bool valid;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, const float* __restrict__ rgb,
-    const float* __restrict__ d_rgb, float grad_scale, float* __restrict__ d_feat, MlpG g) {
+    const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride,
+    const float* __restrict__ rgb, const float* __restrict__ d_rgb, float grad_scale, float* __restrict__ d_feat,
+    MlpG g) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+  const int q = warp & 3, part = warp >> 2, row = q * 32 + lane;  // part in 0..3: 32 hidden columns each
   const int d_in = C + P;
   int64_t count = counters[0];
   if (count > surv_cap) count = surv_cap;
   const int64_t n_tiles = (count + kTile - 1) / kTile;
-  if (static_cast<int64_t>(blockIdx.x) >= n_tiles) return;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  if (static_cast<int64_t>(blockIdx.x) >= n_pairs) return;
 
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW1 = base;
   uint8_t* sW2 = sW1 + align1k(tile_bytes(kHid, K1));
-  uint8_t* sX = sW2 + align1k(tile_bytes(kHid, kHid));
-  uint8_t* sH1 = sX + align1k(tile_bytes(kTile, K1));
-  uint8_t* sH2 = sH1 + align1k(tile_bytes(kTile, kHid));
-  uint8_t* sdZ3 = sH2 + align1k(tile_bytes(kTile, kHid));
-  uint8_t* sOnes = sdZ3 + align1k(tile_bytes(kTile, 16));
-  float* sW3 = reinterpret_cast<float*>(sOnes + align1k(tile_bytes(kTile, 16)));
+  uint8_t* sOnes = sW2 + align1k(tile_bytes(kHid, kHid));
+  uint8_t* ctx_base = sOnes + align1k(tile_bytes(kTile, 16));
+  const size_t ctx_bytes = align1k(tile_bytes(kTile, K1)) + 2 * align1k(tile_bytes(kTile, kHid)) +
+                           align1k(tile_bytes(kTile, 16));
+  float* sW3 = reinterpret_cast<float*>(ctx_base + 2 * ctx_bytes);
   float* sB2 = sW3 + 3 * kHid;
   float* sB3 = sB2 + kHid;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
-  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init_fence(); }
+  if (tid == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_init_fence(); }
   load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3);
   for (int i = tid; i < kTile * 16; i += blockDim.x)  // ones in column 0: db2 = dZ2^T * ones
     *reinterpret_cast<__half*>(sOnes + tile_off(i / 16, i % 16, 16)) = __float2half_rn((i % 16) == 0 ? 1.f : 0.f);
@@ -278,133 +328,211 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_kernel(
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tWork0 = tmem, tWork1 = tmem + 128, tdW2 = tmem + 256, tdW1 = tmem + 384, tdW3 = tmem + 432,
-                 tdB2 = tmem + 448;
-  MmaCtx ctx{smem_u32(&bar), 0u};
+  const uint32_t tdW2 = tmem + 256, tdW1 = tmem + 384, tdW3 = tmem + 432, tdB2 = tmem + 448;
+  TileCtx cx[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint8_t* b = ctx_base + i * ctx_bytes;
+    cx[i].sX = b;
+    cx[i].sH1 = b + align1k(tile_bytes(kTile, K1));
+    cx[i].sH2 = cx[i].sH1 + align1k(tile_bytes(kTile, kHid));
+    cx[i].sdZ3 = cx[i].sH2 + align1k(tile_bytes(kTile, kHid));
+    cx[i].tWork = tmem + 128 * i;
+    cx[i].bar = MmaCtx{smem_u32(&bars[i]), 0u};
+  }
   const float inv_scale = 1.f / grad_scale;
+  const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
   float db3[3] = {0.f, 0.f, 0.f};
   bool first = true;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t s0 = tile * kTile;
-    const int64_t s = s0 + row;
-    const bool valid = s < count;
-    // dZ3 (scaled) for this thread's row, kept in registers and staged for the dW3 GEMM
-    float dz[3] = {0.f, 0.f, 0.f};
-    if (valid) {
+  // ---- per-context stages (all 512 threads unless noted) ----
+  auto stage = [&](TileCtx& c) {  // X~ tile and dZ3 (registers + smem tile)
+    const int64_t s = c.s0 + row;
+    c.valid = s < count;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float o = rgb[s * 3 + c];
-        dz[c] = d_rgb[s * 3 + c] * o * (1.f - o) * grad_scale;
+    for (int k = 0; k < 3; ++k) c.dz[k] = 0.f;
+    if (c.valid) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float o = rgb[s * 3 + k];
+        c.dz[k] = d_rgb[s * 3 + k] * o * (1.f - o) * grad_scale;
       }
     }
-    if (half == 0) {
+    if (part == 0) {
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = j < 3 ? dz[j] : 0.f;
-      *reinterpret_cast<uint4*>(sdZ3 + tile_off(row, 0, 16)) = pack8(v);
-      *reinterpret_cast<uint4*>(sdZ3 + tile_off(row, 8, 16)) = pack8(v + 8);
+      for (int j = 0; j < 16; ++j) v[j] = j < 3 ? c.dz[j] : 0.f;
+      *reinterpret_cast<uint4*>(c.sdZ3 + tile_off(row, 0, 16)) = pack8(v);
+      *reinterpret_cast<uint4*>(c.sdZ3 + tile_off(row, 8, 16)) = pack8(v + 8);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) db3[c] += dz[c];
+      for (int k = 0; k < 3; ++k) db3[k] += c.dz[k];
     }
-    stage_x(sX, K1, s0, count, feat, C, s_ray, pe, P);
-    sync_for_mma();
-    if (tid == 0) {
-      gemm_kk(tWork0, smem_u32(sX), K1, smem_u32(sW1), K1, kHid, K1, false);
-      mma_commit(ctx.bar);
-    }
-    mma_wait(ctx);
-    epi_relu_to_smem(tWork0, q, row, half * 64, nullptr, sH1);
-    sync_for_mma();
-    if (tid == 0) {
-      gemm_kk(tWork1, smem_u32(sH1), kHid, smem_u32(sW2), kHid, kHid, kHid, false);
-      mma_commit(ctx.bar);
-    }
-    mma_wait(ctx);
-    epi_relu_to_smem(tWork1, q, row, half * 64, sB2, sH2);
-    sync_for_mma();
-    if (tid == 0) {  // dW3^T [hidden j][c] += sum_s H2[s][j] dZ3[s][c]
-      gemm_mm(tdW3, smem_u32(sH2), kHid, smem_u32(sdZ3), 16, 16, kTile, !first);
-      mma_commit(ctx.bar);
-    }
-    mma_wait(ctx);
-    // dZ2 in place over H2: thread (row, half) handles its 64 columns
+    // X~: thread (r = tid & 127, h = tid >> 7) fills 16-byte chunks h, h+4, ...
+    {
+      const int h = tid >> 7;
+      const float* __restrict__ f = feat + s * C;
+      const float* __restrict__ e = pe + static_cast<int64_t>(c.valid ? s_ray[s] : 0) * pe_stride;
+      const bool vec = ((C | pe_stride) & 3) == 0;
+      for (int ch = h; ch < K1 / 8; ch += 4) {
+        float v[8];
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      const int c0 = half * 64 + ch * 8;
-      uint8_t* p = sH2 + tile_off(row, c0, kHid);
+        for (int gq = 0; gq < 2; ++gq) {
+          const int col = ch * 8 + gq * 4;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c.valid) {
+            if (vec) {
+              if (col < C) x = __ldg(reinterpret_cast<const float4*>(f + col));
+              else if (col < C + pe_stride) x = __ldg(reinterpret_cast<const float4*>(e + (col - C)));
+            } else {
+              float t[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int cc = col + j;
+                t[j] = cc < C ? __ldg(f + cc) : (cc < C + pe_stride ? __ldg(e + (cc - C)) : 0.f);
+              }
+              x = make_float4(t[0], t[1], t[2], t[3]);
+            }
+          }
+          v[gq * 4] = x.x; v[gq * 4 + 1] = x.y; v[gq * 4 + 2] = x.z; v[gq * 4 + 3] = x.w;
+        }
+        *reinterpret_cast<uint4*>(c.sX + tile_off(row, ch * 8, K1)) = pack8(v);
+      }
+    }
+  };
+  // TMEM work[row][32*part, +32) -> relu(v + bias) -> fp16 -> smem
+  auto epi_relu = [&](TileCtx& c, const float* sBias, uint8_t* sOut) {
+    float v[32];
+    tmem_ld16(c.tWork + lane_sel + part * 32, v);
+    tmem_ld16(c.tWork + lane_sel + part * 32 + 16, v + 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c0 = part * 32 + cc * 8;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[cc * 8 + j] + (sBias ? sBias[c0 + j] : 0.f), 0.f);
+      *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, kHid)) = pack8(o);
+    }
+  };
+  auto epi_dz2 = [&](TileCtx& c) {  // dZ2 = (H2 > 0) * (dZ3 W3), in place over H2
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int c0 = part * 32 + ch * 8;
+      uint8_t* p = c.sH2 + tile_off(row, c0, kHid);
       float h2[8], o[8];
       unpack8(*reinterpret_cast<const uint4*>(p), h2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float gsum = dz[0] * sW3[c0 + j] + dz[1] * sW3[kHid + c0 + j] + dz[2] * sW3[2 * kHid + c0 + j];
-        o[j] = h2[j] > 0.f ? gsum : 0.f;
+        const float gs = c.dz[0] * sW3[c0 + j] + c.dz[1] * sW3[kHid + c0 + j] + c.dz[2] * sW3[2 * kHid + c0 + j];
+        o[j] = h2[j] > 0.f ? gs : 0.f;
       }
       *reinterpret_cast<uint4*>(p) = pack8(o);
     }
-    sync_for_mma();
-    if (tid == 0) {
-      gemm_mm(tdW2, smem_u32(sH2), kHid, smem_u32(sH1), kHid, kHid, kTile, !first);   // dW2 += dZ2^T H1
-      gemm_mm(tdB2, smem_u32(sH2), kHid, smem_u32(sOnes), 16, 16, kTile, !first);     // db2 += dZ2^T 1
-      gemm_km(tWork0, smem_u32(sH2), kHid, smem_u32(sW2), kHid, kHid, kHid, false);   // dH1 = dZ2 W2
-      mma_commit(ctx.bar);
-    }
-    mma_wait(ctx);
-    // dZ1 = (H1 > 0) * dH1, in place over H1
+  };
+  auto epi_dz1 = [&](TileCtx& c) {  // dZ1 = (H1 > 0) * dH1, in place over H1
+    float v[32];
+    tmem_ld16(c.tWork + lane_sel + part * 32, v);
+    tmem_ld16(c.tWork + lane_sel + part * 32 + 16, v + 16);
+    tmem_ld_wait();
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
-      const int c0 = half * 64 + cc * 16;
-      float v[16], h1[16];
-      tmem_ld16(tWork0 + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-      uint8_t* p0 = sH1 + tile_off(row, c0, kHid);
-      uint8_t* p1 = sH1 + tile_off(row, c0 + 8, kHid);
+      uint8_t* p0 = c.sH1 + tile_off(row, part * 32 + cc * 8, kHid);
+      float h1[8], o[8];
       unpack8(*reinterpret_cast<const uint4*>(p0), h1);
-      unpack8(*reinterpret_cast<const uint4*>(p1), h1 + 8);
-      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = h1[j] > 0.f ? v[j] : 0.f;
-      *reinterpret_cast<uint4*>(p0) = pack8(v);
-      *reinterpret_cast<uint4*>(p1) = pack8(v + 8);
+      for (int j = 0; j < 8; ++j) o[j] = h1[j] > 0.f ? v[cc * 8 + j] : 0.f;
+      *reinterpret_cast<uint4*>(p0) = pack8(o);
     }
-    sync_for_mma();
-    if (tid == 0) {
-      gemm_mm(tdW1, smem_u32(sH1), kHid, smem_u32(sX), K1, K1, kTile, !first);        // dW1~ += dZ1^T X~
-      gemm_km(tWork1, smem_u32(sH1), kHid, smem_u32(sW1), K1, 16, kHid, false);       // dX = dZ1 W1[:, :16]
-      mma_commit(ctx.bar);
-    }
-    mma_wait(ctx);
-    if (half == 0) {
+  };
+  auto epi_dx = [&](TileCtx& c) {
+    if (part == 0) {
       float v[16];
-      tmem_ld16(tWork1 + (static_cast<uint32_t>(q * 32) << 16), v);
+      tmem_ld16(c.tWork + lane_sel, v);
       tmem_ld_wait();
-      if (valid) {
-        float* __restrict__ o = d_feat + s * C;
-        for (int c = 0; c < C; ++c) o[c] = v[c] * inv_scale;
+      if (c.valid) {
+        float* __restrict__ o = d_feat + (c.s0 + row) * C;
+        for (int k = 0; k < C; ++k) o[k] = v[k] * inv_scale;
       }
     }
+  };
+  // MMA batches (thread 0 only)
+  auto issue_l1 = [&](TileCtx& c) {
+    gemm_kk(c.tWork, smem_u32(c.sX), K1, smem_u32(sW1), K1, kHid, K1, false);
+    mma_commit(c.bar.bar);
+  };
+  auto issue_l2 = [&](TileCtx& c) {
+    gemm_kk(c.tWork, smem_u32(c.sH1), kHid, smem_u32(sW2), kHid, kHid, kHid, false);
+    mma_commit(c.bar.bar);
+  };
+  auto issue_dw3 = [&](TileCtx& c, bool acc) {  // dW3^T [hidden j][c] += sum_s H2[s][j] dZ3[s][c]
+    gemm_mm(tdW3, smem_u32(c.sH2), kHid, smem_u32(c.sdZ3), 16, 16, kTile, acc);
+    mma_commit(c.bar.bar);
+  };
+  auto issue_l2b = [&](TileCtx& c, bool acc) {
+    gemm_mm(tdW2, smem_u32(c.sH2), kHid, smem_u32(c.sH1), kHid, kHid, kTile, acc);    // dW2 += dZ2^T H1
+    gemm_mm(tdB2, smem_u32(c.sH2), kHid, smem_u32(sOnes), 16, 16, kTile, acc);        // db2 += dZ2^T 1
+    gemm_km(c.tWork, smem_u32(c.sH2), kHid, smem_u32(sW2), kHid, kHid, kHid, false);  // dH1 = dZ2 W2
+    mma_commit(c.bar.bar);
+  };
+  auto issue_l1b = [&](TileCtx& c, bool acc) {
+    gemm_mm(tdW1, smem_u32(c.sH1), kHid, smem_u32(c.sX), K1, K1, kTile, acc);         // dW1~ += dZ1^T X~
+    gemm_km(c.tWork, smem_u32(c.sH1), kHid, smem_u32(sW1), K1, 16, kHid, false);      // dX = dZ1 W1[:, :16]
+    mma_commit(c.bar.bar);
+  };
+  TileCtx& A = cx[0];
+  TileCtx& B = cx[1];
+
+  for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    A.s0 = (2 * pair) * kTile;
+    B.s0 = (2 * pair + 1) * kTile;   // may lie past the count: then every row is invalid (all-zero tile)
+    stage(A);
+    stage(B);
+    sync_for_mma();
+    if (tid == 0) { issue_l1(A); issue_l1(B); }
+    mma_wait(A.bar); epi_relu(A, nullptr, A.sH1);
+    sync_for_mma();
+    if (tid == 0) issue_l2(A);
+    mma_wait(B.bar); epi_relu(B, nullptr, B.sH1);
+    sync_for_mma();
+    if (tid == 0) issue_l2(B);
+    mma_wait(A.bar); epi_relu(A, sB2, A.sH2);
+    sync_for_mma();
+    if (tid == 0) issue_dw3(A, !first);
+    mma_wait(B.bar); epi_relu(B, sB2, B.sH2);
+    sync_for_mma();
+    if (tid == 0) issue_dw3(B, true);
+    mma_wait(A.bar); epi_dz2(A);
+    sync_for_mma();
+    if (tid == 0) issue_l2b(A, !first);
+    mma_wait(B.bar); epi_dz2(B);
+    sync_for_mma();
+    if (tid == 0) issue_l2b(B, true);
+    mma_wait(A.bar); epi_dz1(A);
+    sync_for_mma();
+    if (tid == 0) issue_l1b(A, !first);
+    mma_wait(B.bar); epi_dz1(B);
+    sync_for_mma();
+    if (tid == 0) issue_l1b(B, true);
+    mma_wait(A.bar); epi_dx(A);
+    mma_wait(B.bar); epi_dx(B);
     first = false;
-    // buffers / TMEM work columns are re-used by the next tile after its first sync_for_mma()
     fence_before_sync();
-    __syncthreads();
+    __syncthreads();   // buffers and TMEM work columns are rewritten by the next pair
   }
 
-  // flush the TMEM-resident weight-gradient accumulators (rows = lanes = output feature n)
+  // flush the TMEM-resident weight-gradient accumulators (lane = output feature n)
   fence_after_sync();
   {
     const int n = row;
+    float v[32];
+    tmem_ld16(tdW2 + lane_sel + part * 32, v);
+    tmem_ld16(tdW2 + lane_sel + part * 32 + 16, v + 16);
+    tmem_ld_wait();
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c0 = half * 64 + cc * 16;
-      float v[16];
-      tmem_ld16(tdW2 + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) atomicAdd(g.W2 + n * kHid + c0 + j, v[j] * inv_scale);
-    }
-    if (half == 0) {
+    for (int j = 0; j < 32; ++j) atomicAdd(g.W2 + n * kHid + part * 32 + j, v[j] * inv_scale);
+    if (part == 0) {
       for (int c0 = 0; c0 < K1; c0 += 16) {
-        float v[16];
-        tmem_ld16(tdW1 + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        tmem_ld16(tdW1 + lane_sel + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -413,17 +541,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_kernel(
           else if (c == d_in) atomicAdd(g.b1 + n, v[j] * inv_scale);
         }
       }
-    } else {
-      float v[16];
-      tmem_ld16(tdW3 + (static_cast<uint32_t>(q * 32) << 16), v);  // dW3^T [j = n][c]
+    } else if (part == 1) {
+      tmem_ld16(tdW3 + lane_sel, v);  // dW3^T [j = n][c]
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < 3; ++c) atomicAdd(g.W3 + c * kHid + n, v[c] * inv_scale);
-      tmem_ld16(tdB2 + (static_cast<uint32_t>(q * 32) << 16), v);
+    } else if (part == 2) {
+      tmem_ld16(tdB2 + lane_sel, v);
       tmem_ld_wait();
       atomicAdd(g.b2 + n, v[0] * inv_scale);
     }
-    if (half == 0) {
+    if (part == 0) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float x = db3[c];
@@ -440,11 +568,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_bwd_kernel(
 
 static inline size_t mlp_fwd_smem(int K1) {
   return 1024 + ((tile_bytes(kHid, K1) + 1023) & ~1023u) + tile_bytes(kHid, kHid) + ((tile_bytes(kTile, K1) + 1023) & ~1023u) +
-         tile_bytes(kTile, kHid) + (3 * kHid + kHid + 4 + 3 * kTile) * sizeof(float) + 64;
+         tile_bytes(kTile, kHid) + (3 * kHid + kHid + 4 + 3 * kTile + 4 * kHid) * sizeof(float) + 64;
 }
 static inline size_t mlp_bwd_smem(int K1) {
-  return 1024 + ((tile_bytes(kHid, K1) + 1023) & ~1023u) + tile_bytes(kHid, kHid) + ((tile_bytes(kTile, K1) + 1023) & ~1023u) +
-         2 * tile_bytes(kTile, kHid) + 2 * ((tile_bytes(kTile, 16) + 1023) & ~1023u) + (3 * kHid + kHid + 4) * sizeof(float) + 64;
+  auto a1k = [](size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); };
+  const size_t ctx = a1k(tile_bytes(kTile, K1)) + 2 * a1k(tile_bytes(kTile, kHid)) + a1k(tile_bytes(kTile, 16));
+  return 1024 + a1k(tile_bytes(kHid, K1)) + a1k(tile_bytes(kHid, kHid)) + a1k(tile_bytes(kTile, 16)) + 2 * ctx +
+         (3 * kHid + kHid + 4) * sizeof(float) + 64;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -583,46 +713,48 @@ DVGO_API int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, i
   return launch_status();
 }
 
-static inline int mlp_k1(int d_in) { return ((d_in + 1 + 15) / 16) * 16; }
+static inline int mlp_k1(int C, int pe_stride) { return ((C + pe_stride + 15) / 16) * 16; }
 
-DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P,
+DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                           const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                           const float* W2, const float* b2, const float* W3, const float* b3, int width, float* rgb,
                           dvgo_stream_t stream) {
-  if (width != kHid || C < 0 || P < 0 || C + P < 1 || C + P > 63 || surv_cap < 0) return DVGO_EINVAL;
+  if (width != kHid || C < 0 || P < 0 || C + P < 1 || C + P > 63 || surv_cap < 0 || pe_stride < P + 1) return DVGO_EINVAL;
   if (!feat || !s_ray || (P > 0 && !pe) || !counters || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !rgb)
     return DVGO_EINVAL;
   if (surv_cap == 0) return 0;
-  const int K1 = mlp_k1(C + P);
+  const int K1 = mlp_k1(C, pe_stride);
   const size_t bytes = mlp_fwd_smem(K1);
   cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int64_t tiles = (surv_cap + kTile - 1) / kTile;
   const int grid = static_cast<int>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
   MlpW w{W1, b1, W2, b2, W3, b3};
-  mlp_fwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, rgb);
+  mlp_fwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, pe_stride, rgb);
   return launch_status();
 }
 
-DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P,
+DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                           const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                           const float* W2, const float* b2, const float* W3, const float* b3, int width,
                           const float* rgb, const float* d_rgb, float grad_scale, float* d_feat, float* gW1,
                           float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, dvgo_stream_t stream) {
-  if (width != kHid || C < 1 || C > 16 || P < 0 || C + P > 63 || surv_cap < 0 || !(grad_scale > 0.f)) return DVGO_EINVAL;
+  if (width != kHid || C < 1 || C > 16 || P < 0 || C + P > 63 || surv_cap < 0 || !(grad_scale > 0.f) || pe_stride < P + 1)
+    return DVGO_EINVAL;
   if (!feat || !s_ray || (P > 0 && !pe) || !counters || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !rgb || !d_rgb ||
       !d_feat || !gW1 || !gb1 || !gW2 || !gb2 || !gW3 || !gb3)
     return DVGO_EINVAL;
   if (surv_cap == 0) return 0;
-  const int K1 = mlp_k1(C + P);
+  const int K1 = mlp_k1(C, pe_stride);
   const size_t bytes = mlp_bwd_smem(K1);
   cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int64_t tiles = (surv_cap + kTile - 1) / kTile;
-  const int grid = static_cast<int>(tiles < kNumSMs ? tiles : kNumSMs);
+  const int64_t pairs = (tiles + 1) / 2;
+  const int grid = static_cast<int>(pairs < kNumSMs ? pairs : kNumSMs);
   MlpW w{W1, b1, W2, b2, W3, b3};
   MlpG g{gW1, gb1, gW2, gb2, gW3, gb3};
-  mlp_bwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, rgb,
-                                                                 d_rgb, grad_scale, d_feat, g);
+  mlp_bwd_kernel<<<grid, kBwdThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, pe_stride,
+                                                                 rgb, d_rgb, grad_scale, d_feat, g);
   return launch_status();
 }

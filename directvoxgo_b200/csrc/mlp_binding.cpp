@@ -52,33 +52,33 @@ inline Offsets offsets(int d_in, int width) {
   return o;
 }
 
-void mlp_fwd(Tensor feat, Tensor s_ray, Tensor pe, Tensor counters, Tensor params, int width, Tensor rgb) {
+void mlp_fwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb) {
   chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
   chkf(rgb, "rgb");
-  const int C = feat.size(1), P = pe.size(1);
+  const int C = feat.size(1), pe_stride = pe.size(1);
   const Offsets o = offsets(C + P, width);
   TORCH_CHECK(params.numel() == o.total, "params has the wrong size");
   const int64_t cap = s_ray.numel();
   TORCH_CHECK(feat.size(0) >= cap && rgb.numel() >= cap * 3, "stream buffers too small");
   const c10::cuda::CUDAGuard guard(feat.device());
   const float* p = params.data_ptr<float>();
-  rc_check(dvgo_mlp_fwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P,
+  rc_check(dvgo_mlp_fwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
                         counters.data_ptr<int32_t>(), cap, p + o.W1, p + o.b1, p + o.W2, p + o.b2, p + o.W3, p + o.b3,
                         width, rgb.data_ptr<float>(), cur_stream()), "mlp_fwd");
 }
 
-void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, Tensor counters, Tensor params, int width, Tensor rgb, Tensor d_rgb,
+void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb, Tensor d_rgb,
              double grad_scale, Tensor d_feat, Tensor grads) {
   chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
   chkf(rgb, "rgb"); chkf(d_rgb, "d_rgb"); chkf(d_feat, "d_feat"); chkf(grads, "grads");
-  const int C = feat.size(1), P = pe.size(1);
+  const int C = feat.size(1), pe_stride = pe.size(1);
   const Offsets o = offsets(C + P, width);
   TORCH_CHECK(params.numel() == o.total && grads.numel() == o.total, "params/grads have the wrong size");
   const int64_t cap = s_ray.numel();
   const c10::cuda::CUDAGuard guard(feat.device());
   const float* p = params.data_ptr<float>();
   float* g = grads.data_ptr<float>();
-  rc_check(dvgo_mlp_bwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P,
+  rc_check(dvgo_mlp_bwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
                         counters.data_ptr<int32_t>(), cap, p + o.W1, p + o.b1, p + o.W2, p + o.b2, p + o.W3, p + o.b3,
                         width, rgb.data_ptr<float>(), d_rgb.data_ptr<float>(), static_cast<float>(grad_scale),
                         d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3,

@@ -172,7 +172,7 @@ class FusedRenderer(_FusedBase):
         from .fused_mlp import TensorCoreMLP
         if not hasattr(self, "_tc"):
             self._tc = TensorCoreMLP(self.model.rgbnet, self.device)
-        pe = view_embedding(viewdirs, self.model.viewfreq).contiguous()
+        pe = self._tc.pad_embedding(view_embedding(viewdirs, self.model.viewfreq))
         self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
 
 
@@ -198,6 +198,7 @@ class FusedTrainer(_FusedBase):
         skip = self.cfg.get("skip_zero_grad_fields", []) or []
         self.masked = {k: (k in skip) for k in ("density", "k0")}
         self.rgbnet_state = {}
+        self.stage_events = None  # set to {} to record per-stage CUDA events (bench.py roofline pass)
         if model.rgbnet is not None and self.mlp_mode == "tc":
             from .fused_mlp import TensorCoreMLP
             self._tc = TensorCoreMLP(model.rgbnet, self.device, train=True)
@@ -205,6 +206,21 @@ class FusedTrainer(_FusedBase):
     def set_pervoxel_lr(self, count):
         """View-count learning-rate table for the density grid (lib/masked_adam.py:35-37)."""
         self.per_lr = (count.float() / count.max()).reshape(self.X, self.Y, self.Z).contiguous()
+
+    def _mark(self, name):
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.setdefault(name, []).append(ev)
+
+    def stage_times_ms(self):
+        """Average duration of each stage between consecutive marks (after a synchronize)."""
+        names = list(self.stage_events.keys())
+        out = {}
+        for a, b in zip(names[:-1], names[1:]):
+            ts = [x.elapsed_time(y) for x, y in zip(self.stage_events[a], self.stage_events[b])]
+            out[b] = sum(ts) / max(len(ts), 1)
+        return out
 
     # -- the step -----------------------------------------------------------------------------------
     def step(self, rays_o, rays_d, viewdirs, target):
@@ -214,7 +230,9 @@ class FusedTrainer(_FusedBase):
         self.global_step += 1
         ws = self._workspace(n, True)
         rays_o, rays_d, target = rays_o.contiguous(), rays_d.contiguous(), target.contiguous()
+        self._mark("start")
         self._march(ws, rays_o, rays_d)
+        self._mark("march_fwd")
 
         w_main = float(cfg.get("weight_main", 1.0))
         w_ent = float(cfg.get("weight_entropy_last", 0.0))
@@ -233,9 +251,12 @@ class FusedTrainer(_FusedBase):
             after_rgb()
             ext.rgb_direct_bwd(ws.rgb, ws.d_rgb, ws.counters, ws.d_feat)
         elif self.mlp_mode == "tc":
-            pe = view_embedding(viewdirs, model.viewfreq).contiguous()
+            pe = self._tc.pad_embedding(view_embedding(viewdirs, model.viewfreq))
+            self._mark("embed")
             self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
+            self._mark("mlp_fwd")
             after_rgb()
+            self._mark("loss")
             self._tc.backward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb, ws.d_rgb, ws.d_feat, n_global)
         else:
             m4 = int(ws.counters[0].item())  # parity mode: one host read of the survivor count
@@ -249,25 +270,27 @@ class FusedTrainer(_FusedBase):
                 rgb.backward(ws.d_rgb[:m4])
                 ws.d_feat[:m4].copy_(feat.grad)
 
+        self._mark("mlp_bwd")
         ext.march_bwd(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T,
                       ws.slot_expd, ws.slot_code, ws.d_feat, ws.d_w, ws.alphainv_last, ws.g_last, self.g_density,
                       self.g_k0)
+        self._mark("march_bwd")
         if self.world_size > 1:
             self._allreduce()
+            self._mark("allreduce")
         self._optimise(n_global)
+        self._mark("sweep")
         return ws.loss_acc[0].clone()
 
     def _allreduce(self):
-        import torch.distributed as dist
-        dist.all_reduce(self.g_density, group=self.dist_group)
-        dist.all_reduce(self.g_k0, group=self.dist_group)
+        from .parallel import allreduce_sum_
+        bufs = [self.g_density, self.g_k0]
         if self.model.rgbnet is not None:
             if self.mlp_mode == "tc":
-                dist.all_reduce(self._tc.grad_flat, group=self.dist_group)
+                bufs.append(self._tc.grad_flat)
             else:
-                for p in self.model.rgbnet.parameters():
-                    if p.grad is not None:
-                        dist.all_reduce(p.grad, group=self.dist_group)
+                bufs += [p.grad for p in self.model.rgbnet.parameters() if p.grad is not None]
+        allreduce_sum_(bufs, self.dist_group)
 
     def _tv_now(self):
         cfg, gs = self.cfg, self.global_step

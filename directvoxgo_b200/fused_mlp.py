@@ -30,15 +30,27 @@ class TensorCoreMLP:
         flat = [t.detach().reshape(-1) for l in self.lin for t in (l.weight, l.bias)]
         self.params.copy_(torch.cat(flat))
 
-    def forward(self, feat, s_ray, pe, counters, rgb):
-        ext.mlp_fwd(feat, s_ray, pe, counters, self.params, self.WIDTH, rgb)
+    def pad_embedding(self, pe):
+        """[N,P] view embedding -> [N,P_pad] table: column P = 1 (carries b1 through the first GEMM), then
+        zeros up to a multiple of 4 floats (16-byte loads in the kernel)."""
+        n, P = pe.shape
+        stride = (P + 1 + 3) // 4 * 4
+        out = torch.zeros(n, stride, dtype=pe.dtype, device=pe.device)
+        out[:, :P] = pe
+        out[:, P] = 1.0
+        self._P = P
+        return out
 
-    def backward(self, feat, s_ray, pe, counters, rgb, d_rgb, d_feat, n_global):
+    def forward(self, feat, s_ray, pe_pad, counters, rgb):
+        ext.mlp_fwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb)
+
+    def backward(self, feat, s_ray, pe_pad, counters, rgb, d_rgb, d_feat, n_global):
         """Accumulates weight gradients into self.grad_flat (zeroed here) and writes d_feat."""
         ext.zero_(self.grad_flat)
         # d_rgb <= ~2/(3 n_global): scale so that the largest FP16 backward operand is O(100)
         scale = 2.0 ** math.floor(math.log2(256.0 * n_global))
-        ext.mlp_bwd(feat, s_ray, pe, counters, self.params, self.WIDTH, rgb, d_rgb, scale, d_feat, self.grad_flat)
+        ext.mlp_bwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb, d_rgb,
+                    scale, d_feat, self.grad_flat)
 
     def adam_step(self, step, beta1, beta2, lr, eps):
         adam_upd_cuda.adam_upd(self.params, self.grad_flat, self.exp_avg, self.exp_avg_sq, step, beta1, beta2, lr, eps)

@@ -149,10 +149,12 @@ int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G, dvgo_s
 /* rgbnet on the tensor cores (fused_mlp.cu): x = [feat (C) | pe[s_ray] (P)] -> Linear(C+P, 128) -> ReLU
  * -> Linear(128,128) -> ReLU -> Linear(128,3) -> sigmoid   (lib/dvgo.py:123-131, :524-539 with
  * rgbnet_direct=True, rgbnet_depth=3, rgbnet_width=128 -- the configs' default).
- * feat [surv_cap,C], s_ray [surv_cap] int32, pe [n_rays,P] (per-ray view embedding), counters[0] = M4.
+ * feat [surv_cap,C], s_ray [surv_cap] int32, counters[0] = M4.  pe [n_rays, pe_stride] is the per-ray view
+ * embedding table padded so that column P holds the constant 1 (it carries b1 through the first GEMM) and the
+ * remaining columns are 0; pe_stride >= P+1, a multiple of 4 enables 16-byte loads.
  * Weights are fp32 in torch nn.Linear layout ([out][in]); GEMM operands are rounded to FP16, accumulation
  * is fp32.  rgb [surv_cap,3].  width must be 128 (DVGO_EINVAL otherwise: the caller falls back). */
-int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P,
+int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                  const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
                  const float* b2, const float* W3, const float* b3, int width, float* rgb,
                  dvgo_stream_t stream);
@@ -160,7 +162,7 @@ int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe
  * (accumulated in TMEM per CTA, flushed with atomics; the caller zeroes them).  d_rgb = dL/d(rgb) (after
  * the sigmoid).  grad_scale: power of two applied to the FP16 backward operands and removed exactly in
  * the fp32 epilogues. */
-int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P,
+int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                  const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
                  const float* b2, const float* W3, const float* b3, int width, const float* rgb,
                  const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,

@@ -141,12 +141,16 @@ class RefDVGO:
         return ret
 
     @staticmethod
-    def loss(ret, target, n_rays, weight_main=1.0, weight_entropy_last=0.0, weight_rgbper=0.0):
-        """run.py:377-386."""
-        loss = weight_main * F.mse_loss(ret["rgb_marched"], target)
+    def loss(ret, target, n_rays, weight_main=1.0, weight_entropy_last=0.0, weight_rgbper=0.0, n_global=None):
+        """run.py:377-386.  With n_global (ray-sharded data parallel) every mean runs over the GLOBAL batch:
+        this rank's share of the loss is returned and n_rays is ignored."""
+        share = 1.0 if n_global is None else len(target) / n_global
+        if n_global is not None:
+            n_rays = n_global
+        loss = weight_main * F.mse_loss(ret["rgb_marched"], target) * share
         if weight_entropy_last > 0:
             pout = ret["alphainv_last"].clamp(1e-6, 1 - 1e-6)
-            ent = -(pout * torch.log(pout) + (1 - pout) * torch.log(1 - pout)).mean()
+            ent = -(pout * torch.log(pout) + (1 - pout) * torch.log(1 - pout)).mean() * share
             loss = loss + weight_entropy_last * ent
         if weight_rgbper > 0:
             rgbper = (ret["raw_rgb"] - target[ret["ray_id"]]).pow(2).sum(-1)

@@ -64,7 +64,7 @@ def test_tc_mlp_forward(M, C, P):
     feat, pe, s_ray, counters, cap = _stream(M, 257, C, P, M)
     tc = TensorCoreMLP(net, DEV)
     rgb = torch.full((cap, 3), -7.0, device=DEV)
-    tc.forward(feat, s_ray, pe, counters, rgb)
+    tc.forward(feat, s_ray, tc.pad_embedding(pe), counters, rgb)
     torch.cuda.synchronize()
     x = torch.cat([feat[:M], pe[s_ray[:M].long()]], -1)
     with torch.no_grad():
@@ -116,8 +116,9 @@ def test_tc_mlp_backward(M, n_global):
     tc = TensorCoreMLP(net, DEV, train=True)
     rgb = torch.zeros(cap, 3, device=DEV)
     d_feat = torch.full((cap, C), 3.0, device=DEV)
-    tc.forward(feat, s_ray, pe, counters, rgb)
-    tc.backward(feat, s_ray, pe, counters, rgb, d_rgb, d_feat, n_global)
+    pe_pad = tc.pad_embedding(pe)
+    tc.forward(feat, s_ray, pe_pad, counters, rgb)
+    tc.backward(feat, s_ray, pe_pad, counters, rgb, d_rgb, d_feat, n_global)
     torch.cuda.synchronize()
     assert torch.all(d_feat[M:] == 3.0)
     got = tc.unflatten(tc.grad_flat)
