@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "train rays/s (fwd+bwd+TV+MaskedAdam) @160^3 fine stage"
+WORKLOAD = "DVGO fine stage %d^3 density + 12ch k0 + rgbnet(128), 8192 rays/iter/GPU, fwd+bwd+TV(dense)+MaskedAdam"
 N_RAYS = 8192
 N_BATCHES = 16  # distinct ray batches cycled through (each step sees different incoherent rays)
 
@@ -32,8 +33,8 @@ N_BATCHES = 16  # distinct ray batches cycled through (each step sees different 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default=os.environ.get("DVGO_BENCH_PATH", "auto"),
                     choices=["auto", "fused", "module"], help="fused B200 trainer or op-by-op module path")
@@ -166,7 +167,8 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": rays_s, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "DVGO fine stage %d^3 + 12ch k0 + rgbnet(128), 8192 rays/iter, fwd+bwd+TV+MaskedAdam" % args.grid},
+            "config": {"workload": WORKLOAD % args.grid, "rays_per_step_per_gpu": N_RAYS,
+                       "sample": "each timed step = a %d-ray slice of the 8192-ray step" % n_rays},
             "cpu_baseline": {"value": rays_s, "unit": "rays/s", "cores": threads, "kind": "port",
                              "sample": "%d-ray slice of the 8192-ray step on the full %d^3 grid, %d step(s); "
                                        "reference CUDA ops have no CPU path, so this is oracle/model_ref.py" % (n_rays, args.grid, steps)},
@@ -230,7 +232,6 @@ def run_ours(args):
     barrier()
     launches = pkg._C.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
     t = torch.tensor([ms], device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -255,17 +256,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / args.steps
+    clocks = sampler.stop()  # sampled across both timed regions (device-resident and end-to-end)
     h2d = sum(x.numel() * x.element_size() for x in host_batches[0])
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    hbm_peak, tensor_peak, peak_kind = peaks()
-    # Roofline of the dominant kernel.  Per-stage device times come from CUDA events recorded on the
-    # launching stream around each stage of extra (untimed-region) steps; the dominant stage is one kernel.
-    roof, stages = None, None
+    # Per-stage device times: CUDA events recorded on the launching stream around each stage of extra steps
+    # (outside the timed regions).  EVERY rank runs them -- the steps contain collectives when world > 1.
+    stages = None
     if path == "fused" and hasattr(trainer, "stage_events"):
         trainer.stage_events = {}
         for i in range(10):
@@ -273,6 +269,16 @@ def run_ours(args):
         torch.cuda.synchronize()
         stages = trainer.stage_times_ms()
         trainer.stage_events = None
+    barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tensor_peak, peak_kind = peaks()
+    # Roofline of the dominant kernel (the dominant stage is a single kernel).
+    roof = None
+    if stages is not None:
         M = balg["M0"]
         C = model.k0.shape[1]
         G = balg["G"]
@@ -334,8 +340,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (grids, sampling, compositing, Adam); rgbnet GEMM operands fp16, fp32 accumulate",
         "data": "synthetic",
-        "config": {"workload": "DVGO fine stage %d^3 density + 12ch k0 + rgbnet(128), 8192 rays/iter/GPU, "
-                               "fwd+bwd+TV(dense)+MaskedAdam" % args.grid,
+        "config": {"workload": WORKLOAD % args.grid,
                    "rays_per_step_per_gpu": N_RAYS, "path": path, "rgbnet": getattr(trainer, "mlp_mode", "torch"), "parallelism": "ray-sharded dp%d" % world,
                    "samples_per_step": balg["M0"], "unique_voxels_touched": balg["U"],
                    "l2_policy": "working set (params+grads+Adam state = %.2f GB) larger than the 126 MB L2; "

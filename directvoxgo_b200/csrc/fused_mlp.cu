@@ -23,7 +23,7 @@ using namespace tc;
 // half = warp/4) owns one sample row of the tile and half of the 128 hidden columns (a warp can only
 // read its own 32-lane quarter of TMEM, so warps w and w+4 split the columns of the same rows).
 //   layers 1, 2 : tcgen05.mma, A = activations [sample][feature] (K-major), B = weights [out][in]
-//   layer 3     : fp32 SIMT dot products fused into the layer-2 epilogue (3 outputs -> no MMA tile)
+//   layer 3     : a third MMA with N = 16 (3 outputs used); sigmoid in its 16-column epilogue
 //   b1 is folded into W1 as column d_in of the augmented input (the constant-1 feature).
 // ----------------------------------------------------------------------------------------------------
 constexpr int kHid = 128;
@@ -47,6 +47,24 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
   for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+}
+
+// fp32 x8 -> relu -> fp16 x8, with the max done on packed halves (HMNMX2: one instruction per two values)
+__device__ __forceinline__ uint4 pack8_relu(const float* v) {
+  __half2 h[4];
+  const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) h[q] = __hmax2(__floats2half2_rn(v[2 * q], v[2 * q + 1]), z);
+  return *reinterpret_cast<uint4*>(h);
+}
+// out = (act > 0) ? v : 0 on packed halves: HSET2.GT gives 1.0/0.0, one HMUL2 applies the mask
+__device__ __forceinline__ uint4 pack8_masked(const float* v, const uint4& act) {
+  __half2 h[4];
+  const __half2* a = reinterpret_cast<const __half2*>(&act);
+  const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) h[q] = __hmul2(__floats2half2_rn(v[2 * q], v[2 * q + 1]), __hgt2(a[q], z));
+  return *reinterpret_cast<uint4*>(h);
 }
 
 // Weights -> fp16 canonical tiles (sW1 [128 x K1] incl. the bias column, sW2 [128 x 128]) and the
@@ -167,9 +185,7 @@ __device__ __forceinline__ void epi_relu_to_smem(uint32_t tmem_d, int q, int row
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = v[cc * 8 + j];
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-    *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, kHid)) = pack8(o);
+    *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, kHid)) = pack8_relu(o);
   }
 }
 
@@ -198,14 +214,16 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
   float* sW3 = reinterpret_cast<float*>(sH1 + align1k(tile_bytes(kTile, kHid)));
   float* sB2 = sW3 + 3 * kHid;
   float* sB3 = sB2 + kHid;
-  float* sPart = sB3 + 4;  // [128][3] partial layer-3 sums of the upper column half
-  float4* sL3 = reinterpret_cast<float4*>(sPart + 3 * kTile);  // [128] {W3[0][j], W3[1][j], W3[2][j], b2[j]}
+  uint8_t* sW3k = reinterpret_cast<uint8_t*>(sB3 + 4);  // [16 out (3 used)][128 hidden] fp16: K-major B of layer 3
+  sW3k += (128u - (smem_u32(sW3k) & 127u)) & 127u;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
   if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init_fence(); }
   load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3);
-  for (int j = tid; j < kHid; j += blockDim.x)
-    sL3[j] = make_float4(w.W3[j], w.W3[kHid + j], w.W3[2 * kHid + j], w.b2[j]);
+  for (int i = tid; i < 16 * kHid; i += blockDim.x) {
+    const int c = i / kHid, j = i % kHid;
+    *reinterpret_cast<__half*>(sW3k + tile_off(c, j, kHid)) = __float2half_rn(c < 3 ? w.W3[c * kHid + j] : 0.f);
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -229,33 +247,27 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
       mma_commit(ctx.bar);
     }
     mma_wait(ctx);
-    // layer-2 epilogue fused with layer 3 (fp32 SIMT): acc_c = sum_j relu(z2_j + b2_j) * W3[c][j]
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    {
-      float v[64];
-      tmem_ld64(tD2 + (static_cast<uint32_t>(q * 32) << 16) + half * 64, v);
+    // layer-2 epilogue: H2 = relu(z2 + b2) as fp16, in place over H1 (the layer-2 MMA has finished reading it)
+    epi_relu_to_smem(tD2, q, row, half * 64, sB2, sH1);
+    sync_for_mma();
+    if (tid == 0) {  // layer 3 on the tensor core as well: [128 x 128] x [128 x 16] (3 outputs used)
+      gemm_kk(tD1, smem_u32(sH1), kHid, smem_u32(sW3k), kHid, 16, kHid, false);
+      mma_commit(ctx.bar);
+    }
+    mma_wait(ctx);
+    if (half == 0) {
+      float v[16];
+      tmem_ld16(tD1 + (static_cast<uint32_t>(q * 32) << 16), v);
+      tmem_ld_wait();
+      if (s0 + row < count) {
+        float* __restrict__ o = rgb + (s0 + row) * 3;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float4 t = sL3[half * 64 + j];  // one broadcast 16-byte load per hidden unit
-        const float hv = fmaxf(v[j] + t.w, 0.f);
-        a0 = fmaf(hv, t.x, a0);
-        a1 = fmaf(hv, t.y, a1);
-        a2 = fmaf(hv, t.z, a2);
+        for (int c = 0; c < 3; ++c) o[c] = 1.f / (1.f + expf(-(v[c] + sB3[c])));
       }
     }
-    if (half == 1) { sPart[row * 3] = a0; sPart[row * 3 + 1] = a1; sPart[row * 3 + 2] = a2; }
     fence_before_sync();
     __syncthreads();
-    if (half == 0 && s0 + row < count) {
-      const float z0 = a0 + sPart[row * 3] + sB3[0];
-      const float z1 = a1 + sPart[row * 3 + 1] + sB3[1];
-      const float z2 = a2 + sPart[row * 3 + 2] + sB3[2];
-      float* __restrict__ o = rgb + (s0 + row) * 3;
-      o[0] = 1.f / (1.f + expf(-z0));
-      o[1] = 1.f / (1.f + expf(-z1));
-      o[2] = 1.f / (1.f + expf(-z2));
-    }
-    // sPart / sX / sH1 / TMEM are re-used by the next tile only after the next sync_for_mma()
+    // sX / sH1 / TMEM are re-used by the next tile
   }
   fence_before_sync();
   __syncthreads();
@@ -265,7 +277,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
 // ---- backward (with forward recompute) ---------------------------------------------------------------
 // Per tile: recompute H1, H2 (as in forward); dZ3 = d_rgb * rgb (1-rgb) * S; then
 //   dW3^T += H2^T dZ3      (MMA, A = H2 MN-major, B = dZ3 MN-major, N = 16)
-//   dZ2    = (H2 > 0) * (dZ3 W3)                                   (SIMT epilogue, in place over H2)
+//   dH2    = dZ3 W3 (MMA, K = 16) ; dZ2 = (H2 > 0) * dH2           (epilogue, in place over H2)
 //   dW2   += dZ2^T H1 ;  db2 += dZ2^T 1 ;  dH1 = dZ2 W2            (MMAs)
 //   dZ1    = (H1 > 0) * dH1                                        (epilogue, in place over H1)
 //   dW1~  += dZ1^T X~   (column d_in of the augmented input gives db1) ;  dX = dZ1 W1[:, :16]   (MMAs)
@@ -277,15 +289,21 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
 // Pipelining: the five MMA batches of a tile are separated by SIMT epilogues that depend on them, so a
 // single tile leaves the tensor pipe idle ~85% of the time (measured, profiles/r01_*).  Each CTA
 // therefore works on TWO tiles (contexts A and B, each with its own activation buffers, TMEM work
-// columns and mbarrier) in an interleaved schedule: while all 512 threads run the epilogue of one
-// context, the MMA batch of the other is in flight.  One thread issues every MMA in program order, so
-// both contexts can accumulate into the same TMEM weight-gradient columns.
-constexpr int kBwdThreads = 512;
+// columns and mbarriers) and is warp-specialised: 16 epilogue warps alternate between the two contexts
+// while a dedicated issuer warp feeds the tensor core, so descriptor building / MMA issue of one
+// context overlaps the epilogue of the other.  Hand-offs are mbarriers only (no __syncthreads in the
+// loop): ready[ctx] (512 epilogue arrivals -> issuer may read the smem tiles / overwrite the TMEM work
+// columns) and full[ctx] (tcgen05.commit -> epilogue may read TMEM / overwrite the tiles in place).
+// One thread issues every MMA in program order, so both contexts can accumulate into the same TMEM
+// weight-gradient columns.
+constexpr int kBwdEpiThreads = 512;               // 16 epilogue warps: (row quarter q) x (32-column part)
+constexpr int kBwdThreads = kBwdEpiThreads + 32;  // + one MMA-issuer warp
 
 struct TileCtx {
   uint8_t* sX; uint8_t* sH1; uint8_t* sH2; uint8_t* sdZ3;
   uint32_t tWork;
-  MmaCtx bar;
+  MmaCtx bar;     // full[ctx]: MMA batch complete
+  MmaCtx ready;   // ready[ctx]: epilogue output in place
   int64_t s0;
   float dz[3];
   bool valid;
@@ -297,10 +315,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     const float* __restrict__ rgb, const float* __restrict__ d_rgb, float grad_scale, float* __restrict__ d_feat,
     MlpG g) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[4];  // full[0], full[1], ready[0], ready[1]
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, part = warp >> 2, row = q * 32 + lane;  // part in 0..3: 32 hidden columns each
+  const bool is_issuer = warp == kBwdEpiThreads / 32;
+  const int q = warp & 3, part = (warp >> 2) & 3, row = q * 32 + lane;  // part in 0..3: 32 hidden columns each
   const int d_in = C + P;
   int64_t count = counters[0];
   if (count > surv_cap) count = surv_cap;
@@ -312,7 +331,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   uint8_t* sW1 = base;
   uint8_t* sW2 = sW1 + align1k(tile_bytes(kHid, K1));
   uint8_t* sOnes = sW2 + align1k(tile_bytes(kHid, kHid));
-  uint8_t* ctx_base = sOnes + align1k(tile_bytes(kTile, 16));
+  uint8_t* sW3t = sOnes + align1k(tile_bytes(kTile, 16));   // [128 hidden j][16: c < 3] = W3^T, K-major B of dH2
+  uint8_t* ctx_base = sW3t + align1k(tile_bytes(kHid, 16));
   const size_t ctx_bytes = align1k(tile_bytes(kTile, K1)) + 2 * align1k(tile_bytes(kTile, kHid)) +
                            align1k(tile_bytes(kTile, 16));
   float* sW3 = reinterpret_cast<float*>(ctx_base + 2 * ctx_bytes);
@@ -320,10 +340,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   float* sB3 = sB2 + kHid;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
-  if (tid == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_init_fence(); }
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), kBwdEpiThreads);
+    mbar_init(smem_u32(&bars[3]), kBwdEpiThreads);
+    mbar_init_fence();
+  }
   load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3);
-  for (int i = tid; i < kTile * 16; i += blockDim.x)  // ones in column 0: db2 = dZ2^T * ones
+  for (int i = tid; i < kTile * 16; i += blockDim.x) {  // ones in column 0: db2 = dZ2^T * ones
     *reinterpret_cast<__half*>(sOnes + tile_off(i / 16, i % 16, 16)) = __float2half_rn((i % 16) == 0 ? 1.f : 0.f);
+    const int j = i / 16, c = i % 16;
+    *reinterpret_cast<__half*>(sW3t + tile_off(j, c, 16)) = __float2half_rn(c < 3 ? w.W3[c * kHid + j] : 0.f);
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -339,6 +368,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     cx[i].sdZ3 = cx[i].sH2 + align1k(tile_bytes(kTile, kHid));
     cx[i].tWork = tmem + 128 * i;
     cx[i].bar = MmaCtx{smem_u32(&bars[i]), 0u};
+    cx[i].ready = MmaCtx{smem_u32(&bars[2 + i]), 0u};
   }
   const float inv_scale = 1.f / grad_scale;
   const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
@@ -369,7 +399,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     }
     // X~: thread (r = tid & 127, h = tid >> 7) fills 16-byte chunks h, h+4, ...
     {
-      const int h = tid >> 7;
+      const int h = part;
       const float* __restrict__ f = feat + s * C;
       const float* __restrict__ e = pe + static_cast<int64_t>(c.valid ? s_ray[s] : 0) * pe_stride;
       const bool vec = ((C | pe_stride) & 3) == 0;
@@ -405,43 +435,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     tmem_ld16(c.tWork + lane_sel + part * 32, v);
     tmem_ld16(c.tWork + lane_sel + part * 32 + 16, v + 16);
     tmem_ld_wait();
+    if (sBias) {
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c0 = part * 32 + cc * 8;
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[cc * 8 + j] + (sBias ? sBias[c0 + j] : 0.f), 0.f);
-      *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, kHid)) = pack8(o);
-    }
-  };
-  auto epi_dz2 = [&](TileCtx& c) {  // dZ2 = (H2 > 0) * (dZ3 W3), in place over H2
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      const int c0 = part * 32 + ch * 8;
-      uint8_t* p = c.sH2 + tile_off(row, c0, kHid);
-      float h2[8], o[8];
-      unpack8(*reinterpret_cast<const uint4*>(p), h2);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gs = c.dz[0] * sW3[c0 + j] + c.dz[1] * sW3[kHid + c0 + j] + c.dz[2] * sW3[2 * kHid + c0 + j];
-        o[j] = h2[j] > 0.f ? gs : 0.f;
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b = *reinterpret_cast<const float4*>(sBias + part * 32 + j4 * 4);
+        v[j4 * 4] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
       }
-      *reinterpret_cast<uint4*>(p) = pack8(o);
     }
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      *reinterpret_cast<uint4*>(sOut + tile_off(row, part * 32 + cc * 8, kHid)) = pack8_relu(v + cc * 8);
   };
-  auto epi_dz1 = [&](TileCtx& c) {  // dZ1 = (H1 > 0) * dH1, in place over H1
+  // out = (act > 0) * TMEM work, in place over the activation tile (dZ2 over H2, dZ1 over H1)
+  auto epi_mask = [&](TileCtx& c, uint8_t* sAct) {
     float v[32];
     tmem_ld16(c.tWork + lane_sel + part * 32, v);
     tmem_ld16(c.tWork + lane_sel + part * 32 + 16, v + 16);
     tmem_ld_wait();
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
-      uint8_t* p0 = c.sH1 + tile_off(row, part * 32 + cc * 8, kHid);
-      float h1[8], o[8];
-      unpack8(*reinterpret_cast<const uint4*>(p0), h1);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = h1[j] > 0.f ? v[cc * 8 + j] : 0.f;
-      *reinterpret_cast<uint4*>(p0) = pack8(o);
+      uint4* p = reinterpret_cast<uint4*>(sAct + tile_off(row, part * 32 + cc * 8, kHid));
+      *p = pack8_masked(v + cc * 8, *p);
     }
   };
   auto epi_dx = [&](TileCtx& c) {
@@ -464,8 +478,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     gemm_kk(c.tWork, smem_u32(c.sH1), kHid, smem_u32(sW2), kHid, kHid, kHid, false);
     mma_commit(c.bar.bar);
   };
-  auto issue_dw3 = [&](TileCtx& c, bool acc) {  // dW3^T [hidden j][c] += sum_s H2[s][j] dZ3[s][c]
-    gemm_mm(tdW3, smem_u32(c.sH2), kHid, smem_u32(c.sdZ3), 16, 16, kTile, acc);
+  auto issue_dw3 = [&](TileCtx& c, bool acc) {
+    gemm_mm(tdW3, smem_u32(c.sH2), kHid, smem_u32(c.sdZ3), 16, 16, kTile, acc);   // dW3^T += H2^T dZ3
+    gemm_kk(c.tWork, smem_u32(c.sdZ3), 16, smem_u32(sW3t), 16, kHid, 16, false);  // dH2 = dZ3 W3  (K = 16)
     mma_commit(c.bar.bar);
   };
   auto issue_l2b = [&](TileCtx& c, bool acc) {
@@ -481,48 +496,59 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   };
   TileCtx& A = cx[0];
   TileCtx& B = cx[1];
-
-  for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-    A.s0 = (2 * pair) * kTile;
-    B.s0 = (2 * pair + 1) * kTile;   // may lie past the count: then every row is invalid (all-zero tile)
-    stage(A);
-    stage(B);
-    sync_for_mma();
-    if (tid == 0) { issue_l1(A); issue_l1(B); }
-    mma_wait(A.bar); epi_relu(A, nullptr, A.sH1);
-    sync_for_mma();
-    if (tid == 0) issue_l2(A);
-    mma_wait(B.bar); epi_relu(B, nullptr, B.sH1);
-    sync_for_mma();
-    if (tid == 0) issue_l2(B);
-    mma_wait(A.bar); epi_relu(A, sB2, A.sH2);
-    sync_for_mma();
-    if (tid == 0) issue_dw3(A, !first);
-    mma_wait(B.bar); epi_relu(B, sB2, B.sH2);
-    sync_for_mma();
-    if (tid == 0) issue_dw3(B, true);
-    mma_wait(A.bar); epi_dz2(A);
-    sync_for_mma();
-    if (tid == 0) issue_l2b(A, !first);
-    mma_wait(B.bar); epi_dz2(B);
-    sync_for_mma();
-    if (tid == 0) issue_l2b(B, true);
-    mma_wait(A.bar); epi_dz1(A);
-    sync_for_mma();
-    if (tid == 0) issue_l1b(A, !first);
-    mma_wait(B.bar); epi_dz1(B);
-    sync_for_mma();
-    if (tid == 0) issue_l1b(B, true);
-    mma_wait(A.bar); epi_dx(A);
-    mma_wait(B.bar); epi_dx(B);
-    first = false;
+  // epilogue side: publish this thread's smem writes / TMEM reads of a context to the issuer
+  auto publish = [&](TileCtx& c) {
+    fence_async_smem();
     fence_before_sync();
-    __syncthreads();   // buffers and TMEM work columns are rewritten by the next pair
+    mbar_arrive(c.ready.bar);
+  };
+  // issuer side: wait until all 512 epilogue threads have published the context
+  auto acquire = [&](TileCtx& c) {
+    mbar_wait(c.ready.bar, c.ready.phase);
+    c.ready.phase ^= 1u;
+    fence_after_sync();
+  };
+
+  if (is_issuer) {
+    if (lane == 0) {
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        acquire(A); issue_l1(A);
+        acquire(B); issue_l1(B);
+        acquire(A); issue_l2(A);
+        acquire(B); issue_l2(B);
+        acquire(A); issue_dw3(A, !first);
+        acquire(B); issue_dw3(B, true);
+        acquire(A); issue_l2b(A, !first);
+        acquire(B); issue_l2b(B, true);
+        acquire(A); issue_l1b(A, !first);
+        acquire(B); issue_l1b(B, true);
+        first = false;
+      }
+    }
+  } else {
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      A.s0 = (2 * pair) * kTile;
+      B.s0 = (2 * pair + 1) * kTile;   // may lie past the count: then every row is invalid (all-zero tile)
+      stage(A); publish(A);
+      stage(B); publish(B);
+      mma_wait(A.bar); epi_relu(A, nullptr, A.sH1); publish(A);
+      mma_wait(B.bar); epi_relu(B, nullptr, B.sH1); publish(B);
+      mma_wait(A.bar); epi_relu(A, sB2, A.sH2); publish(A);
+      mma_wait(B.bar); epi_relu(B, sB2, B.sH2); publish(B);
+      mma_wait(A.bar); epi_mask(A, A.sH2); publish(A);
+      mma_wait(B.bar); epi_mask(B, B.sH2); publish(B);
+      mma_wait(A.bar); epi_mask(A, A.sH1); publish(A);
+      mma_wait(B.bar); epi_mask(B, B.sH1); publish(B);
+      mma_wait(A.bar); epi_dx(A);   // the last batch of the pair has completed: tiles may be re-staged
+      mma_wait(B.bar); epi_dx(B);
+    }
   }
+  fence_before_sync();
+  __syncthreads();
 
   // flush the TMEM-resident weight-gradient accumulators (lane = output feature n)
   fence_after_sync();
-  {
+  if (!is_issuer) {
     const int n = row;
     float v[32];
     tmem_ld16(tdW2 + lane_sel + part * 32, v);
@@ -568,12 +594,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
 
 static inline size_t mlp_fwd_smem(int K1) {
   return 1024 + ((tile_bytes(kHid, K1) + 1023) & ~1023u) + tile_bytes(kHid, kHid) + ((tile_bytes(kTile, K1) + 1023) & ~1023u) +
-         tile_bytes(kTile, kHid) + (3 * kHid + kHid + 4 + 3 * kTile + 4 * kHid) * sizeof(float) + 64;
+         tile_bytes(kTile, kHid) + (3 * kHid + kHid + 4) * sizeof(float) + tile_bytes(16, kHid) + 256 + 64;
 }
 static inline size_t mlp_bwd_smem(int K1) {
   auto a1k = [](size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); };
   const size_t ctx = a1k(tile_bytes(kTile, K1)) + 2 * a1k(tile_bytes(kTile, kHid)) + a1k(tile_bytes(kTile, 16));
-  return 1024 + a1k(tile_bytes(kHid, K1)) + a1k(tile_bytes(kHid, kHid)) + a1k(tile_bytes(kTile, 16)) + 2 * ctx +
+  return 1024 + a1k(tile_bytes(kHid, K1)) + a1k(tile_bytes(kHid, kHid)) + 2 * a1k(tile_bytes(kTile, 16)) + 2 * ctx +
          (3 * kHid + kHid + 4) * sizeof(float) + 64;
 }
 

@@ -101,6 +101,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar_saddr, uint32_t count) {
 __device__ __forceinline__ void mbar_init_fence() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar_saddr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
+}
 // Wait for the phase with the given parity; bounded spin so a protocol bug traps instead of hanging
 // the GPU (a hung box is a strike on the shared pool).
 __device__ __forceinline__ void mbar_wait(uint32_t bar_saddr, uint32_t parity) {

@@ -69,11 +69,11 @@ def test_tc_mlp_forward(M, C, P):
     x = torch.cat([feat[:M], pe[s_ray[:M].long()]], -1)
     with torch.no_grad():
         ref = torch.sigmoid(net(x))
-        # emulation of the kernel's operand rounding: fp16 inputs / weights / hidden-1, fp32 accumulate
+        # emulation of the kernel's operand rounding: fp16 inputs / weights / hidden activations, fp32 accumulate
         l = [m for m in net.modules() if isinstance(m, torch.nn.Linear)]
         h1 = torch.relu(_h(x).double() @ _h(l[0].weight).double().t() + _h(l[0].bias).double())
         h2 = torch.relu(_h(h1.float()).double() @ _h(l[1].weight).double().t() + l[1].bias.double())
-        emu = torch.sigmoid(h2 @ l[2].weight.double().t() + l[2].bias.double()).float()
+        emu = torch.sigmoid(_h(h2.float()).double() @ _h(l[2].weight).double().t() + l[2].bias.double()).float()
     assert torch.all(rgb[M:] == -7.0)                                    # nothing written past the count
     np.testing.assert_allclose(to_np(rgb[:M]), to_np(emu), rtol=0, atol=1e-4)   # same rounding model (fp16 ties may flip)
     np.testing.assert_allclose(to_np(rgb[:M]), to_np(ref), rtol=0, atol=2e-3)   # stated tolerance vs exact fp32
@@ -94,7 +94,7 @@ def _emulate_backward(net, x, d_rgb, rgb, scale):
     dz3 = d_rgb.double() * rgb.double() * (1 - rgb.double()) * scale
     dW3 = hd(dz3).t() @ H2
     db3 = dz3.sum(0)
-    dz2 = hd((H2 > 0) * (dz3 @ W3))
+    dz2 = hd((H2 > 0) * (hd(dz3) @ hd(W3)))
     dW2 = dz2.t() @ H1
     db2 = dz2.sum(0)
     dz1 = hd((H1 > 0) * (dz2 @ hd(W2)))
