@@ -288,7 +288,7 @@ def run_ours(args):
             "mlp_fwd": ("tensor", M * 43520.0),
             "mlp_bwd": ("tensor", M * 43520.0 * 2),
             "march_bwd": ("hbm", balg["U"] * (1 + C) * 8 + M * (16 + C * 4 + 4)),    # grad cells RMW + sample stream in
-            "sweep": ("hbm", G * (1 + C) * 32),                                      # p,g,m,v in; p,m,v,g=0 out
+            "sweep": ("hbm", G * (1 + C) * 32 / (world if getattr(trainer, "_slab", lambda: None)() else 1)),  # p,g,m,v in; p,m,v,g=0 out
         }
         dom = max((k for k in stages if k in alg), key=lambda k: stages[k])
         kind, work = alg[dom]

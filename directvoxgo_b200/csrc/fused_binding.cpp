@@ -156,14 +156,15 @@ void march_bwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor t_min, Tens
 
 void sweep(Tensor param_in, Tensor param_out, Tensor grad, Tensor exp_avg, Tensor exp_avg_sq,
            c10::optional<Tensor> perlr, int X, int Y, int Z, int C, bool tv, bool tv_dense, double wx, double wy,
-           double wz, bool masked, int step, double beta1, double beta2, double lr, double eps) {
+           double wz, bool masked, int step, double beta1, double beta2, double lr, double eps, int x_begin,
+           int x_end) {
   F32(param_in); F32(param_out); F32(grad); F32(exp_avg); F32(exp_avg_sq);
   const int64_t n = (int64_t)X * Y * Z * C;
   TORCH_CHECK(param_in.numel() == n && param_out.numel() == n && grad.numel() == n && exp_avg.numel() == n &&
                   exp_avg_sq.numel() == n, "sweep: all buffers must have X*Y*Z*C elements");
   const c10::cuda::CUDAGuard guard(param_in.device());
   rc_check(dvgo_fused_sweep(fp(param_in), fpm(param_out), fpm(grad), fpm(exp_avg), fpm(exp_avg_sq), fp_opt(perlr), X,
-                            Y, Z, C, tv, tv_dense, static_cast<float>(wx), static_cast<float>(wy),
+                            Y, Z, C, x_begin, x_end, tv, tv_dense, static_cast<float>(wx), static_cast<float>(wy),
                             static_cast<float>(wz), masked, step, static_cast<float>(beta1),
                             static_cast<float>(beta2), static_cast<float>(lr), static_cast<float>(eps), cur_stream()),
            "sweep");
@@ -212,7 +213,12 @@ void dvgo_bind_fused(pybind11::module_& m) {
   m.def("ray_finish", &ray_finish);
   m.def("sample_grad", &sample_grad);
   m.def("march_bwd", &march_bwd);
-  m.def("sweep", &sweep);
+  m.def("sweep", &sweep, pybind11::arg("param_in"), pybind11::arg("param_out"), pybind11::arg("grad"),
+        pybind11::arg("exp_avg"), pybind11::arg("exp_avg_sq"), pybind11::arg("perlr"), pybind11::arg("X"),
+        pybind11::arg("Y"), pybind11::arg("Z"), pybind11::arg("C"), pybind11::arg("tv"), pybind11::arg("tv_dense"),
+        pybind11::arg("wx"), pybind11::arg("wy"), pybind11::arg("wz"), pybind11::arg("masked"), pybind11::arg("step"),
+        pybind11::arg("beta1"), pybind11::arg("beta2"), pybind11::arg("lr"), pybind11::arg("eps"),
+        pybind11::arg("x_begin") = 0, pybind11::arg("x_end") = -1);
   m.def("ncdhw_to_cl", &ncdhw_to_cl);
   m.def("cl_to_ncdhw", &cl_to_ncdhw);
   m.def("zero_", &zero_);

@@ -40,16 +40,18 @@ template <int VEC, bool kTV>
 __global__ void __launch_bounds__(256) sweep_kernel(
     const float* __restrict__ pin, float* __restrict__ pout, float* __restrict__ grad,
     float* __restrict__ m_, float* __restrict__ v_, const float* __restrict__ perlr, int X, int Y,
-    int Z, int C, int tv_dense, float wy, float wz, int masked, float step_size, float beta1,
-    float beta2, float eps) {
-  const int64_t n_elem = static_cast<int64_t>(X) * Y * Z * C;
-  const int64_t n_work = n_elem / VEC;
+    int Z, int C, int x_begin, int x_end, int tv_dense, float wy, float wz, int masked,
+    float step_size, float beta1, float beta2, float eps) {
+  // this launch owns the x-slab [x_begin, x_end) (the whole grid on one GPU, 1/n of it when the sweep is
+  // sharded after a reduce-scatter); neighbours outside the slab are still read from the full buffers
+  const int64_t e_begin = static_cast<int64_t>(x_begin) * Y * Z * C;
+  const int64_t n_work = static_cast<int64_t>(x_end - x_begin) * Y * Z * C / VEC;
   const int64_t sz = C;                                // element stride of z +- 1
   const int64_t sy = static_cast<int64_t>(Z) * C;      // y +- 1
   const int64_t sx = static_cast<int64_t>(Y) * Z * C;  // x +- 1
   for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < n_work;
        q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t e0 = q * VEC;
+    const int64_t e0 = e_begin + q * VEC;
     float p[VEC], g[VEC], pn[VEC];
     if constexpr (VEC == 4) {
       const float4 a = *reinterpret_cast<const float4*>(pin + e0);
@@ -180,21 +182,25 @@ using namespace dvgo;
 
 DVGO_API int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float* exp_avg,
                               float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C,
-                              int tv, int tv_dense, float wx, float wy, float wz, int masked, int step,
-                              float beta1, float beta2, float lr, float eps, dvgo_stream_t stream) {
+                              int x_begin, int x_end, int tv, int tv_dense, float wx, float wy, float wz,
+                              int masked, int step, float beta1, float beta2, float lr, float eps,
+                              dvgo_stream_t stream) {
   (void)wx;
   if (X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || step <= 0) return DVGO_EINVAL;
+  if (x_end < 0) x_end = X;
+  if (x_begin < 0 || x_begin > x_end || x_end > X) return DVGO_EINVAL;
+  if (x_begin == x_end) return 0;
   if (!param_in || !param_out || !grad || !exp_avg || !exp_avg_sq) return DVGO_EINVAL;
   if (tv && param_in == param_out) return DVGO_EINVAL;  // TV needs the old neighbours
   const float step_size = lr * sqrtf(1.f - powf(beta2, static_cast<float>(step))) /
                           (1.f - powf(beta1, static_cast<float>(step)));  // adam_upd_kernel.cu:72
   wy /= 6;  // total_variation_kernel.cu:45-47
   wz /= 6;
-  const int64_t n = static_cast<int64_t>(X) * Y * Z * C;
+  const int64_t n = static_cast<int64_t>(x_end - x_begin) * Y * Z * C;
   const bool vec = (C % 4 == 0) && al16(param_in) && al16(param_out) && al16(grad) && al16(exp_avg) &&
                    al16(exp_avg_sq) && (!perlr || al16(perlr));
   cudaStream_t s = as_stream(stream);
-#define SWEEP_ARGS param_in, param_out, grad, exp_avg, exp_avg_sq, perlr, X, Y, Z, C, tv_dense, wy, wz, \
+#define SWEEP_ARGS param_in, param_out, grad, exp_avg, exp_avg_sq, perlr, X, Y, Z, C, x_begin, x_end, tv_dense, wy, wz, \
                    masked, step_size, beta1, beta2, eps
   if (vec) {
     const int blocks = sweep_grid(n / 4, 256);

@@ -178,11 +178,16 @@ class FusedRenderer(_FusedBase):
 
 class FusedTrainer(_FusedBase):
     def __init__(self, model, cfg_train, render_kwargs, world_size=1, dist_group=None, mlp="auto",
-                 betas=(0.9, 0.99), eps=1e-8):
+                 betas=(0.9, 0.99), eps=1e-8, rank=None, shard_sweep=True):
         super().__init__(model, render_kwargs, mlp)
         self.cfg = dict(cfg_train)
         self.world_size = world_size
         self.dist_group = dist_group
+        self.shard_sweep = shard_sweep
+        if rank is None and world_size > 1:
+            import torch.distributed as dist
+            rank = dist.get_rank(dist_group)
+        self.rank = rank or 0
         self.betas, self.eps = betas, eps
         self.global_step = 0
         self.opt_step = 0
@@ -275,22 +280,46 @@ class FusedTrainer(_FusedBase):
                       ws.slot_expd, ws.slot_code, ws.d_feat, ws.d_w, ws.alphainv_last, ws.g_last, self.g_density,
                       self.g_k0)
         self._mark("march_bwd")
-        if self.world_size > 1:
-            self._allreduce()
-            self._mark("allreduce")
         self._optimise(n_global)
         self._mark("sweep")
         return ws.loss_acc[0].clone()
 
-    def _allreduce(self):
+    # -- gradient exchange (ray-sharded data parallel) -----------------------------------------------
+    def _slab(self):
+        """This rank's x-slab when the sweep is sharded: needs X divisible by the world size."""
+        if self.world_size > 1 and self.shard_sweep and self.X % self.world_size == 0:
+            n = self.X // self.world_size
+            return self.rank * n, (self.rank + 1) * n
+        return None
+
+    def _reduce_grads(self, slab):
+        import torch.distributed as dist
         from .parallel import allreduce_sum_
-        bufs = [self.g_density, self.g_k0]
+        small = []
         if self.model.rgbnet is not None:
-            if self.mlp_mode == "tc":
-                bufs.append(self._tc.grad_flat)
-            else:
-                bufs += [p.grad for p in self.model.rgbnet.parameters() if p.grad is not None]
-        allreduce_sum_(bufs, self.dist_group)
+            small = [self._tc.grad_flat] if self.mlp_mode == "tc" else \
+                [p.grad for p in self.model.rgbnet.parameters() if p.grad is not None]
+        if slab is None:
+            allreduce_sum_([self.g_density, self.g_k0] + small, self.dist_group)
+            return
+        x0, x1 = slab
+        for g in (self.g_density, self.g_k0):
+            # in-place reduce-scatter: rank r receives the sum of slab r into its own slab of the buffer
+            dist.reduce_scatter_tensor(g[x0:x1], g, op=dist.ReduceOp.SUM, group=self.dist_group)
+        allreduce_sum_(small, self.dist_group)
+
+    def _gather_params(self, slab, names):
+        import torch.distributed as dist
+        x0, x1 = slab
+        for name in names:
+            p = getattr(self, name)
+            dist.all_gather_into_tensor(p, p[x0:x1], group=self.dist_group)   # in place
+        # the other ranks' slabs of the gradient accumulators still hold this rank's partial sums
+        for g in (self.g_density, self.g_k0):
+            if x0 > 0:
+                ext.zero_(g[:x0])
+            if x1 < self.X:
+                ext.zero_(g[x1:])
 
     def _tv_now(self):
         cfg, gs = self.cfg, self.global_step
@@ -303,6 +332,12 @@ class FusedTrainer(_FusedBase):
 
     def _optimise(self, n_global):
         cfg = self.cfg
+        slab = self._slab()
+        if self.world_size > 1:
+            self._reduce_grads(slab)
+            self._mark("grad_exchange")
+        x0, x1 = slab if slab is not None else (0, self.X)
+        updated = []
         self.opt_step += 1
         b1, b2 = self.betas
         tv_on, tv_dense = self._tv_now()
@@ -326,10 +361,14 @@ class FusedTrainer(_FusedBase):
             masked = self.masked[name] and per_lr is None  # dispatch of lib/masked_adam.py:60-71
             ext.sweep(cur, nxt, getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
                       per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, self.opt_step,
-                      b1, b2, lr, self.eps)
+                      b1, b2, lr, self.eps, x0, x1)
             if tv:
                 setattr(self, name, nxt)
                 setattr(self, name + "_next", cur)
+            updated.append(name)
+        if slab is not None:
+            self._gather_params(slab, updated)
+            self._mark("param_gather")
         if self.model.rgbnet is not None and self.lr["rgbnet"] > 0:
             if self.mlp_mode == "tc":
                 self._tc.adam_step(self.opt_step, b1, b2, self.lr["rgbnet"], self.eps)

@@ -136,11 +136,14 @@ int dvgo_fused_march_bwd(const float* rays_o, const float* rays_d, const dvgo_sc
  * with TV the new parameters go to a second buffer and the caller swaps -- no extra HBM traffic).
  * layout: channels = C innermost for k0 (pass C), 1 for density.  wy/wz as in total_variation_add_grad
  * (the caller passes the un-divided weights; /6 and the wx->wz quirk are applied inside).
- * perlr (may be NULL): per-element learning-rate scale (adam_upd_with_perlr). */
+ * perlr (may be NULL): per-element learning-rate scale (adam_upd_with_perlr).
+ * [x_begin, x_end): the x-slab this call updates (x_end < 0 = X).  All pointers address the FULL grids;
+ * ray-sharded training reduce-scatters the gradient, sweeps 1/n of the grid per rank and all-gathers the
+ * parameters (TV neighbours across the slab boundary come from the replicated old parameters). */
 int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float* exp_avg,
-                     float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C, int tv,
-                     int tv_dense, float wx, float wy, float wz, int masked, int step, float beta1,
-                     float beta2, float lr, float eps, dvgo_stream_t stream);
+                     float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C, int x_begin,
+                     int x_end, int tv, int tv_dense, float wx, float wy, float wz, int masked, int step,
+                     float beta1, float beta2, float lr, float eps, dvgo_stream_t stream);
 
 /* Layout converters at the state_dict boundary: [C,X,Y,Z] <-> [X,Y,Z,C]. */
 int dvgo_grid_ncdhw_to_cl(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);
