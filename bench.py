@@ -40,6 +40,7 @@ def parse():
                     choices=["auto", "fused", "module"], help="fused B200 trainer or op-by-op module path")
     ap.add_argument("--grid", type=int, default=160)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the secondary 800x800 render measurement")
     return ap.parse_args()
 
 
@@ -135,6 +136,56 @@ def algorithmic_bytes(model, batch, rk):
     return {"U": U, "G": G, "M0": int(pts.shape[0]),
             "gather_scatter": U * (1 + C) * 4 * 3, "grad_read": E * 4, "adam_dense": G * (1 + C) * 28,
             "total": U * (1 + C) * 4 * 3 + E * 4 + G * (1 + C) * 28}
+
+
+def render_metric(model, rk, device, n_frames=2, chunk=65536, sphere=False):
+    """Secondary metric of BASELINE.json: ms per rendered 800x800 frame (run.py:57-110: rays of a view ->
+    chunks -> forward, render_depth=True), device-timed with CUDA events, rays generated on the device.
+    sphere=True: the 'procedural occupancy' variant of SURVEY.md 8d (density +5 inside a ball of radius 0.6
+    half-extents, -5 outside, occupancy mask derived from it) -- labelled as an extra."""
+    import copy
+    import torch
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.dvgo import MaskCache
+    from directvoxgo_b200.fused import FusedRenderer
+    m = model
+    if sphere:
+        m = copy.deepcopy(model)
+        with torch.no_grad():
+            X, Y, Z = m.density.shape[2:]
+            ax = [torch.linspace(-1, 1, n, device=device) for n in (X, Y, Z)]
+            r = torch.stack(torch.meshgrid(*ax, indexing="ij"), -1).norm(dim=-1)
+            m.density.copy_(torch.where(r < 0.6, 5.0, -5.0)[None, None])
+            alpha = torch.nn.functional.max_pool3d(m.activate_density(m.density), 3, 1, 1)[0, 0]
+            m.mask_cache = MaskCache(mask=(alpha > m.fast_color_thres), xyz_min=m.xyz_min, xyz_max=m.xyz_max).to(device)
+    renderer = FusedRenderer(m, rk)
+    H = W = syn.BLENDER["H"]
+    K = syn.intrinsics(H, W)
+    poses = syn.random_poses(n_frames + 1, seed=4242)
+    samples = 0
+
+    def frame(c2w):
+        nonlocal samples
+        ro, rd, vd = syn.rays_of_view(H, W, K, c2w, device=device)
+        ro, rd, vd = ro.reshape(-1, 3), rd.reshape(-1, 3), vd.reshape(-1, 3)
+        out = []
+        for i in range(0, ro.shape[0], chunk):
+            o = renderer.render(ro[i:i + chunk].contiguous(), rd[i:i + chunk].contiguous(), vd[i:i + chunk].contiguous())
+            out.append(o["rgb_marched"])
+        return torch.cat(out)
+
+    frame(poses[0])  # warm-up (allocates the workspace)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for c2w in poses[1:]:
+        img = frame(c2w)
+    ev1.record()
+    torch.cuda.synchronize()
+    ws = renderer._workspace(min(chunk, H * W), False)
+    return {"ms_per_frame": ev0.elapsed_time(ev1) / n_frames, "frames": n_frames, "rays_per_call": chunk,
+            "resolution": "%dx%d" % (H, W), "grid": "sphere-occupancy (extra)" if sphere else "random-init N(0,1), nothing culled",
+            "survivors_last_call": int(ws.counters[0].item()), "mean_rgb": float(img.mean())}
 
 
 def cpu_reference_run(grid, n_rays, steps, warmup, threads):
@@ -326,6 +377,15 @@ def run_ours(args):
                 "peak": hbm_peak, "unit": "GB/s", "frac": bytes_alg / (k_ms * 1e-3) / 1e9 / hbm_peak,
                 "traffic": None, "peak_kind": peak_kind, "kernel_ms": k_ms, "algorithmic_bytes": bytes_alg}
 
+    render = None
+    if world == 1 and not args.no_render:
+        try:
+            if hasattr(trainer, "sync_to_model"):
+                trainer.sync_to_model()
+            render = {"dense": render_metric(model, rk, device, 2, 65536, False),
+                      "sphere": render_metric(model, rk, device, 2, 65536, True)}
+        except Exception as e:  # secondary metric: never let it break the headline line
+            render = {"error": repr(e)[:200]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -353,6 +413,7 @@ def run_ours(args):
         "roofline": roof,
         "step_hbm_frac": balg["total"] / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
         "cpu_baseline": cpu,
+        "render_800x800": render,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

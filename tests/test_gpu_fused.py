@@ -205,3 +205,67 @@ def test_fused_dmpigo_render_and_step(golden_dir):
     np.testing.assert_allclose(to_np(out["rgb_marched"]), g["out_rgb_marched"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(to_np(out["alphainv_last"]), g["out_alphainv_last"], rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(to_np(out["depth"]), g["out_depth"], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("n_rays", [1, 33, 1000])
+def test_fused_trainer_ragged_ray_counts_and_misses(n_rays):
+    """Ray counts that are not multiples of the warp / tile size, and rays that miss the box entirely
+    (every ray still emits >= 1 sample, render_utils_kernel.cu:46-47, which the bbox mask removes)."""
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedTrainer
+    from directvoxgo_b200.trainer import ModuleTrainer
+    m1 = _fine_model(32, dens_scale=2.0, mask_p=0.2).to(DEV)
+    m2 = copy.deepcopy(m1)
+    cfg, rk = dict(syn.FINE_TRAIN), dict(syn.RENDER_KWARGS)
+    ro, rd, vd, tgt = syn.random_training_rays(n_rays, n_views=7, seed=11, device=DEV)
+    rd[: max(1, n_rays // 3)] *= -1.0          # these rays point away from the scene
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    la = float(ModuleTrainer(m1, cfg, rk).step(ro, rd, vd, tgt))
+    for mode in ("torch", "tc"):
+        m = copy.deepcopy(m2)
+        lb = float(FusedTrainer(m, cfg, rk, mlp=mode).step(ro, rd, vd, tgt))
+        assert abs(la - lb) < (1e-5 if mode == "torch" else 2e-3) * max(1.0, abs(la)), (mode, la, lb)
+
+
+def test_fused_all_rays_miss():
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedRenderer, FusedTrainer
+    m = _fine_model(32).to(DEV)
+    ro, rd, vd, tgt = syn.random_training_rays(257, n_views=5, seed=2, device=DEV)
+    rd = -rd
+    vd = -vd
+    out = FusedRenderer(m, dict(syn.RENDER_KWARGS)).render(ro, rd, vd)
+    assert torch.all(out["alphainv_last"] == 1) and torch.allclose(out["rgb_marched"], torch.ones_like(out["rgb_marched"]))
+    assert torch.all(out["depth"] == 0)
+    tr = FusedTrainer(m, dict(syn.FINE_TRAIN), dict(syn.RENDER_KWARGS))
+    loss = float(tr.step(ro, rd, vd, tgt))
+    ref = float(((1.0 - tgt) ** 2).mean()) + 1e-3 * float(-(torch.tensor(1 - 1e-6).log() * (1 - 1e-6) + torch.tensor(1e-6).log() * 1e-6))
+    assert abs(loss - ref) < 1e-5
+    assert int(tr._workspace(257, True).counters[0]) == 0
+
+
+def test_fused_full_size_invariants():
+    """BASELINE size (160^3, 8192 rays, ~2.4 M samples): size-independent properties of the fused forward --
+    per-ray sum of weights + alphainv_last == 1 (render_utils_kernel.cu:445-457), survivor count equal to the
+    op-by-op path's sample count, rgb in [0,1], slot bookkeeping consistent."""
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedRenderer
+    m = _fine_model(160, dens_scale=1.0, mask_p=0.0).to(DEV)
+    ro, rd, vd, _ = syn.random_training_rays(8192, n_views=100, seed=1000, device=DEV)
+    rk = dict(syn.RENDER_KWARGS)
+    fr = FusedRenderer(m, rk)
+    out = fr.render(ro, rd, vd)
+    ws = fr._workspace(8192, False)
+    m4 = int(ws.counters[0])
+    assert int(ws.counters[1]) == 0 and 2_000_000 < m4 < 3_000_000
+    with torch.no_grad():
+        ref = m(ro, rd, vd, global_step=0, **rk)
+    assert m4 == ref["ray_id"].numel()
+    wsum = torch.zeros(8192, device=DEV).index_add_(0, ws.s_ray[:m4].long(), ws.s_weight[:m4])
+    # samples below the weight threshold (1e-4) are dropped from the stream: allow their mass
+    n_steps = ws.n_steps[:8192].float()
+    assert torch.all((wsum + out["alphainv_last"] - 1).abs() < 1e-4 * n_steps + 1e-4)
+    assert float(out["rgb_marched"].min()) >= 0 and float(out["rgb_marched"].max()) <= 1 + 1e-5
+    codes = ws.slot_code[: int(ws.ray_off[8192])]
+    assert int((codes >= 0).sum()) == m4 and int(codes.max()) == m4 - 1
+    np.testing.assert_allclose(to_np(out["rgb_marched"]), to_np(ref["rgb_marched"]), rtol=0, atol=2e-3)
