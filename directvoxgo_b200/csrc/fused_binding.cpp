@@ -93,6 +93,23 @@ void march_fwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor density, c1
                                 fpm(s_weight), fpm(alphainv_last), ipm(counters), cur_stream()), "march_fwd");
 }
 
+void k0_gather(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor k0_cl, Tensor t_min, Tensor ray_off, Tensor s_ray,
+               Tensor s_slot, Tensor counters, Tensor feat) {
+  F32(rays_o); F32(rays_d); F32(k0_cl); F32(t_min); I32(ray_off); I32(s_ray); I32(s_slot); I32(counters); F32(feat);
+  const c10::cuda::CUDAGuard guard(rays_o.device());
+  rc_check(dvgo_fused_k0_gather(fp(rays_o), fp(rays_d), &sc.s, fp(k0_cl), fp(t_min), ipm(ray_off), ipm(s_ray),
+                                ipm(s_slot), ipm(counters), s_ray.numel(), fpm(feat), cur_stream()), "k0_gather");
+}
+
+void k0_scatter(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor t_min, Tensor ray_off, Tensor s_ray, Tensor s_slot,
+                Tensor counters, Tensor d_feat, Tensor grad_k0_cl) {
+  F32(rays_o); F32(rays_d); F32(t_min); I32(ray_off); I32(s_ray); I32(s_slot); I32(counters); F32(d_feat);
+  F32(grad_k0_cl);
+  const c10::cuda::CUDAGuard guard(rays_o.device());
+  rc_check(dvgo_fused_k0_scatter(fp(rays_o), fp(rays_d), &sc.s, fp(t_min), ipm(ray_off), ipm(s_ray), ipm(s_slot),
+                                 ipm(counters), s_ray.numel(), fp(d_feat), fpm(grad_k0_cl), cur_stream()), "k0_scatter");
+}
+
 void rgb_direct(Tensor feat, Tensor counters, Tensor rgb) {
   F32(feat); I32(counters); F32(rgb);
   const c10::cuda::CUDAGuard guard(feat.device());
@@ -207,6 +224,8 @@ void dvgo_bind_fused(pybind11::module_& m) {
       .def("max_steps", &Scene::max_steps);
   m.def("ray_setup", &ray_setup);
   m.def("march_fwd", &march_fwd);
+  m.def("k0_gather", &k0_gather);
+  m.def("k0_scatter", &k0_scatter);
   m.def("rgb_direct", &rgb_direct);
   m.def("rgb_direct_bwd", &rgb_direct_bwd);
   m.def("composite", &composite);

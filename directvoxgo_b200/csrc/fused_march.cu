@@ -436,6 +436,108 @@ __global__ void __launch_bounds__(256, 3) march_bwd_kernel(
   }
 }
 
+
+// ---- k0 gather / scatter over the compacted survivor stream -------------------------------------------
+// The transmittance scan makes march_fwd / march_bwd walk a ray chunk by chunk; the k0 traffic (8 corners x
+// C floats per survivor -- 6x the density traffic) does not depend on the scan at all.  These two kernels do
+// it with one thread per (survivor, 16-byte channel group): every load / reduction of a thread is
+// independent, so many more are in flight per SM than inside the per-ray kernels.
+template <int C>
+__global__ void __launch_bounds__(256) k0_gather_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
+    const float* __restrict__ k0, const float* __restrict__ t_min, const int32_t* __restrict__ ray_off,
+    const int32_t* __restrict__ s_ray, const int32_t* __restrict__ s_slot,
+    const int32_t* __restrict__ counters, int64_t surv_cap, float* __restrict__ feat) {
+  constexpr int G = (C % 4 == 0) ? C / 4 : 1;   // channel groups per sample
+  constexpr int W = (C % 4 == 0) ? 4 : C;       // floats per group
+  const SceneDev sc = load_scene(a);
+  int64_t n = counters[0];
+  if (n > surv_cap) n = surv_cap;
+  const int64_t total = n * G;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t p = i / G;
+    const int q = static_cast<int>(i - p * G);
+    const int r = s_ray[p];
+    const int step = s_slot[p] - ray_off[r];
+    const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
+    float px, py, pz;
+    sample_point(sc, g, step, px, py, pz);
+    const Corner8 cn = corner8(sc, px, py, pz);
+    float acc[W];
+#pragma unroll
+    for (int c = 0; c < W; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (!cn.ok(k)) continue;
+      const float* __restrict__ v = k0 + static_cast<int64_t>(cn.off(k)) * C + q * W;
+      const float wk = cn.w(k);
+      if (C % 4 == 0) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(v));
+        acc[0] = fma_(f.x, wk, acc[0]); acc[1] = fma_(f.y, wk, acc[1]);
+        acc[2 % W] = fma_(f.z, wk, acc[2 % W]); acc[3 % W] = fma_(f.w, wk, acc[3 % W]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < W; ++c) acc[c] = fma_(__ldg(v + c), wk, acc[c]);
+      }
+    }
+    float* __restrict__ o = feat + p * C + q * W;
+    if (C % 4 == 0) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2 % W], acc[3 % W]);
+    else {
+#pragma unroll
+      for (int c = 0; c < W; ++c) o[c] = acc[c];
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) k0_scatter_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
+    const float* __restrict__ t_min, const int32_t* __restrict__ ray_off,
+    const int32_t* __restrict__ s_ray, const int32_t* __restrict__ s_slot,
+    const int32_t* __restrict__ counters, int64_t surv_cap, const float* __restrict__ d_feat,
+    float* __restrict__ grad_k0) {
+  constexpr int G = (C % 4 == 0) ? C / 4 : 1;
+  constexpr int W = (C % 4 == 0) ? 4 : C;
+  const SceneDev sc = load_scene(a);
+  int64_t n = counters[0];
+  if (n > surv_cap) n = surv_cap;
+  const int64_t total = n * G;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t p = i / G;
+    const int q = static_cast<int>(i - p * G);
+    const int r = s_ray[p];
+    const int step = s_slot[p] - ray_off[r];
+    const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
+    float px, py, pz;
+    sample_point(sc, g, step, px, py, pz);
+    const Corner8 cn = corner8(sc, px, py, pz);
+    float d[W];
+    const float* __restrict__ src = d_feat + p * C + q * W;
+    if (C % 4 == 0) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+      d[0] = f.x; d[1] = f.y; d[2 % W] = f.z; d[3 % W] = f.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < W; ++c) d[c] = __ldg(src + c);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (!cn.ok(k)) continue;
+      float* __restrict__ dst = grad_k0 + static_cast<int64_t>(cn.off(k)) * C + q * W;
+      const float wk = cn.w(k);
+      if (C % 4 == 0) {
+        atomicAdd(reinterpret_cast<float4*>(dst),
+                  make_float4(fmul(wk, d[0]), fmul(wk, d[1]), fmul(wk, d[2 % W]), fmul(wk, d[3 % W])));
+      } else {
+#pragma unroll
+        for (int c = 0; c < W; ++c) atomicAdd(dst + c, fmul(wk, d[c]));
+      }
+    }
+  }
+}
+
 static inline int ray_blocks(int n_rays, int wpb) {
   const int64_t want = (static_cast<int64_t>(n_rays) + wpb - 1) / wpb;
   const int64_t cap = static_cast<int64_t>(kNumSMs) * 32;
@@ -512,5 +614,37 @@ DVGO_API int dvgo_fused_march_bwd(const float* rays_o, const float* rays_d, cons
                                                     as_stream(stream)>>>(
       rays_o, rays_d, to_args(scene), n_rays, t_min, n_steps, ray_off, slot_alpha, slot_T, slot_expd,
       slot_code, d_feat, d_w, alphainv_last, g_last, grad_density, grad_k0_cl)));
+  return launch_status();
+}
+
+DVGO_API int dvgo_fused_k0_gather(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                                  const float* k0_cl, const float* t_min, const int32_t* ray_off,
+                                  const int32_t* s_ray, const int32_t* s_slot, const int32_t* counters,
+                                  int64_t surv_cap, float* feat, dvgo_stream_t stream) {
+  if (!scene || surv_cap < 0) return DVGO_EINVAL;
+  if (surv_cap == 0) return 0;
+  if (!rays_o || !rays_d || !k0_cl || !t_min || !ray_off || !s_ray || !s_slot || !counters || !feat)
+    return DVGO_EINVAL;
+  const int groups = (scene->C % 4 == 0) ? scene->C / 4 : 1;
+  const int64_t want = (surv_cap * groups + 255) / 256;
+  const int blocks = static_cast<int>(want < kNumSMs * 32 ? want : kNumSMs * 32);
+  DVGO_DISPATCH_C(scene->C, (k0_gather_kernel<kC><<<blocks, 256, 0, as_stream(stream)>>>(
+      rays_o, rays_d, to_args(scene), k0_cl, t_min, ray_off, s_ray, s_slot, counters, surv_cap, feat)));
+  return launch_status();
+}
+
+DVGO_API int dvgo_fused_k0_scatter(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                                   const float* t_min, const int32_t* ray_off, const int32_t* s_ray,
+                                   const int32_t* s_slot, const int32_t* counters, int64_t surv_cap,
+                                   const float* d_feat, float* grad_k0_cl, dvgo_stream_t stream) {
+  if (!scene || surv_cap < 0) return DVGO_EINVAL;
+  if (surv_cap == 0) return 0;
+  if (!rays_o || !rays_d || !t_min || !ray_off || !s_ray || !s_slot || !counters || !d_feat || !grad_k0_cl)
+    return DVGO_EINVAL;
+  const int groups = (scene->C % 4 == 0) ? scene->C / 4 : 1;
+  const int64_t want = (surv_cap * groups + 255) / 256;
+  const int blocks = static_cast<int>(want < kNumSMs * 32 ? want : kNumSMs * 32);
+  DVGO_DISPATCH_C(scene->C, (k0_scatter_kernel<kC><<<blocks, 256, 0, as_stream(stream)>>>(
+      rays_o, rays_d, to_args(scene), t_min, ray_off, s_ray, s_slot, counters, surv_cap, d_feat, grad_k0_cl)));
   return launch_status();
 }

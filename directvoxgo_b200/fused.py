@@ -96,6 +96,7 @@ class _FusedBase:
         if mlp == "tc" and not hasattr(ext, "mlp_fwd"):
             raise ImportError("tensor-core rgbnet kernels are not built")
         self.mlp_mode = mlp
+        self.split_k0 = True
         if model.rgbnet is not None and not getattr(model, "rgbnet_direct", True):
             if mlp == "tc":
                 raise NotImplementedError("tc rgbnet implements rgbnet_direct=True (the configs' default)")
@@ -118,9 +119,13 @@ class _FusedBase:
     def _march(self, ws, rays_o, rays_d):
         ext.zero_(ws.zblock)
         ext.ray_setup(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off)
-        ext.march_fwd(self.scene, rays_o, rays_d, self.density, self.k0, ws.t_min, ws.n_steps, ws.ray_off,
-                      ws.slot_alpha, ws.slot_T, ws.slot_expd, ws.slot_code, ws.feat, ws.s_ray, ws.s_slot,
-                      ws.s_weight, ws.alphainv_last, ws.counters)
+        # density march (scan-bound, per ray) then the k0 gather over the compacted stream (fully parallel)
+        ext.march_fwd(self.scene, rays_o, rays_d, self.density, None if self.split_k0 else self.k0, ws.t_min,
+                      ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T, ws.slot_expd, ws.slot_code, ws.feat, ws.s_ray,
+                      ws.s_slot, ws.s_weight, ws.alphainv_last, ws.counters)
+        if self.split_k0:
+            ext.k0_gather(self.scene, rays_o, rays_d, self.k0, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot,
+                          ws.counters, ws.feat)
 
     def _rgb_torch(self, ws, viewdirs, m4, grad):
         """rgbnet through torch/cuBLAS fp32 on the first m4 survivors; returns (rgb, feat leaf)."""
@@ -278,7 +283,10 @@ class FusedTrainer(_FusedBase):
         self._mark("mlp_bwd")
         ext.march_bwd(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T,
                       ws.slot_expd, ws.slot_code, ws.d_feat, ws.d_w, ws.alphainv_last, ws.g_last, self.g_density,
-                      self.g_k0)
+                      None if self.split_k0 else self.g_k0)
+        if self.split_k0:
+            ext.k0_scatter(self.scene, rays_o, rays_d, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot, ws.counters,
+                           ws.d_feat, self.g_k0)
         self._mark("march_bwd")
         self._optimise(n_global)
         self._mark("sweep")

@@ -89,6 +89,19 @@ int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, const dvgo_sc
                          float* s_weight, float* alphainv_last, int32_t* counters,
                          dvgo_stream_t stream);
 
+/* k0 gather / scatter over the survivor stream (one thread per survivor and 16-byte channel group).
+ * march_fwd with k0_cl == NULL followed by k0_gather is equivalent to march_fwd with k0_cl; likewise
+ * march_bwd with grad_k0_cl == NULL followed by k0_scatter.  Splitting them takes the k0 traffic (6x the
+ * density traffic) out of the per-ray scan loops, where it is latency-bound. */
+int dvgo_fused_k0_gather(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                         const float* k0_cl, const float* t_min, const int32_t* ray_off,
+                         const int32_t* s_ray, const int32_t* s_slot, const int32_t* counters,
+                         int64_t surv_cap, float* feat, dvgo_stream_t stream);
+int dvgo_fused_k0_scatter(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                          const float* t_min, const int32_t* ray_off, const int32_t* s_ray,
+                          const int32_t* s_slot, const int32_t* counters, int64_t surv_cap,
+                          const float* d_feat, float* grad_k0_cl, dvgo_stream_t stream);
+
 /* rgb = sigmoid(feat) for models without rgbnet (lib/dvgo.py:512-514); rgb [M4,3], C must be 3. */
 int dvgo_fused_rgb_direct(const float* feat, const int32_t* counters, int64_t surv_cap, float* rgb,
                           dvgo_stream_t stream);
