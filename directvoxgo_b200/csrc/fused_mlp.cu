@@ -23,7 +23,7 @@ using namespace tc;
 // half = warp/4) owns one sample row of the tile and half of the 128 hidden columns (a warp can only
 // read its own 32-lane quarter of TMEM, so warps w and w+4 split the columns of the same rows).
 //   layers 1, 2 : tcgen05.mma, A = activations [sample][feature] (K-major), B = weights [out][in]
-//   layer 3     : a third MMA with N = 16 (3 outputs used); sigmoid in its 16-column epilogue
+//   layer 3     : fp32 SIMT dot products fused into the layer-2 epilogue (3 outputs: cheaper than an N=16 MMA)
 //   b1 is folded into W1 as column d_in of the augmented input (the constant-1 feature).
 // ----------------------------------------------------------------------------------------------------
 constexpr int kHid = 128;
@@ -122,6 +122,49 @@ __device__ __forceinline__ void stage_x(uint8_t* sX, int K1, int64_t base, int64
   }
 }
 
+// Software-pipelined staging (vector path: C and pe_stride multiples of 4): the raw fp32 inputs of the NEXT
+// tile are loaded into registers while the current tile computes, and only converted + stored to shared
+// memory at the top of the next iteration.  The in-kernel timeline (tools/mlp_timeline.py) showed ~3300
+// of ~9000 cycles per tile exposed in the synchronous stage_x (two dependent global-load latencies:
+// s_ray -> embedding row); the ray index is therefore fetched one tile further ahead.
+template <int NCH>   // chunks (of 8 halves) this thread fills: ch = first + k*stride, k < NCH
+struct XRegs {
+  float4 v[2 * NCH];
+};
+template <int NCH>
+__device__ __forceinline__ void x_load(XRegs<NCH>& xr, int first, int stride, int K1, int64_t s, bool valid, int ray,
+                                       const float* __restrict__ feat, int C, const float* __restrict__ pe,
+                                       int pe_stride) {
+  const float* __restrict__ f = feat + s * C;
+  const float* __restrict__ e = pe + static_cast<int64_t>(ray) * pe_stride;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int ch = first + k * stride;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int c = ch * 8 + g * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && ch * 8 < K1) {
+        if (c < C) x = __ldg(reinterpret_cast<const float4*>(f + c));
+        else if (c < C + pe_stride) x = __ldg(reinterpret_cast<const float4*>(e + (c - C)));
+      }
+      xr.v[2 * k + g] = x;
+    }
+  }
+}
+template <int NCH>
+__device__ __forceinline__ void x_store(const XRegs<NCH>& xr, int first, int stride, int K1, int r, uint8_t* sX) {
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int ch = first + k * stride;
+    if (ch * 8 < K1) {
+      const float v[8] = {xr.v[2 * k].x, xr.v[2 * k].y, xr.v[2 * k].z, xr.v[2 * k].w,
+                          xr.v[2 * k + 1].x, xr.v[2 * k + 1].y, xr.v[2 * k + 1].z, xr.v[2 * k + 1].w};
+      *reinterpret_cast<uint4*>(sX + tile_off(r, ch * 8, K1)) = pack8(v);
+    }
+  }
+}
+
 struct MmaCtx {
   uint32_t bar;     // mbarrier shared address
   uint32_t phase;   // parity to wait for next
@@ -139,26 +182,34 @@ __device__ __forceinline__ void sync_for_mma() {
   fence_after_sync();
 }
 
-// GEMM issue helpers (ONE thread).  A/B tiles in the canonical layout; `cols` = tile row length.
+// GEMM issue helpers (ONE thread).  A/B tiles in the canonical layout; `cols` = tile row length.  The
+// descriptors of consecutive K steps differ only in the 14-bit start-address field, so they are built once
+// and advanced with one 64-bit add per step (descriptor construction was ~1k cycles of single-thread issue
+// per GEMM before).
+__device__ __forceinline__ void gemm_issue(uint32_t d, uint64_t a_desc, uint32_t a_step, uint64_t b_desc,
+                                           uint32_t b_step, uint32_t idesc, int ksteps, bool accumulate) {
+  const uint64_t a_inc = a_step >> 4, b_inc = b_step >> 4;
+#pragma unroll 4
+  for (int k = 0; k < ksteps; ++k) {
+    mma_f16(d, a_desc, b_desc, idesc, (accumulate || k) ? 1u : 0u);
+    a_desc += a_inc;
+    b_desc += b_inc;
+  }
+}
 __device__ __forceinline__ void gemm_kk(uint32_t d, uint32_t a, int a_cols, uint32_t b, int b_cols, int N, int K,
                                         bool accumulate) {  // A K-major, B K-major
-  const uint32_t idesc = make_idesc_f16(128, N, 0, 0);
-  for (int k = 0; k < K / kMmaK; ++k)
-    mma_f16(d, desc_kmajor(a + k * 256u, a_cols), desc_kmajor(b + k * 256u, b_cols), idesc, (accumulate || k) ? 1u : 0u);
+  gemm_issue(d, desc_kmajor(a, a_cols), 256u, desc_kmajor(b, b_cols), 256u, make_idesc_f16(128, N, 0, 0),
+             K / kMmaK, accumulate);
 }
 __device__ __forceinline__ void gemm_km(uint32_t d, uint32_t a, int a_cols, uint32_t b, int b_cols, int N, int K,
                                         bool accumulate) {  // A K-major, B MN-major (B tile rows = K)
-  const uint32_t idesc = make_idesc_f16(128, N, 0, 1);
-  for (int k = 0; k < K / kMmaK; ++k)
-    mma_f16(d, desc_kmajor(a + k * 256u, a_cols), desc_mnmajor(b + k * 2u * group_stride(b_cols), b_cols), idesc,
-            (accumulate || k) ? 1u : 0u);
+  gemm_issue(d, desc_kmajor(a, a_cols), 256u, desc_mnmajor(b, b_cols), 2u * group_stride(b_cols),
+             make_idesc_f16(128, N, 0, 1), K / kMmaK, accumulate);
 }
 __device__ __forceinline__ void gemm_mm(uint32_t d, uint32_t a, int a_cols, uint32_t b, int b_cols, int N, int K,
                                         bool accumulate) {  // A MN-major, B MN-major (rows of both = K)
-  const uint32_t idesc = make_idesc_f16(128, N, 1, 1);
-  for (int k = 0; k < K / kMmaK; ++k)
-    mma_f16(d, desc_mnmajor(a + k * 2u * group_stride(a_cols), a_cols),
-            desc_mnmajor(b + k * 2u * group_stride(b_cols), b_cols), idesc, (accumulate || k) ? 1u : 0u);
+  gemm_issue(d, desc_mnmajor(a, a_cols), 2u * group_stride(a_cols), desc_mnmajor(b, b_cols),
+             2u * group_stride(b_cols), make_idesc_f16(128, N, 1, 1), K / kMmaK, accumulate);
 }
 
 // TMEM [this thread's row][c_begin, c_begin+64) -> relu(v + bias) -> fp16 -> smem tile row.  bias may be
@@ -194,7 +245,8 @@ __device__ __forceinline__ size_t align1k(size_t x) { return (x + 1023) & ~stati
 // ---- forward ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride, float* __restrict__ rgb) {
+    const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride, float* __restrict__ rgb,
+    long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -214,16 +266,14 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
   float* sW3 = reinterpret_cast<float*>(sH1 + align1k(tile_bytes(kTile, kHid)));
   float* sB2 = sW3 + 3 * kHid;
   float* sB3 = sB2 + kHid;
-  uint8_t* sW3k = reinterpret_cast<uint8_t*>(sB3 + 4);  // [16 out (3 used)][128 hidden] fp16: K-major B of layer 3
-  sW3k += (128u - (smem_u32(sW3k) & 127u)) & 127u;
+  float* sPart = sB3 + 4;  // [128][3] partial layer-3 sums of the upper column half
+  float4* sL3 = reinterpret_cast<float4*>(sPart + 3 * kTile);  // [128] {W3[0][j], W3[1][j], W3[2][j], b2[j]}
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
   if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init_fence(); }
   load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3);
-  for (int i = tid; i < 16 * kHid; i += blockDim.x) {
-    const int c = i / kHid, j = i % kHid;
-    *reinterpret_cast<__half*>(sW3k + tile_off(c, j, kHid)) = __float2half_rn(c < 3 ? w.W3[c * kHid + j] : 0.f);
-  }
+  for (int j = tid; j < kHid; j += blockDim.x)
+    sL3[j] = make_float4(w.W3[j], w.W3[kHid + j], w.W3[2 * kHid + j], w.b2[j]);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -231,43 +281,90 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
   const uint32_t tD1 = tmem, tD2 = tmem + 128;
   MmaCtx ctx{smem_u32(&bar), 0u};
 
+  // software pipeline state (vector path only)
+  const bool vec = ((C | pe_stride) & 3) == 0 && K1 <= 48;
+  const int xr_r = tid & 127, xr_h = tid >> 7;
+  XRegs<3> xr;
+  int ray_next = 0;   // ray index of this thread's row in the tile after the prefetched one
+  auto row_ray = [&](int64_t t) -> int {
+    const int64_t sidx = t * kTile + xr_r;
+    return (t < n_tiles && sidx < count) ? __ldg(s_ray + sidx) : 0;
+  };
+  if (vec) {
+    const int64_t t0 = blockIdx.x;
+    const int ray0 = row_ray(t0);
+    x_load<3>(xr, xr_h, 2, K1, t0 * kTile + xr_r, t0 * kTile + xr_r < count, ray0, feat, C, pe, pe_stride);
+    ray_next = row_ray(t0 + gridDim.x);
+  }
+  int dbg_n = 0;
+  auto stamp = [&]() {  // optional in-kernel timeline (tools/mlp_timeline.py): CTA 0, threads 0 and 255
+    if (dbg && blockIdx.x == 0 && (tid == 0 || tid == 255) && dbg_n < 64) dbg[(tid ? 64 : 0) + dbg_n++] = clock64();
+  };
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t s0 = tile * kTile;
-    stage_x(sX, K1, s0, count, feat, C, s_ray, pe, pe_stride);
+    stamp();
+    if (vec) {
+      x_store<3>(xr, xr_h, 2, K1, xr_r, sX);
+      const int64_t tn = tile + gridDim.x;   // prefetch the next tile of this CTA; its loads land during this tile
+      x_load<3>(xr, xr_h, 2, K1, tn * kTile + xr_r, tn < n_tiles && tn * kTile + xr_r < count, ray_next, feat, C, pe,
+                pe_stride);
+      ray_next = row_ray(tn + gridDim.x);
+    } else {
+      stage_x(sX, K1, s0, count, feat, C, s_ray, pe, pe_stride);
+    }
+    stamp();
     sync_for_mma();
+    stamp();
     if (tid == 0) {
       gemm_kk(tD1, smem_u32(sX), K1, smem_u32(sW1), K1, kHid, K1, false);
       mma_commit(ctx.bar);
     }
+    stamp();
     mma_wait(ctx);
+    stamp();
     epi_relu_to_smem(tD1, q, row, half * 64, nullptr, sH1);
+    stamp();
     sync_for_mma();
+    stamp();
     if (tid == 0) {
       gemm_kk(tD2, smem_u32(sH1), kHid, smem_u32(sW2), kHid, kHid, kHid, false);
       mma_commit(ctx.bar);
     }
+    stamp();
     mma_wait(ctx);
-    // layer-2 epilogue: H2 = relu(z2 + b2) as fp16, in place over H1 (the layer-2 MMA has finished reading it)
-    epi_relu_to_smem(tD2, q, row, half * 64, sB2, sH1);
-    sync_for_mma();
-    if (tid == 0) {  // layer 3 on the tensor core as well: [128 x 128] x [128 x 16] (3 outputs used)
-      gemm_kk(tD1, smem_u32(sH1), kHid, smem_u32(sW3k), kHid, 16, kHid, false);
-      mma_commit(ctx.bar);
-    }
-    mma_wait(ctx);
-    if (half == 0) {
-      float v[16];
-      tmem_ld16(tD1 + (static_cast<uint32_t>(q * 32) << 16), v);
-      tmem_ld_wait();
-      if (s0 + row < count) {
-        float* __restrict__ o = rgb + (s0 + row) * 3;
+    stamp();
+    // layer-2 epilogue fused with layer 3 (fp32 SIMT, H2 never leaves registers): a third MMA (N = 16) was
+    // measured at ~1700 cycles per tile (8 small MMAs issue at ~85 cycles each + sync + 16-column epilogue)
+    // against ~400 for these FMAs (tools/mlp_timeline.py)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    {
+      float v[64];
+      tmem_ld64(tD2 + (static_cast<uint32_t>(q * 32) << 16) + half * 64, v);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o[c] = 1.f / (1.f + expf(-(v[c] + sB3[c])));
+      for (int j = 0; j < 64; ++j) {
+        const float4 t = sL3[half * 64 + j];  // one broadcast 16-byte load per hidden unit
+        const float hv = fmaxf(v[j] + t.w, 0.f);
+        a0 = fmaf(hv, t.x, a0);
+        a1 = fmaf(hv, t.y, a1);
+        a2 = fmaf(hv, t.z, a2);
       }
     }
+    stamp();
+    if (half == 1) { sPart[row * 3] = a0; sPart[row * 3 + 1] = a1; sPart[row * 3 + 2] = a2; }
     fence_before_sync();
     __syncthreads();
-    // sX / sH1 / TMEM are re-used by the next tile
+    stamp();
+    if (half == 0 && s0 + row < count) {
+      const float z0 = a0 + sPart[row * 3] + sB3[0];
+      const float z1 = a1 + sPart[row * 3 + 1] + sB3[1];
+      const float z2 = a2 + sPart[row * 3 + 2] + sB3[2];
+      float* __restrict__ o = rgb + (s0 + row) * 3;
+      o[0] = 1.f / (1.f + expf(-z0));
+      o[1] = 1.f / (1.f + expf(-z1));
+      o[2] = 1.f / (1.f + expf(-z2));
+    }
+    stamp();
+    // sPart is rewritten by the next tile only after two more CTA-wide barriers
   }
   fence_before_sync();
   __syncthreads();
@@ -376,54 +473,54 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   bool first = true;
 
   // ---- per-context stages (all 512 threads unless noted) ----
-  auto stage = [&](TileCtx& c) {  // X~ tile and dZ3 (registers + smem tile)
-    const int64_t s = c.s0 + row;
-    c.valid = s < count;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) c.dz[k] = 0.f;
-    if (c.valid) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float o = rgb[s * 3 + k];
-        c.dz[k] = d_rgb[s * 3 + k] * o * (1.f - o) * grad_scale;
-      }
+  // Staging of a context = global loads (X~ chunks of this thread, and for part 0 the d_rgb / rgb of the row)
+  // then conversion + shared-memory stores.  The loads of BOTH contexts are issued before either is
+  // consumed, and the ray indices (the head of the dependent chain s_ray -> embedding row) are fetched one
+  // pair ahead, so a pair pays one global-memory latency instead of four (tools/mlp_timeline.py).
+  const bool vecx = ((C | pe_stride) & 3) == 0 && K1 <= 64;
+  struct Staged { XRegs<2> x; float o[3], d[3]; };
+  auto ray_of = [&](int64_t s0) -> int {
+    const int64_t sidx = s0 + row;
+    return sidx < count ? __ldg(s_ray + sidx) : 0;
+  };
+  auto stage_load = [&](TileCtx& c, Staged& st, int ray) {
+    const int64_t sidx = c.s0 + row;
+    c.valid = sidx < count;
+    if (vecx) {
+      x_load<2>(st.x, part, 4, K1, sidx, c.valid, ray, feat, C, pe, pe_stride);
     }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { st.o[k] = 0.f; st.d[k] = 0.f; }
+    if (part == 0 && c.valid) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { st.o[k] = __ldg(rgb + sidx * 3 + k); st.d[k] = __ldg(d_rgb + sidx * 3 + k); }
+    }
+  };
+  auto stage_store = [&](TileCtx& c, const Staged& st, int ray) {
     if (part == 0) {
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = j < 3 ? c.dz[j] : 0.f;
+      for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        v[k] = st.d[k] * st.o[k] * (1.f - st.o[k]) * grad_scale;   // dZ3 (scaled)
+        db3[k] += v[k];
+      }
       *reinterpret_cast<uint4*>(c.sdZ3 + tile_off(row, 0, 16)) = pack8(v);
       *reinterpret_cast<uint4*>(c.sdZ3 + tile_off(row, 8, 16)) = pack8(v + 8);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) db3[k] += c.dz[k];
     }
-    // X~: thread (r = tid & 127, h = tid >> 7) fills 16-byte chunks h, h+4, ...
-    {
-      const int h = part;
-      const float* __restrict__ f = feat + s * C;
-      const float* __restrict__ e = pe + static_cast<int64_t>(c.valid ? s_ray[s] : 0) * pe_stride;
-      const bool vec = ((C | pe_stride) & 3) == 0;
-      for (int ch = h; ch < K1 / 8; ch += 4) {
+    if (vecx) {
+      x_store<2>(st.x, part, 4, K1, row, c.sX);
+    } else {  // generic (scalar) path: C or the embedding stride not a multiple of 4
+      const int64_t sidx = c.s0 + row;
+      const float* __restrict__ f = feat + sidx * C;
+      const float* __restrict__ e = pe + static_cast<int64_t>(ray) * pe_stride;
+      for (int ch = part; ch < K1 / 8; ch += 4) {
         float v[8];
 #pragma unroll
-        for (int gq = 0; gq < 2; ++gq) {
-          const int col = ch * 8 + gq * 4;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c.valid) {
-            if (vec) {
-              if (col < C) x = __ldg(reinterpret_cast<const float4*>(f + col));
-              else if (col < C + pe_stride) x = __ldg(reinterpret_cast<const float4*>(e + (col - C)));
-            } else {
-              float t[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int cc = col + j;
-                t[j] = cc < C ? __ldg(f + cc) : (cc < C + pe_stride ? __ldg(e + (cc - C)) : 0.f);
-              }
-              x = make_float4(t[0], t[1], t[2], t[3]);
-            }
-          }
-          v[gq * 4] = x.x; v[gq * 4 + 1] = x.y; v[gq * 4 + 2] = x.z; v[gq * 4 + 3] = x.w;
+        for (int j = 0; j < 8; ++j) {
+          const int cc = ch * 8 + j;
+          v[j] = !c.valid ? 0.f : (cc < C ? __ldg(f + cc) : (cc < C + pe_stride ? __ldg(e + (cc - C)) : 0.f));
         }
         *reinterpret_cast<uint4*>(c.sX + tile_off(row, ch * 8, K1)) = pack8(v);
       }
@@ -526,11 +623,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       }
     }
   } else {
+    int rayA = ray_of((2 * static_cast<int64_t>(blockIdx.x)) * kTile);
+    int rayB = ray_of((2 * static_cast<int64_t>(blockIdx.x) + 1) * kTile);
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       A.s0 = (2 * pair) * kTile;
       B.s0 = (2 * pair + 1) * kTile;   // may lie past the count: then every row is invalid (all-zero tile)
-      stage(A); publish(A);
-      stage(B); publish(B);
+      {
+        Staged stA, stB;
+        stage_load(A, stA, rayA);
+        stage_load(B, stB, rayB);
+        const int rA = rayA, rB = rayB;
+        rayA = ray_of((2 * (pair + gridDim.x)) * kTile);       // next pair's ray indices, needed only then
+        rayB = ray_of((2 * (pair + gridDim.x) + 1) * kTile);
+        stage_store(A, stA, rA); publish(A);
+        stage_store(B, stB, rB); publish(B);
+      }
       mma_wait(A.bar); epi_relu(A, nullptr, A.sH1); publish(A);
       mma_wait(B.bar); epi_relu(B, nullptr, B.sH1); publish(B);
       mma_wait(A.bar); epi_relu(A, sB2, A.sH2); publish(A);
@@ -594,7 +701,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
 
 static inline size_t mlp_fwd_smem(int K1) {
   return 1024 + ((tile_bytes(kHid, K1) + 1023) & ~1023u) + tile_bytes(kHid, kHid) + ((tile_bytes(kTile, K1) + 1023) & ~1023u) +
-         tile_bytes(kTile, kHid) + (3 * kHid + kHid + 4) * sizeof(float) + tile_bytes(16, kHid) + 256 + 64;
+         tile_bytes(kTile, kHid) + (3 * kHid + kHid + 4 + 3 * kTile + 4 * kHid) * sizeof(float) + 64;
 }
 static inline size_t mlp_bwd_smem(int K1) {
   auto a1k = [](size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); };
@@ -741,10 +848,22 @@ DVGO_API int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, i
 
 static inline int mlp_k1(int C, int pe_stride) { return ((C + pe_stride + 15) / 16) * 16; }
 
+DVGO_API int dvgo_mlp_fwd_timed(const float*, int, const int32_t*, const float*, int, int, const int32_t*, int64_t, const float*,
+                                const float*, const float*, const float*, const float*, const float*, int, float*, long long*,
+                                dvgo_stream_t);
+
 DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                           const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                           const float* W2, const float* b2, const float* W3, const float* b3, int width, float* rgb,
                           dvgo_stream_t stream) {
+  return dvgo_mlp_fwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, W1, b1, W2, b2, W3, b3, width, rgb,
+                            nullptr, stream);
+}
+
+DVGO_API int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
+                                const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
+                                const float* W2, const float* b2, const float* W3, const float* b3, int width,
+                                float* rgb, long long* timeline, dvgo_stream_t stream) {
   if (width != kHid || C < 0 || P < 0 || C + P < 1 || C + P > 63 || surv_cap < 0 || pe_stride < P + 1) return DVGO_EINVAL;
   if (!feat || !s_ray || (P > 0 && !pe) || !counters || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !rgb)
     return DVGO_EINVAL;
@@ -756,7 +875,8 @@ DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const 
   const int64_t tiles = (surv_cap + kTile - 1) / kTile;
   const int grid = static_cast<int>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
   MlpW w{W1, b1, W2, b2, W3, b3};
-  mlp_fwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, pe_stride, rgb);
+  mlp_fwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, pe_stride, rgb,
+                                                                 timeline);
   return launch_status();
 }
 

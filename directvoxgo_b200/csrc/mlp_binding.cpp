@@ -67,6 +67,19 @@ void mlp_fwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tenso
                         width, rgb.data_ptr<float>(), cur_stream()), "mlp_fwd");
 }
 
+Tensor mlp_fwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb) {
+  const int C = feat.size(1), pe_stride = pe.size(1);
+  const Offsets o = offsets(C + P, width);
+  const c10::cuda::CUDAGuard guard(feat.device());
+  auto tl = torch::zeros({128}, feat.options().dtype(torch::kInt64));
+  const float* p = params.data_ptr<float>();
+  rc_check(dvgo_mlp_fwd_timed(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
+                              counters.data_ptr<int32_t>(), s_ray.numel(), p + o.W1, p + o.b1, p + o.W2, p + o.b2,
+                              p + o.W3, p + o.b3, width, rgb.data_ptr<float>(),
+                              reinterpret_cast<long long*>(tl.data_ptr<int64_t>()), cur_stream()), "mlp_fwd_timed");
+  return tl;
+}
+
 void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb, Tensor d_rgb,
              double grad_scale, Tensor d_feat, Tensor grads) {
   chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
@@ -90,5 +103,6 @@ void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("tc_selftest", &tc_selftest);
   m.def("tc_probe", &tc_probe);
   m.def("mlp_fwd", &mlp_fwd);
+  m.def("mlp_fwd_timeline", &mlp_fwd_timeline);
   m.def("mlp_bwd", &mlp_bwd);
 }

@@ -174,6 +174,12 @@ int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe
                  const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
                  const float* b2, const float* W3, const float* b3, int width, float* rgb,
                  dvgo_stream_t stream);
+/* Same as dvgo_mlp_fwd; if `timeline` is non-NULL, CTA 0 records clock64() at every phase boundary of its
+ * first tiles into timeline[0..63] (thread 0) and timeline[64..127] (thread 255) -- kernel-author tooling. */
+int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
+                       const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
+                       const float* W2, const float* b2, const float* W3, const float* b3, int width, float* rgb,
+                       long long* timeline, dvgo_stream_t stream);
 /* Backward with forward recompute: d_feat [surv_cap,C] = dL/dfeat, and gW*, gb* += weight gradients
  * (accumulated in TMEM per CTA, flushed with atomics; the caller zeroes them).  d_rgb = dL/d(rgb) (after
  * the sigmoid).  grad_scale: power of two applied to the FP16 backward operands and removed exactly in
