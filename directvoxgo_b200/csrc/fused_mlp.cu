@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
     const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride,
     const float* __restrict__ rgb, const float* __restrict__ d_rgb, float grad_scale, float* __restrict__ d_feat,
-    MlpG g) {
+    MlpG g, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4];  // full[0], full[1], ready[0], ready[1]
   __shared__ uint32_t tmem_base_s;
@@ -562,7 +562,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       tmem_ld_wait();
       if (c.valid) {
         float* __restrict__ o = d_feat + (c.s0 + row) * C;
-        for (int k = 0; k < C; ++k) o[k] = v[k] * inv_scale;
+        if ((C & 3) == 0) {   // static register indexing + 16-byte stores (a runtime-indexed loop spills v[])
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            if (k4 * 4 < C)
+              *reinterpret_cast<float4*>(o + k4 * 4) = make_float4(v[k4 * 4] * inv_scale, v[k4 * 4 + 1] * inv_scale,
+                                                                   v[k4 * 4 + 2] * inv_scale, v[k4 * 4 + 3] * inv_scale);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k < C) o[k] = v[k] * inv_scale;
+        }
       }
     }
   };
@@ -606,48 +616,71 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     fence_after_sync();
   };
 
+  int dbg_n = 0;
+  auto stamp = [&]() {  // optional in-kernel timeline: CTA 0, epilogue thread 0 -> [0,64), issuer lane 0 -> [64,128)
+    if (dbg && blockIdx.x == 0 && dbg_n < 64 && (tid == 0 || (is_issuer && lane == 0)))
+      dbg[(is_issuer ? 64 : 0) + dbg_n++] = clock64();
+  };
   if (is_issuer) {
     if (lane == 0) {
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        acquire(A); issue_l1(A);
-        acquire(B); issue_l1(B);
-        acquire(A); issue_l2(A);
-        acquire(B); issue_l2(B);
-        acquire(A); issue_dw3(A, !first);
-        acquire(B); issue_dw3(B, true);
-        acquire(A); issue_l2b(A, !first);
-        acquire(B); issue_l2b(B, true);
-        acquire(A); issue_l1b(A, !first);
-        acquire(B); issue_l1b(B, true);
+        stamp();
+        acquire(A); stamp(); issue_l1(A); stamp();
+        acquire(B); stamp(); issue_l1(B); stamp();
+        acquire(A); stamp(); issue_l2(A); stamp();
+        acquire(B); stamp(); issue_l2(B); stamp();
+        acquire(A); stamp(); issue_dw3(A, !first); stamp();
+        acquire(B); stamp(); issue_dw3(B, true); stamp();
+        acquire(A); stamp(); issue_l2b(A, !first); stamp();
+        acquire(B); stamp(); issue_l2b(B, true); stamp();
+        acquire(A); stamp(); issue_l1b(A, !first); stamp();
+        acquire(B); stamp(); issue_l1b(B, true); stamp();
         first = false;
       }
     }
   } else {
+    // Software pipeline over pairs: the global loads of the NEXT pair are issued before the last two
+    // epilogue phases of the current one, so that at the pair boundary only the conversion + shared-memory
+    // stores remain (the timeline showed the tensor core idle ~7.5k of ~21k cycles per pair there).
+    Staged stA, stB;
     int rayA = ray_of((2 * static_cast<int64_t>(blockIdx.x)) * kTile);
     int rayB = ray_of((2 * static_cast<int64_t>(blockIdx.x) + 1) * kTile);
+    A.s0 = (2 * static_cast<int64_t>(blockIdx.x)) * kTile;
+    B.s0 = A.s0 + kTile;                // may lie past the count: then every row is invalid (all-zero tile)
+    stage_load(A, stA, rayA);
+    stage_load(B, stB, rayB);
+    int rA = rayA, rB = rayB;
+    rayA = ray_of(A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
+    rayB = ray_of(B.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      A.s0 = (2 * pair) * kTile;
-      B.s0 = (2 * pair + 1) * kTile;   // may lie past the count: then every row is invalid (all-zero tile)
-      {
-        Staged stA, stB;
-        stage_load(A, stA, rayA);
-        stage_load(B, stB, rayB);
-        const int rA = rayA, rB = rayB;
-        rayA = ray_of((2 * (pair + gridDim.x)) * kTile);       // next pair's ray indices, needed only then
-        rayB = ray_of((2 * (pair + gridDim.x) + 1) * kTile);
-        stage_store(A, stA, rA); publish(A);
-        stage_store(B, stB, rB); publish(B);
-      }
-      mma_wait(A.bar); epi_relu(A, nullptr, A.sH1); publish(A);
-      mma_wait(B.bar); epi_relu(B, nullptr, B.sH1); publish(B);
-      mma_wait(A.bar); epi_relu(A, sB2, A.sH2); publish(A);
-      mma_wait(B.bar); epi_relu(B, sB2, B.sH2); publish(B);
-      mma_wait(A.bar); epi_mask(A, A.sH2); publish(A);
-      mma_wait(B.bar); epi_mask(B, B.sH2); publish(B);
-      mma_wait(A.bar); epi_mask(A, A.sH1); publish(A);
-      mma_wait(B.bar); epi_mask(B, B.sH1); publish(B);
-      mma_wait(A.bar); epi_dx(A);   // the last batch of the pair has completed: tiles may be re-staged
-      mma_wait(B.bar); epi_dx(B);
+      stamp();
+      stage_store(A, stA, rA); publish(A);
+      stage_store(B, stB, rB); publish(B);
+      const bool validA = A.valid, validB = B.valid;
+      const int64_t s0A = A.s0, s0B = B.s0;
+      stamp();
+      mma_wait(A.bar); stamp(); epi_relu(A, nullptr, A.sH1); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_relu(B, nullptr, B.sH1); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_relu(A, sB2, A.sH2); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_relu(B, sB2, B.sH2); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_mask(A, A.sH2); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_mask(B, B.sH2); publish(B); stamp();
+      // prefetch the next pair (registers only; the tiles are still in use)
+      A.s0 = (2 * (pair + gridDim.x)) * kTile;
+      B.s0 = A.s0 + kTile;
+      stage_load(A, stA, rayA);
+      stage_load(B, stB, rayB);
+      rA = rayA; rB = rayB;
+      rayA = ray_of(A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
+      rayB = ray_of(B.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
+      const bool nvA = A.valid, nvB = B.valid;
+      const int64_t nsA = A.s0, nsB = B.s0;
+      A.valid = validA; A.s0 = s0A; B.valid = validB; B.s0 = s0B;   // the current pair's identity for epi_dx
+      mma_wait(A.bar); stamp(); epi_mask(A, A.sH1); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_mask(B, B.sH1); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_dx(A);   // the last batch of the pair has completed: tiles may be re-staged
+      mma_wait(B.bar); stamp(); epi_dx(B); stamp();
+      A.valid = nvA; A.s0 = nsA; B.valid = nvB; B.s0 = nsB;
     }
   }
   fence_before_sync();
@@ -880,11 +913,26 @@ DVGO_API int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, 
   return launch_status();
 }
 
+DVGO_API int dvgo_mlp_bwd_timed(const float*, int, const int32_t*, const float*, int, int, const int32_t*, int64_t, const float*,
+                                const float*, const float*, const float*, const float*, const float*, int, const float*,
+                                const float*, float, float*, float*, float*, float*, float*, float*, float*, long long*,
+                                dvgo_stream_t);
+
 DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                           const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                           const float* W2, const float* b2, const float* W3, const float* b3, int width,
                           const float* rgb, const float* d_rgb, float grad_scale, float* d_feat, float* gW1,
                           float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, dvgo_stream_t stream) {
+  return dvgo_mlp_bwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, W1, b1, W2, b2, W3, b3, width, rgb, d_rgb,
+                            grad_scale, d_feat, gW1, gb1, gW2, gb2, gW3, gb3, nullptr, stream);
+}
+
+DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
+                                const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
+                                const float* W2, const float* b2, const float* W3, const float* b3, int width,
+                                const float* rgb, const float* d_rgb, float grad_scale, float* d_feat, float* gW1,
+                                float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, long long* timeline,
+                                dvgo_stream_t stream) {
   if (width != kHid || C < 1 || C > 16 || P < 0 || C + P > 63 || surv_cap < 0 || !(grad_scale > 0.f) || pe_stride < P + 1)
     return DVGO_EINVAL;
   if (!feat || !s_ray || (P > 0 && !pe) || !counters || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !rgb || !d_rgb ||
@@ -901,6 +949,6 @@ DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const 
   MlpW w{W1, b1, W2, b2, W3, b3};
   MlpG g{gW1, gb1, gW2, gb2, gW3, gb3};
   mlp_bwd_kernel<<<grid, kBwdThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, pe_stride,
-                                                                 rgb, d_rgb, grad_scale, d_feat, g);
+                                                                 rgb, d_rgb, grad_scale, d_feat, g, timeline);
   return launch_status();
 }

@@ -97,6 +97,23 @@ void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tenso
                         d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3,
                         cur_stream()), "mlp_bwd");
 }
+
+Tensor mlp_bwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb,
+                        Tensor d_rgb, double grad_scale, Tensor d_feat, Tensor grads) {
+  const int C = feat.size(1), pe_stride = pe.size(1);
+  const Offsets o = offsets(C + P, width);
+  const c10::cuda::CUDAGuard guard(feat.device());
+  auto tl = torch::zeros({128}, feat.options().dtype(torch::kInt64));
+  const float* p = params.data_ptr<float>();
+  float* g = grads.data_ptr<float>();
+  rc_check(dvgo_mlp_bwd_timed(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
+                              counters.data_ptr<int32_t>(), s_ray.numel(), p + o.W1, p + o.b1, p + o.W2, p + o.b2,
+                              p + o.W3, p + o.b3, width, rgb.data_ptr<float>(), d_rgb.data_ptr<float>(),
+                              static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2,
+                              g + o.b2, g + o.W3, g + o.b3, reinterpret_cast<long long*>(tl.data_ptr<int64_t>()),
+                              cur_stream()), "mlp_bwd_timed");
+  return tl;
+}
 }  // namespace
 
 void dvgo_bind_mlp(pybind11::module_& m) {
@@ -105,4 +122,5 @@ void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("mlp_fwd", &mlp_fwd);
   m.def("mlp_fwd_timeline", &mlp_fwd_timeline);
   m.def("mlp_bwd", &mlp_bwd);
+  m.def("mlp_bwd_timeline", &mlp_bwd_timeline);
 }

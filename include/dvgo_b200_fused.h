@@ -190,6 +190,14 @@ int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe
                  const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
                  float* gb2, float* gW3, float* gb3, dvgo_stream_t stream);
 
+/* dvgo_mlp_bwd with an optional in-kernel timeline (CTA 0: epilogue thread 0 -> timeline[0..63], issuer ->
+ * timeline[64..127], clock64 at every phase boundary of the first tile pair) -- kernel-author tooling. */
+int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
+                       const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
+                       const float* b2, const float* W3, const float* b3, int width, const float* rgb,
+                       const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
+                       float* gb2, float* gW3, float* gb3, long long* timeline, dvgo_stream_t stream);
+
 /* Tensor-core self test (one CTA): D[128,N] = A * B^T with tcgen05.mma kind::f16 (fp16 operands), for each operand
  * orientation the rgbnet kernels use.  a_mn=0: A is [128][K]; a_mn=1: A is [K][128]; b_mn=0: B is
  * [N][K]; b_mn=1: B is [K][N].  N % 16 == 0, N <= 256, K % 16 == 0, K <= 128.  D is [128][N]. */

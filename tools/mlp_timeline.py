@@ -25,3 +25,23 @@ for who, off in (("thread 0", 0), ("thread 255", 64)):
         d = [b - a for a, b in zip(seg[:-1], seg[1:])]
         print("  tile %d: total %d cyc | " % (tile, seg[-1] - seg[0] if len(seg) > per_tile else sum(d)) +
               ", ".join("%s %d" % (n, x) for n, x in zip(names, d)))
+
+# ---- backward ----
+d_rgb = (torch.randn(cap, 3, device="cuda") / (3 * 8192)).contiguous()
+tcb = TensorCoreMLP(net, "cuda", train=True)
+d_feat = torch.zeros(cap, 12, device="cuda")
+for _ in range(2):
+    tl = ext.mlp_bwd_timeline(feat, s_ray, pe_pad, 27, counters, tcb.params, 128, rgb, d_rgb, 2.0 ** 21, d_feat, tcb.grad_flat)
+torch.cuda.synchronize()
+epi = ["stage A+B"] + [x for ph in ("relu1", "relu2", "mask2", "mask1") for x in
+                       ("wait A", ph + " A", "wait B", ph + " B")] + ["wait A", "dx A + wait B", "dx B"]
+iss = [x for ph in ("L1", "L2", "dW3+dH2", "dW2+db2+dH1", "dW1+dX") for x in
+       ("acq A", ph + " A", "acq B", ph + " B")]
+for who, off, names in (("epilogue thread 0", 0, epi), ("issuer", 64, iss)):
+    t = [x for x in tl[off:off + 64].cpu().tolist() if x]
+    n = len(names) + 1
+    print(who, "(2nd pair)")
+    seg = t[n:2 * n]
+    if len(seg) == n:
+        d = [b - a for a, b in zip(seg[:-1], seg[1:])]
+        print("  pair total %d cyc | " % (seg[-1] - seg[0]) + ", ".join("%s %d" % (a, b) for a, b in zip(names, d)))
