@@ -27,6 +27,7 @@ using namespace tc;
 //   b1 is folded into W1 as column d_in of the augmented input (the constant-1 feature).
 // ----------------------------------------------------------------------------------------------------
 constexpr int kHid = 128;
+constexpr int kHidA = kHid + 16;  // hidden width augmented with the constant-1 column (carries b2 / db2 in bwd)
 constexpr int kTile = 128;
 constexpr int kMlpThreads = 256;
 
@@ -70,14 +71,17 @@ __device__ __forceinline__ uint4 pack8_masked(const float* v, const uint4& act) 
 // Weights -> fp16 canonical tiles (sW1 [128 x K1] incl. the bias column, sW2 [128 x 128]) and the
 // small fp32 arrays used by the SIMT parts (W3 [3][128], b2 [128], b3 [3]).
 __device__ void load_weights(const MlpW& w, int d_in, int K1, uint8_t* sW1, uint8_t* sW2, float* sW3, float* sB2,
-                             float* sB3) {
+                             float* sB3, int w2_cols = kHid) {
   for (int i = threadIdx.x; i < kHid * K1; i += blockDim.x) {
     const int n = i / K1, c = i % K1;
     const float v = c < d_in ? w.W1[n * d_in + c] : (c == d_in ? w.b1[n] : 0.f);
     *reinterpret_cast<__half*>(sW1 + tile_off(n, c, K1)) = __float2half_rn(v);
   }
-  for (int i = threadIdx.x; i < kHid * kHid; i += blockDim.x)
-    *reinterpret_cast<__half*>(sW2 + tile_off(i / kHid, i % kHid, kHid)) = __float2half_rn(w.W2[i]);
+  for (int i = threadIdx.x; i < kHid * w2_cols; i += blockDim.x) {  // w2_cols = 144: column 128 holds b2
+    const int n = i / w2_cols, c = i % w2_cols;
+    const float v = c < kHid ? w.W2[n * kHid + c] : (c == kHid ? w.b2[n] : 0.f);
+    *reinterpret_cast<__half*>(sW2 + tile_off(n, c, w2_cols)) = __float2half_rn(v);
+  }
   for (int i = threadIdx.x; i < 3 * kHid; i += blockDim.x) sW3[i] = w.W3[i];
   for (int i = threadIdx.x; i < kHid; i += blockDim.x) sB2[i] = w.b2[i];
   if (threadIdx.x < 3) sB3[threadIdx.x] = w.b3[threadIdx.x];
@@ -220,7 +224,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
   tmem_ld_wait();
 }
 __device__ __forceinline__ void epi_relu_to_smem(uint32_t tmem_d, int q, int row, int c_begin, const float* sBias,
-                                                 uint8_t* sOut) {
+                                                 uint8_t* sOut, int out_cols) {
   float v[64];
   tmem_ld64(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + c_begin, v);
 #pragma unroll
@@ -236,7 +240,7 @@ __device__ __forceinline__ void epi_relu_to_smem(uint32_t tmem_d, int q, int row
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = v[cc * 8 + j];
     }
-    *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, kHid)) = pack8_relu(o);
+    *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, out_cols)) = pack8_relu(o);
   }
 }
 
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     stamp();
     mma_wait(ctx);
     stamp();
-    epi_relu_to_smem(tD1, q, row, half * 64, nullptr, sH1);
+    epi_relu_to_smem(tD1, q, row, half * 64, nullptr, sH1, kHid);
     stamp();
     sync_for_mma();
     stamp();
@@ -427,11 +431,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW1 = base;
   uint8_t* sW2 = sW1 + align1k(tile_bytes(kHid, K1));
-  uint8_t* sOnes = sW2 + align1k(tile_bytes(kHid, kHid));
-  uint8_t* sW3t = sOnes + align1k(tile_bytes(kTile, 16));   // [128 hidden j][16: c < 3] = W3^T, K-major B of dH2
+  uint8_t* sW3t = sW2 + align1k(tile_bytes(kHid, kHidA));   // [128 hidden j][16: c < 3] = W3^T, K-major B of dH2
   uint8_t* ctx_base = sW3t + align1k(tile_bytes(kHid, 16));
-  const size_t ctx_bytes = align1k(tile_bytes(kTile, K1)) + 2 * align1k(tile_bytes(kTile, kHid)) +
-                           align1k(tile_bytes(kTile, 16));
+  const size_t ctx_bytes = align1k(tile_bytes(kTile, K1)) + align1k(tile_bytes(kTile, kHidA)) +
+                           align1k(tile_bytes(kTile, kHid)) + align1k(tile_bytes(kTile, 16));
   float* sW3 = reinterpret_cast<float*>(ctx_base + 2 * ctx_bytes);
   float* sB2 = sW3 + 3 * kHid;
   float* sB3 = sB2 + kHid;
@@ -444,24 +447,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     mbar_init(smem_u32(&bars[3]), kBwdEpiThreads);
     mbar_init_fence();
   }
-  load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3);
-  for (int i = tid; i < kTile * 16; i += blockDim.x) {  // ones in column 0: db2 = dZ2^T * ones
-    *reinterpret_cast<__half*>(sOnes + tile_off(i / 16, i % 16, 16)) = __float2half_rn((i % 16) == 0 ? 1.f : 0.f);
+  load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3, kHidA);
+  for (int i = tid; i < kTile * 16; i += blockDim.x) {
     const int j = i / 16, c = i % 16;
     *reinterpret_cast<__half*>(sW3t + tile_off(j, c, 16)) = __float2half_rn(c < 3 ? w.W3[c * kHid + j] : 0.f);
+    // columns 128..143 of both H1 tiles: the constant 1 (b2 rides the layer-2 GEMM, db2 the dW2 GEMM), then 0;
+    // the epilogues only ever write columns < 128
+    for (int cx_i = 0; cx_i < 2; ++cx_i) {
+      uint8_t* h1 = ctx_base + cx_i * ctx_bytes + align1k(tile_bytes(kTile, K1));
+      *reinterpret_cast<__half*>(h1 + tile_off(j, kHid + c, kHidA)) = __float2half_rn(c == 0 ? 1.f : 0.f);
+    }
   }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tdW2 = tmem + 256, tdW1 = tmem + 384, tdW3 = tmem + 432, tdB2 = tmem + 448;
+  const uint32_t tdW2 = tmem + 256, tdW1 = tmem + 400, tdW3 = tmem + 448;  // dW2|db2: 144 cols, dW1~: 48, dW3^T: 16
   TileCtx cx[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     uint8_t* b = ctx_base + i * ctx_bytes;
     cx[i].sX = b;
     cx[i].sH1 = b + align1k(tile_bytes(kTile, K1));
-    cx[i].sH2 = cx[i].sH1 + align1k(tile_bytes(kTile, kHid));
+    cx[i].sH2 = cx[i].sH1 + align1k(tile_bytes(kTile, kHidA));
     cx[i].sdZ3 = cx[i].sH2 + align1k(tile_bytes(kTile, kHid));
     cx[i].tWork = tmem + 128 * i;
     cx[i].bar = MmaCtx{smem_u32(&bars[i]), 0u};
@@ -527,7 +535,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     }
   };
   // TMEM work[row][32*part, +32) -> relu(v + bias) -> fp16 -> smem
-  auto epi_relu = [&](TileCtx& c, const float* sBias, uint8_t* sOut) {
+  auto epi_relu = [&](TileCtx& c, const float* sBias, uint8_t* sOut, int out_cols) {
     float v[32];
     tmem_ld16(c.tWork + lane_sel + part * 32, v);
     tmem_ld16(c.tWork + lane_sel + part * 32 + 16, v + 16);
@@ -541,17 +549,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     }
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc)
-      *reinterpret_cast<uint4*>(sOut + tile_off(row, part * 32 + cc * 8, kHid)) = pack8_relu(v + cc * 8);
+      *reinterpret_cast<uint4*>(sOut + tile_off(row, part * 32 + cc * 8, out_cols)) = pack8_relu(v + cc * 8);
   };
   // out = (act > 0) * TMEM work, in place over the activation tile (dZ2 over H2, dZ1 over H1)
-  auto epi_mask = [&](TileCtx& c, uint8_t* sAct) {
+  auto epi_mask = [&](TileCtx& c, uint8_t* sAct, int act_cols) {
     float v[32];
     tmem_ld16(c.tWork + lane_sel + part * 32, v);
     tmem_ld16(c.tWork + lane_sel + part * 32 + 16, v + 16);
     tmem_ld_wait();
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
-      uint4* p = reinterpret_cast<uint4*>(sAct + tile_off(row, part * 32 + cc * 8, kHid));
+      uint4* p = reinterpret_cast<uint4*>(sAct + tile_off(row, part * 32 + cc * 8, act_cols));
       *p = pack8_masked(v + cc * 8, *p);
     }
   };
@@ -582,7 +590,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     mma_commit(c.bar.bar);
   };
   auto issue_l2 = [&](TileCtx& c) {
-    gemm_kk(c.tWork, smem_u32(c.sH1), kHid, smem_u32(sW2), kHid, kHid, kHid, false);
+    gemm_kk(c.tWork, smem_u32(c.sH1), kHidA, smem_u32(sW2), kHidA, kHid, kHidA, false);  // K = 144: + b2
     mma_commit(c.bar.bar);
   };
   auto issue_dw3 = [&](TileCtx& c, bool acc) {
@@ -591,14 +599,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     mma_commit(c.bar.bar);
   };
   auto issue_l2b = [&](TileCtx& c, bool acc) {
-    gemm_mm(tdW2, smem_u32(c.sH2), kHid, smem_u32(c.sH1), kHid, kHid, kTile, acc);    // dW2 += dZ2^T H1
-    gemm_mm(tdB2, smem_u32(c.sH2), kHid, smem_u32(sOnes), 16, 16, kTile, acc);        // db2 += dZ2^T 1
-    gemm_km(c.tWork, smem_u32(c.sH2), kHid, smem_u32(sW2), kHid, kHid, kHid, false);  // dH1 = dZ2 W2
+    gemm_mm(tdW2, smem_u32(c.sH2), kHid, smem_u32(c.sH1), kHidA, kHidA, kTile, acc);   // [dW2 | db2] += dZ2^T [H1 | 1]
+    gemm_km(c.tWork, smem_u32(c.sH2), kHid, smem_u32(sW2), kHidA, kHid, kHid, false);  // dH1 = dZ2 W2
     mma_commit(c.bar.bar);
   };
   auto issue_l1b = [&](TileCtx& c, bool acc) {
-    gemm_mm(tdW1, smem_u32(c.sH1), kHid, smem_u32(c.sX), K1, K1, kTile, acc);         // dW1~ += dZ1^T X~
-    gemm_km(c.tWork, smem_u32(c.sH1), kHid, smem_u32(sW1), K1, 16, kHid, false);      // dX = dZ1 W1[:, :16]
+    gemm_mm(tdW1, smem_u32(c.sH1), kHidA, smem_u32(c.sX), K1, K1, kTile, acc);        // dW1~ += dZ1^T X~
+    gemm_km(c.tWork, smem_u32(c.sH1), kHidA, smem_u32(sW1), K1, 16, kHid, false);     // dX = dZ1 W1[:, :16]
     mma_commit(c.bar.bar);
   };
   TileCtx& A = cx[0];
@@ -659,12 +666,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       const bool validA = A.valid, validB = B.valid;
       const int64_t s0A = A.s0, s0B = B.s0;
       stamp();
-      mma_wait(A.bar); stamp(); epi_relu(A, nullptr, A.sH1); publish(A); stamp();
-      mma_wait(B.bar); stamp(); epi_relu(B, nullptr, B.sH1); publish(B); stamp();
-      mma_wait(A.bar); stamp(); epi_relu(A, sB2, A.sH2); publish(A); stamp();
-      mma_wait(B.bar); stamp(); epi_relu(B, sB2, B.sH2); publish(B); stamp();
-      mma_wait(A.bar); stamp(); epi_mask(A, A.sH2); publish(A); stamp();
-      mma_wait(B.bar); stamp(); epi_mask(B, B.sH2); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_relu(A, nullptr, A.sH1, kHidA); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_relu(B, nullptr, B.sH1, kHidA); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_relu(A, nullptr, A.sH2, kHid); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_relu(B, nullptr, B.sH2, kHid); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_mask(A, A.sH2, kHid); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_mask(B, B.sH2, kHid); publish(B); stamp();
       // prefetch the next pair (registers only; the tiles are still in use)
       A.s0 = (2 * (pair + gridDim.x)) * kTile;
       B.s0 = A.s0 + kTile;
@@ -676,8 +683,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       const bool nvA = A.valid, nvB = B.valid;
       const int64_t nsA = A.s0, nsB = B.s0;
       A.valid = validA; A.s0 = s0A; B.valid = validB; B.s0 = s0B;   // the current pair's identity for epi_dx
-      mma_wait(A.bar); stamp(); epi_mask(A, A.sH1); publish(A); stamp();
-      mma_wait(B.bar); stamp(); epi_mask(B, B.sH1); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_mask(A, A.sH1, kHidA); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_mask(B, B.sH1, kHidA); publish(B); stamp();
       mma_wait(A.bar); stamp(); epi_dx(A);   // the last batch of the pair has completed: tiles may be re-staged
       mma_wait(B.bar); stamp(); epi_dx(B); stamp();
       A.valid = nvA; A.s0 = nsA; B.valid = nvB; B.s0 = nsB;
@@ -713,7 +720,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
 #pragma unroll
       for (int c = 0; c < 3; ++c) atomicAdd(g.W3 + c * kHid + n, v[c] * inv_scale);
     } else if (part == 2) {
-      tmem_ld16(tdB2 + lane_sel, v);
+      tmem_ld16(tdW2 + lane_sel + kHid, v);   // column 128 of [dW2 | db2]
       tmem_ld_wait();
       atomicAdd(g.b2 + n, v[0] * inv_scale);
     }
@@ -738,8 +745,9 @@ static inline size_t mlp_fwd_smem(int K1) {
 }
 static inline size_t mlp_bwd_smem(int K1) {
   auto a1k = [](size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); };
-  const size_t ctx = a1k(tile_bytes(kTile, K1)) + 2 * a1k(tile_bytes(kTile, kHid)) + a1k(tile_bytes(kTile, 16));
-  return 1024 + a1k(tile_bytes(kHid, K1)) + a1k(tile_bytes(kHid, kHid)) + 2 * a1k(tile_bytes(kTile, 16)) + 2 * ctx +
+  const size_t ctx = a1k(tile_bytes(kTile, K1)) + a1k(tile_bytes(kTile, kHidA)) + a1k(tile_bytes(kTile, kHid)) +
+                     a1k(tile_bytes(kTile, 16));
+  return 1024 + a1k(tile_bytes(kHid, K1)) + a1k(tile_bytes(kHid, kHidA)) + a1k(tile_bytes(kHid, 16)) + 2 * ctx +
          (3 * kHid + kHid + 4) * sizeof(float) + 64;
 }
 
