@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--ramp-s", dest="ramp_s", type=float, default=1.5,
+                    help="seconds of untimed steps before the W warm-up steps (GPU clock ramp)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--path", default=os.environ.get("DVGO_BENCH_PATH", "auto"),
                     choices=["auto", "fused", "module"], help="fused B200 trainer or op-by-op module path")
@@ -269,6 +271,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------
+    # Untimed clock ramp: a B200 idling at its floor clock needs ~1 s of load to reach its boost clock; W warm-up
+    # steps (a few ms) are not enough and the first timed steps would otherwise run at a lower clock.
+    t_ramp = time.time()
+    while time.time() - t_ramp < args.ramp_s:
+        for i in range(50):
+            trainer.step(*dev_batches[i % N_BATCHES])
+        torch.cuda.synchronize()
     for i in range(args.warmup):
         trainer.step(*dev_batches[i % N_BATCHES])
     barrier()
@@ -348,10 +357,14 @@ def run_ours(args):
             ach, peak, unit = work / t / 1e9, hbm_peak, "GB/s"
         else:
             ach, peak, unit = work / t / 1e12, tensor_peak, "TFLOP/s"
-        kernel_names = {"march_fwd": "march_fwd_kernel<12>", "mlp_fwd": "mlp_fwd_kernel", "mlp_bwd": "mlp_bwd_kernel",
-                        "march_bwd": "march_bwd_kernel<12>", "sweep": "sweep_kernel<4,true> (+density sweep, rgbnet Adam)"}
+        kernel_names = {"march_fwd": "march_fwd_kernel<12> + k0_gather_kernel<12>", "mlp_fwd": "mlp_fwd_kernel", "mlp_bwd": "mlp_bwd_kernel",
+                        "march_bwd": "k0_scatter_kernel<12> + march_bwd_kernel<12>", "sweep": "sweep_kernel<4,true> (+density sweep, rgbnet Adam)"}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture of this
+        # command (profiles/r01_ncu_final_kernels.md); valid for the default workload only.
+        ncu_traffic = {"march_fwd": 35.3e6 + 457.4e6, "mlp_fwd": 145.2e6, "mlp_bwd": 272.3e6, "march_bwd": 64.9e6 + 599.3e6, "sweep": 1465.5e6 + 75.6e6}
+        traffic = ncu_traffic.get(dom) if (args.grid == 160 and world == 1) else None
         roof = {"bound": kind, "kernel": kernel_names[dom], "achieved": ach, "peak": peak, "unit": unit,
-                "frac": ach / peak, "traffic": None, "peak_kind": peak_kind + (" (bf16 sustained; fp16 runs at the same rate)" if kind == "tensor" else ""),
+                "frac": ach / peak, "traffic": traffic, "peak_kind": peak_kind + (" (bf16 sustained; fp16 runs at the same rate)" if kind == "tensor" else ""),
                 "kernel_ms": stages[dom], "algorithmic_work_per_launch": work,
                 "all_stages": {k: {"ms": stages[k], "bound": alg[k][0],
                                    "frac": (alg[k][1] / (stages[k] * 1e-3) / (1e9 * hbm_peak if alg[k][0] == "hbm" else 1e12 * tensor_peak))}
@@ -405,7 +418,7 @@ def run_ours(args):
                    "samples_per_step": balg["M0"], "unique_voxels_touched": balg["U"],
                    "l2_policy": "working set (params+grads+Adam state = %.2f GB) larger than the 126 MB L2; "
                                 "%d distinct ray batches cycled" % (balg["G"] * 13 * 16 / 1e9, N_BATCHES),
-                   "algorithmic_bytes_per_step": balg["total"]},
+                   "algorithmic_bytes_per_step": balg["total"], "clock_ramp_s": args.ramp_s},
         "e2e": {"value": N_RAYS * world / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_host},
         "gpu_launches": int(launches),
