@@ -21,6 +21,15 @@ import torch.nn.functional as F
 from . import oracle as orc
 
 
+def set_ops(ns):
+    """Swap the provider of the reference's custom ops (default: the C oracle on the CPU).  The GPU tests pass a
+    namespace built from oracle/_ref -- the reference's OWN CUDA kernels -- to run and time the reference's op
+    sequence on the same B200 (tests/test_gpu_vs_ref.py).  Returns the previous provider."""
+    global orc
+    prev, orc = orc, ns
+    return prev
+
+
 class _Raw2Alpha(torch.autograd.Function):  # lib/dvgo.py:618-642
     @staticmethod
     def forward(ctx, density, shift, interval):
@@ -86,6 +95,17 @@ class RefDVGO:
         self.rgbnet_direct = rgbnet_direct
         self.opt_state = {}
 
+    def to(self, device):
+        """Move the state (GPU tests only: reference CUDA kernels from oracle/_ref as the op provider)."""
+        for n in ("xyz_min", "xyz_max", "mask", "xyz2ijk_scale", "xyz2ijk_shift", "viewfreq"):
+            setattr(self, n, getattr(self, n).to(device))
+        self.density = self.density.detach().to(device).requires_grad_()
+        self.k0 = self.k0.detach().to(device).requires_grad_()
+        if self.rgbnet is not None:
+            self.rgbnet = [(W.detach().to(device).requires_grad_(), b.detach().to(device).requires_grad_())
+                           for W, b in self.rgbnet]
+        return self
+
     def params(self):
         ps = {"density": self.density, "k0": self.k0}
         if self.rgbnet is not None:
@@ -130,14 +150,14 @@ class RefDVGO:
                 rgb = torch.sigmoid(self.mlp(torch.cat([k0, emb], -1)))  # :536-539
             else:
                 rgb = torch.sigmoid(self.mlp(torch.cat([k0[:, 3:], emb], -1)) + k0[:, :3])  # :541
-        rgb_marched = torch.zeros(N, 3).index_add(0, ray_id, weights.unsqueeze(-1) * rgb)  # :554-558
+        rgb_marched = torch.zeros(N, 3, device=rays_o.device).index_add(0, ray_id, weights.unsqueeze(-1) * rgb)  # :554-558
         rgb_marched = rgb_marched + alphainv_last.unsqueeze(-1) * bg  # :559
         ret = {"alphainv_last": alphainv_last, "weights": weights, "rgb_marched": rgb_marched,
                "raw_alpha": alpha, "raw_rgb": rgb, "ray_id": ray_id, "step_id": step_id,
                "N_steps": N_steps, "t_min": t_min, "t_max": t_max}
         if render_depth:
             with torch.no_grad():  # :569-576
-                ret["depth"] = torch.zeros(N).index_add(0, ray_id, weights * step_id)
+                ret["depth"] = torch.zeros(N, device=rays_o.device).index_add(0, ray_id, weights * step_id)
         return ret
 
     @staticmethod
