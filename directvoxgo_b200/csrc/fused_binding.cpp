@@ -7,6 +7,7 @@
 #include <torch/extension.h>
 
 #include "../../include/dvgo_b200_fused.h"
+#include "../../include/dvgo_b200_prep.h"
 
 namespace {
 
@@ -213,6 +214,114 @@ void zero_(Tensor t) {
   rc_check(dvgo_fused_zero(t.data_ptr(), t.numel(), cur_stream()), "zero");
 }
 
+// ---- include/dvgo_b200_prep.h: ray generation, training-ray preparation, whole-grid sweeps -------------------
+struct View {
+  dvgo_view_t v;
+  View(int H, int W, double fx, double fy, double cx, double cy, std::vector<double> c2w, bool inverse_y, bool flip_x,
+       bool flip_y, int mode, bool ndc, double ndc_sx, double ndc_sy) {
+    TORCH_CHECK(c2w.size() == 12, "c2w: 12 values (rows 0..2 of the 3x4 / 4x4 matrix)");
+    TORCH_CHECK(mode == 0 || mode == 1, "mode: 0 = lefttop, 1 = center");
+    v.H = H; v.W = W;
+    v.fx = static_cast<float>(fx); v.fy = static_cast<float>(fy); v.cx = static_cast<float>(cx); v.cy = static_cast<float>(cy);
+    for (int i = 0; i < 12; ++i) v.c2w[i] = static_cast<float>(c2w[i]);
+    v.inverse_y = inverse_y; v.flip_x = flip_x; v.flip_y = flip_y; v.mode = mode; v.ndc = ndc;
+    v.ndc_sx = static_cast<float>(ndc_sx); v.ndc_sy = static_cast<float>(ndc_sy);
+  }
+};
+
+void rays_of_view(const View& v, int64_t pix_begin, int64_t n_pix, c10::optional<Tensor> rays_o,
+                  c10::optional<Tensor> rays_d, c10::optional<Tensor> viewdirs) {
+  const Tensor* any = nullptr;
+  for (auto* t : {&rays_o, &rays_d, &viewdirs})
+    if (t->has_value()) {
+      chk(**t, "rays_of_view output", torch::kFloat32);
+      TORCH_CHECK((*t)->numel() >= 3 * n_pix, "rays_of_view: output too small");
+      any = &**t;
+    }
+  TORCH_CHECK(any, "rays_of_view: no output given");
+  const c10::cuda::CUDAGuard guard(any->device());
+  rc_check(dvgo_rays_of_view(&v.v, pix_begin, n_pix, rays_o.has_value() ? fpm(*rays_o) : nullptr,
+                             rays_d.has_value() ? fpm(*rays_d) : nullptr,
+                             viewdirs.has_value() ? fpm(*viewdirs) : nullptr, cur_stream()), "rays_of_view");
+}
+
+Tensor hit_coarse_geo(const Scene& sc, Tensor rays_o, Tensor rays_d) {
+  F32(rays_o); F32(rays_d);
+  TORCH_CHECK(rays_o.dim() == 2 && rays_o.size(1) == 3 && rays_d.sizes() == rays_o.sizes(), "rays must be [N,3]");
+  const c10::cuda::CUDAGuard guard(rays_o.device());
+  auto hit = torch::empty({rays_o.size(0)}, rays_o.options().dtype(torch::kBool));
+  rc_check(dvgo_hit_coarse_geo(&sc.s, fp(rays_o), fp(rays_d), rays_o.size(0),
+                               reinterpret_cast<uint8_t*>(hit.data_ptr<bool>()), cur_stream()), "hit_coarse_geo");
+  return hit;
+}
+
+Tensor view_hit_coarse_geo(const View& v, const Scene& sc) {
+  const c10::cuda::CUDAGuard guard(sc.xyz_min.device());
+  auto hit = torch::empty({v.v.H, v.v.W}, sc.xyz_min.options().dtype(torch::kBool));
+  rc_check(dvgo_view_hit_coarse_geo(&v.v, &sc.s, reinterpret_cast<uint8_t*>(hit.data_ptr<bool>()), cur_stream()),
+           "view_hit_coarse_geo");
+  return hit;
+}
+
+void view_gather_rays(const View& v, Tensor hit, Tensor pos_incl, Tensor top, c10::optional<Tensor> img, Tensor rgb_tr,
+                      Tensor rays_o_tr, Tensor rays_d_tr, Tensor viewdirs_tr) {
+  chk(hit, "hit", torch::kBool); chk(pos_incl, "pos_incl", torch::kInt64); chk(top, "top", torch::kInt64);
+  F32(rgb_tr); F32(rays_o_tr); F32(rays_d_tr); F32(viewdirs_tr);
+  const int64_t n = static_cast<int64_t>(v.v.H) * v.v.W;
+  TORCH_CHECK(hit.numel() == n && pos_incl.numel() == n && top.numel() == 1, "view_gather_rays: size mismatch");
+  if (img.has_value()) { chk(*img, "img", torch::kFloat32); TORCH_CHECK(img->numel() == 3 * n, "img must be [H,W,3]"); }
+  const c10::cuda::CUDAGuard guard(hit.device());
+  rc_check(dvgo_view_gather_rays(&v.v, reinterpret_cast<const uint8_t*>(hit.data_ptr<bool>()),
+                                 pos_incl.data_ptr<int64_t>(), top.data_ptr<int64_t>(),
+                                 img.has_value() ? fp(*img) : nullptr, fpm(rgb_tr), fpm(rays_o_tr), fpm(rays_d_tr),
+                                 fpm(viewdirs_tr), cur_stream()), "view_gather_rays");
+}
+
+void voxel_count_scatter(Tensor rays_o, Tensor rays_d, Tensor xyz_min, Tensor xyz_max, double near, double far,
+                         double stepdist, int n_samples, Tensor acc) {
+  F32(rays_o); F32(rays_d); F32(xyz_min); F32(xyz_max); F32(acc);
+  TORCH_CHECK(acc.dim() == 3, "acc must be [X,Y,Z]");
+  const c10::cuda::CUDAGuard guard(acc.device());
+  rc_check(dvgo_voxel_count_scatter(fp(rays_o), fp(rays_d), rays_o.numel() / 3, fp(xyz_min), fp(xyz_max), acc.size(0),
+                                    acc.size(1), acc.size(2), static_cast<float>(near), static_cast<float>(far),
+                                    static_cast<float>(stepdist), n_samples, fpm(acc), cur_stream()), "voxel_count_scatter");
+}
+
+void voxel_count_commit(Tensor acc, Tensor count) {
+  F32(acc); F32(count);
+  TORCH_CHECK(acc.numel() == count.numel(), "voxel_count_commit: size mismatch");
+  const c10::cuda::CUDAGuard guard(acc.device());
+  rc_check(dvgo_voxel_count_commit(fpm(acc), fpm(count), acc.numel(), cur_stream()), "voxel_count_commit");
+}
+
+Tensor alpha_maxpool_mask(Tensor density, double act_shift, double interval, double thres, c10::optional<Tensor> mask_in) {
+  F32(density);
+  TORCH_CHECK(density.dim() >= 3, "density must be [...,X,Y,Z]");
+  const int d = density.dim();
+  const int X = density.size(d - 3), Y = density.size(d - 2), Z = density.size(d - 1);
+  TORCH_CHECK(density.numel() == static_cast<int64_t>(X) * Y * Z, "density must have one channel");
+  const c10::cuda::CUDAGuard guard(density.device());
+  if (mask_in.has_value()) { chk(*mask_in, "mask_in", torch::kBool); TORCH_CHECK(mask_in->numel() == density.numel(), "mask size"); }
+  auto out = torch::empty({X, Y, Z}, density.options().dtype(torch::kBool));
+  auto tmp = torch::empty({X, Y, Z}, density.options());
+  rc_check(dvgo_alpha_maxpool_mask(fp(density), X, Y, Z, static_cast<float>(act_shift), static_cast<float>(interval),
+                                   static_cast<float>(thres),
+                                   mask_in.has_value() ? reinterpret_cast<const uint8_t*>(mask_in->data_ptr<bool>()) : nullptr,
+                                   reinterpret_cast<uint8_t*>(out.data_ptr<bool>()), fpm(tmp), cur_stream()),
+           "alpha_maxpool_mask");
+  return out;
+}
+
+Tensor resize_trilinear(Tensor src, int X2, int Y2, int Z2) {
+  F32(src);
+  TORCH_CHECK(src.dim() == 5 && src.size(0) == 1, "src must be [1,C,X,Y,Z]");
+  const c10::cuda::CUDAGuard guard(src.device());
+  auto dst = torch::empty({1, src.size(1), X2, Y2, Z2}, src.options());
+  rc_check(dvgo_resize_trilinear(fp(src), src.size(1), src.size(2), src.size(3), src.size(4), fpm(dst), X2, Y2, Z2,
+                                 cur_stream()), "resize_trilinear");
+  return dst;
+}
+
 }  // namespace
 
 void dvgo_bind_mlp(pybind11::module_& m);  // mlp_binding.cpp
@@ -241,5 +350,16 @@ void dvgo_bind_fused(pybind11::module_& m) {
   m.def("ncdhw_to_cl", &ncdhw_to_cl);
   m.def("cl_to_ncdhw", &cl_to_ncdhw);
   m.def("zero_", &zero_);
+  pybind11::class_<View>(m, "View")
+      .def(pybind11::init<int, int, double, double, double, double, std::vector<double>, bool, bool, bool, int, bool,
+                          double, double>());
+  m.def("rays_of_view", &rays_of_view);
+  m.def("hit_coarse_geo", &hit_coarse_geo);
+  m.def("view_hit_coarse_geo", &view_hit_coarse_geo);
+  m.def("view_gather_rays", &view_gather_rays);
+  m.def("voxel_count_scatter", &voxel_count_scatter);
+  m.def("voxel_count_commit", &voxel_count_commit);
+  m.def("alpha_maxpool_mask", &alpha_maxpool_mask);
+  m.def("resize_trilinear", &resize_trilinear);
   dvgo_bind_mlp(m);
 }

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import render_utils_cuda, total_variation_cuda
+from . import _C, render_utils_cuda, total_variation_cuda
 from .ops import Alphas2Weights, Raw2Alpha, grid_sample_trilinear, segment_coo
 
 
@@ -164,47 +164,52 @@ class DirectVoxGO(nn.Module):
 
     @torch.no_grad()
     def scale_volume_grid(self, num_voxels):
-        """Progressive growing (lib/dvgo.py:228-263): trilinear up-sampling of both grids and a fresh
-        occupancy mask = maxpool3(alpha) > fast_color_thres (AND the coarse mask when there is one)."""
+        """Progressive growing (lib/dvgo.py:228-263): trilinear up-sampling of both grids (`dvgo_resize_trilinear`,
+        ATen's align_corners=True arithmetic) and a fresh occupancy mask = maxpool3(alpha) > fast_color_thres
+        (`dvgo_alpha_maxpool_mask`), AND the coarse mask when there is one."""
         self._set_grid_resolution(num_voxels)
         size = tuple(int(s) for s in self.world_size)
-        self.density = nn.Parameter(F.interpolate(self.density.data, size=size, mode="trilinear", align_corners=True))
+        self.density = nn.Parameter(_C.ext.resize_trilinear(self.density.data.contiguous(), *size))
         if self.k0_dim > 0:
-            self.k0 = nn.Parameter(F.interpolate(self.k0.data, size=size, mode="trilinear", align_corners=True))
+            self.k0 = nn.Parameter(_C.ext.resize_trilinear(self.k0.data.contiguous(), *size))
         else:
             self.k0 = nn.Parameter(torch.zeros([1, self.k0_dim, *size], device=self.density.device))
-        alpha = F.max_pool3d(self.activate_density(self.density), kernel_size=3, padding=1, stride=1)[0, 0]
-        mask = alpha > self.fast_color_thres
+        mask = _C.ext.alpha_maxpool_mask(self.density.data, float(self.act_shift), float(self.voxel_size_ratio),
+                                         float(self.fast_color_thres), None)
         if self.mask_cache_path:
             coarse = MaskCache(path=self.mask_cache_path, mask_cache_thres=self.mask_cache_thres).to(self.xyz_min.device)
             mask &= coarse(_grid_points(self.xyz_min, self.xyz_max, size))
         self.mask_cache = MaskCache(mask=mask, xyz_min=self.xyz_min, xyz_max=self.xyz_max)
 
+    @torch.no_grad()
+    def update_occupancy_cache(self):
+        """The periodic occupancy refresh of the training loop (run.py:330-332), in place:
+        mask &= maxpool3(alpha(density)) > fast_color_thres."""
+        m = self.mask_cache.mask
+        assert m.shape == self.density.shape[2:], "the refresh needs the mask at the density resolution (run.py:331)"
+        m.copy_(_C.ext.alpha_maxpool_mask(self.density.data, float(self.act_shift), float(self.voxel_size_ratio),
+                                          float(self.fast_color_thres), m))
+
+    @torch.no_grad()
     def voxel_count_views(self, rays_o_tr, rays_d_tr, imsz, near, far, stepsize, downrate=1, irregular_shape=False):
-        """How many training views see each voxel (lib/dvgo.py:265-295) -- the scatter-only use of the
-        trilinear backward: grad of sum(sample(ones)) w.r.t. `ones`, thresholded at > 1 per view."""
+        """How many training views see each voxel (lib/dvgo.py:265-295) -- the scatter-only use of the trilinear
+        backward: grad of sum(sample(ones)) w.r.t. `ones`, thresholded at > 1 per view.  One kernel per view
+        scatters the trilinear weights of every (ray, sample) straight into a per-view accumulator (no point
+        tensor, no autograd graph), a second folds `acc > 1` into the count and re-zeroes it."""
         t0 = time.time()
         n_samples = int(np.linalg.norm(np.array(self.density.shape[2:]) + 1) / stepsize) + 1
         device = self.density.device
-        rng = torch.arange(n_samples, device=device)[None].float()
+        stepdist = float(stepsize * self.voxel_size)
         count = torch.zeros_like(self.density.detach())
+        acc = torch.zeros(tuple(self.density.shape[2:]), device=device)
         for ro_v, rd_v in zip(rays_o_tr.split(imsz), rays_d_tr.split(imsz)):
-            ones = torch.ones_like(self.density).requires_grad_()
-            if irregular_shape:
-                ro_c, rd_c = ro_v.split(10000), rd_v.split(10000)
-            else:
-                ro_c = ro_v[::downrate, ::downrate].to(device).flatten(0, -2).split(10000)
-                rd_c = rd_v[::downrate, ::downrate].to(device).flatten(0, -2).split(10000)
-            for ro, rd in zip(ro_c, rd_c):
-                vec = torch.where(rd == 0, torch.full_like(rd, 1e-6), rd)
-                ra, rb = (self.xyz_max - ro) / vec, (self.xyz_min - ro) / vec
-                t_min = torch.minimum(ra, rb).amax(-1).clamp(min=near, max=far)
-                step = stepsize * self.voxel_size * rng
-                interpx = t_min[..., None] + step / rd.norm(dim=-1, keepdim=True)
-                pts = ro[..., None, :] + rd[..., None, :] * interpx[..., None]
-                self.grid_sampler(pts, ones).sum().backward()
-            with torch.no_grad():
-                count += (ones.grad > 1)
+            if not irregular_shape:
+                ro_v, rd_v = ro_v[::downrate, ::downrate], rd_v[::downrate, ::downrate]
+            ro = ro_v.to(device).reshape(-1, 3).contiguous()
+            rd = rd_v.to(device).reshape(-1, 3).contiguous()
+            _C.ext.voxel_count_scatter(ro, rd, self.xyz_min, self.xyz_max, float(near), float(far), stepdist,
+                                       n_samples, acc)
+            _C.ext.voxel_count_commit(acc, count)
         self._last_count_seconds = time.time() - t0
         return count
 
@@ -229,18 +234,24 @@ class DirectVoxGO(nn.Module):
         return out[0] if len(out) == 1 else out
 
     # ------------------------------------------------------------------ ray sampling
+    def coarse_geo_scene(self, near, far, stepsize, **render_kwargs):
+        """Scene constants for the occupancy-only kernels (hit test, training-ray preparation)."""
+        mc = self.mask_cache
+        X, Y, Z = (int(v) for v in self.density.shape[2:])
+        return _C.ext.Scene(X, Y, Z, max(int(self.k0.shape[1]), 1), self.xyz_min, self.xyz_max, mc.mask,
+                            mc.xyz2ijk_scale, mc.xyz2ijk_shift, float(near), float(far),
+                            float(stepsize * self.voxel_size), float(self.act_shift),
+                            float(stepsize * self.voxel_size_ratio), float(self.fast_color_thres), False, 0)
+
+    @torch.no_grad()
     def hit_coarse_geo(self, rays_o, rays_d, near, far, stepsize, **render_kwargs):
-        """Which rays touch occupied space at all (lib/dvgo.py:412-423)."""
+        """Which rays touch occupied space at all (lib/dvgo.py:412-423): one warp per ray walks the samples and
+        stops at the first one that is inside the bbox and occupied (`dvgo_hit_coarse_geo`)."""
         shape = rays_o.shape[:-1]
-        rays_o = rays_o.reshape(-1, 3).contiguous()
-        rays_d = rays_d.reshape(-1, 3).contiguous()
-        stepdist = float(stepsize * self.voxel_size)
-        pts, outside, ray_id = render_utils_cuda.sample_pts_on_rays(
-            rays_o, rays_d, self.xyz_min, self.xyz_max, near, far, stepdist)[:3]
-        keep = (~outside).nonzero(as_tuple=True)[0]
-        occ = self.mask_cache(pts[keep])
-        hit = torch.zeros(len(rays_o), dtype=torch.bool, device=rays_o.device)
-        hit[ray_id[keep][occ]] = True
+        dev = self.density.device
+        rays_o = rays_o.reshape(-1, 3).to(dev).contiguous()
+        rays_d = rays_d.reshape(-1, 3).to(dev).contiguous()
+        hit = _C.ext.hit_coarse_geo(self.coarse_geo_scene(near, far, stepsize), rays_o, rays_d)
         return hit.reshape(shape)
 
     def sample_ray(self, rays_o, rays_d, near, far, stepsize, is_train=0, **render_kwargs):

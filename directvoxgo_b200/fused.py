@@ -173,6 +173,35 @@ class FusedRenderer(_FusedBase):
             out["depth"] = ws.depth_acc.clone()
         return out
 
+    @torch.no_grad()
+    def render_view(self, H, W, K, c2w, ndc=False, inverse_y=False, flip_x=False, flip_y=False, chunk=65536,
+                    render_depth=True):
+        """One full view (run.py:82-99): the rays of each chunk of pixels are generated on the device straight
+        into a reusable [chunk,3] workspace (`dvgo_rays_of_view`, lib/ray_utils.py:80-85) instead of three
+        [H*W,3] tensors per view, then rendered.  Returns [H,W,3] rgb, [H,W] depth / alphainv_last."""
+        from .ray_utils import make_view
+        view = make_view(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y)
+        n = H * W
+        chunk = min(chunk, n)
+        if getattr(self, "_view_rays", None) is None or self._view_rays[0].shape[0] != chunk:
+            self._view_rays = [torch.empty(chunk, 3, device=self.device) for _ in range(3)]
+        ro, rd, vd = self._view_rays
+        rgb = torch.empty(n, 3, device=self.device)
+        last = torch.empty(n, device=self.device)
+        depth = torch.empty(n, device=self.device) if render_depth else None
+        for p0 in range(0, n, chunk):
+            m = min(chunk, n - p0)
+            ext.rays_of_view(view, p0, m, ro, rd, vd)
+            out = self.render(ro[:m], rd[:m], vd[:m], render_depth)
+            rgb[p0:p0 + m] = out["rgb_marched"]
+            last[p0:p0 + m] = out["alphainv_last"]
+            if render_depth:
+                depth[p0:p0 + m] = out["depth"]
+        res = {"rgb_marched": rgb.reshape(H, W, 3), "alphainv_last": last.reshape(H, W)}
+        if render_depth:
+            res["depth"] = depth.reshape(H, W)
+        return res
+
     def _tc_forward(self, ws, viewdirs):
         from .fused_mlp import TensorCoreMLP
         if not hasattr(self, "_tc"):
@@ -183,7 +212,7 @@ class FusedRenderer(_FusedBase):
 
 class FusedTrainer(_FusedBase):
     def __init__(self, model, cfg_train, render_kwargs, world_size=1, dist_group=None, mlp="auto",
-                 betas=(0.9, 0.99), eps=1e-8, rank=None, shard_sweep=True):
+                 betas=(0.9, 0.99), eps=1e-8, rank=None, shard_sweep=True, global_step=0):
         super().__init__(model, render_kwargs, mlp)
         self.cfg = dict(cfg_train)
         self.world_size = world_size
@@ -194,7 +223,7 @@ class FusedTrainer(_FusedBase):
             rank = dist.get_rank(dist_group)
         self.rank = rank or 0
         self.betas, self.eps = betas, eps
-        self.global_step = 0
+        self.global_step = global_step        # resume point: lr pre-decayed as lib/utils.py:21-22 does
         self.opt_step = 0
         z = torch.zeros_like
         self.density_next = torch.empty_like(self.density)
@@ -205,6 +234,8 @@ class FusedTrainer(_FusedBase):
         self.lr = {k: float(self.cfg.get("lrate_" + k, 0.0)) for k in ("density", "k0", "rgbnet")}
         decay_steps = self.cfg.get("lrate_decay", 20) * 1000
         self.decay = 0.1 ** (1.0 / decay_steps)
+        for k in self.lr:
+            self.lr[k] *= 0.1 ** (global_step / decay_steps)
         skip = self.cfg.get("skip_zero_grad_fields", []) or []
         self.masked = {k: (k in skip) for k in ("density", "k0")}
         self.rgbnet_state = {}
@@ -389,6 +420,78 @@ class FusedTrainer(_FusedBase):
                                            self.lr["rgbnet"], self.eps)
         for k in self.lr:  # run.py:401-406
             self.lr[k] *= self.decay
+
+    # -- optimiser state in the reference's MaskedAdam.state_dict() format (checkpoint boundary, run.py:420-437) --
+    def _opt_entries(self):
+        """(group name, [parameter names]) in the reference's group order (lrate_* keys of cfg_train that exist
+        on the model and have lr > 0, lib/utils.py:24-44)."""
+        out = []
+        for key in self.cfg:
+            if not key.startswith("lrate_") or key == "lrate_decay":
+                continue
+            name = key[len("lrate_"):]
+            if name in ("density", "k0") and self.lr.get(name, 0) > 0:
+                out.append((name, [name]))
+            elif name == "rgbnet" and self.model.rgbnet is not None and self.lr.get(name, 0) > 0:
+                out.append((name, ["rgbnet." + n for n, _ in self.model.rgbnet.named_parameters()]))
+        return out
+
+    @torch.no_grad()
+    def optimizer_state_dict(self):
+        state, groups, idx = {}, [], 0
+        for name, pnames in self._opt_entries():
+            ids = []
+            if name == "density":
+                tensors = [(self.m_density.reshape(1, 1, self.X, self.Y, self.Z).clone(),
+                            self.v_density.reshape(1, 1, self.X, self.Y, self.Z).clone())]
+            elif name == "k0":
+                tensors = [(ext.cl_to_ncdhw(self.m_k0), ext.cl_to_ncdhw(self.v_k0))]
+            elif self.mlp_mode == "tc":
+                tensors = [(m.clone(), v.clone()) for m, v in zip(self._tc.unflatten(self._tc.exp_avg),
+                                                                  self._tc.unflatten(self._tc.exp_avg_sq))]
+            else:
+                tensors = []
+                for p in self.model.rgbnet.parameters():
+                    st = self.rgbnet_state.get(p)
+                    tensors.append((st["exp_avg"].clone(), st["exp_avg_sq"].clone()) if st else
+                                   (torch.zeros_like(p), torch.zeros_like(p)))
+            for m, v in tensors:
+                if self.opt_step > 0:
+                    state[idx] = {"step": self.opt_step, "exp_avg": m, "exp_avg_sq": v}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": self.lr[name], "skip_zero_grad": bool(self.masked.get(name, False)),
+                           "betas": tuple(self.betas), "eps": self.eps, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_optimizer_state_dict(self, sd):
+        """Accepts the `optimizer_state_dict` of a reference checkpoint (same model, same cfg_train)."""
+        entries = self._opt_entries()
+        assert len(entries) == len(sd["param_groups"]), "optimizer groups do not match cfg_train"
+        steps = set()
+        for (name, _), grp in zip(entries, sd["param_groups"]):
+            self.lr[name] = float(grp["lr"])
+            sts = [sd["state"].get(i) for i in grp["params"]]
+            if any(s is None for s in sts):
+                continue
+            steps.update(int(s["step"]) for s in sts)
+            dev = self.device
+            if name == "density":
+                self.m_density.copy_(sts[0]["exp_avg"].to(dev).reshape(self.X, self.Y, self.Z))
+                self.v_density.copy_(sts[0]["exp_avg_sq"].to(dev).reshape(self.X, self.Y, self.Z))
+            elif name == "k0":
+                self.m_k0.copy_(ext.ncdhw_to_cl(sts[0]["exp_avg"].to(dev).float().contiguous()))
+                self.v_k0.copy_(ext.ncdhw_to_cl(sts[0]["exp_avg_sq"].to(dev).float().contiguous()))
+            elif self.mlp_mode == "tc":
+                self._tc.exp_avg.copy_(torch.cat([s["exp_avg"].reshape(-1) for s in sts]).to(dev))
+                self._tc.exp_avg_sq.copy_(torch.cat([s["exp_avg_sq"].reshape(-1) for s in sts]).to(dev))
+            else:
+                for p, s in zip(self.model.rgbnet.parameters(), sts):
+                    self.rgbnet_state[p] = {"exp_avg": s["exp_avg"].to(dev).clone(),
+                                            "exp_avg_sq": s["exp_avg_sq"].to(dev).clone()}
+        assert len(steps) <= 1, "parameters with different step counts are not supported"
+        self.opt_step = steps.pop() if steps else 0
 
     @torch.no_grad()
     def sync_to_model(self):
