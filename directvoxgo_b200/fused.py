@@ -107,7 +107,7 @@ class _FusedBase:
     @staticmethod
     def _tc_supported(model):
         lin = [m for m in model.rgbnet.modules() if isinstance(m, torch.nn.Linear)]
-        return (len(lin) == 3 and lin[0].out_features == 128 and lin[1].out_features == 128 and
+        return (len(lin) == 3 and lin[0].out_features <= 128 and lin[1].out_features == lin[0].out_features and
                 getattr(model, "rgbnet_direct", True) and getattr(model, "posbase_pe", 0) == 0)
 
     def _workspace(self, n_rays, train):
@@ -484,8 +484,9 @@ class FusedTrainer(_FusedBase):
                 self.m_k0.copy_(ext.ncdhw_to_cl(sts[0]["exp_avg"].to(dev).float().contiguous()))
                 self.v_k0.copy_(ext.ncdhw_to_cl(sts[0]["exp_avg_sq"].to(dev).float().contiguous()))
             elif self.mlp_mode == "tc":
-                self._tc.exp_avg.copy_(torch.cat([s["exp_avg"].reshape(-1) for s in sts]).to(dev))
-                self._tc.exp_avg_sq.copy_(torch.cat([s["exp_avg_sq"].reshape(-1) for s in sts]).to(dev))
+                for key, flat in (("exp_avg", self._tc.exp_avg), ("exp_avg_sq", self._tc.exp_avg_sq)):
+                    for dst, s in zip(self._tc.unflatten(flat), sts):
+                        dst.copy_(s[key].to(dev))
             else:
                 for p, s in zip(self.model.rgbnet.parameters(), sts):
                     self.rgbnet_state[p] = {"exp_avg": s["exp_avg"].to(dev).clone(),

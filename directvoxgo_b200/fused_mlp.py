@@ -9,26 +9,43 @@ from . import adam_upd_cuda, ext
 
 
 class TensorCoreMLP:
+    """Hidden widths below 128 (e.g. the LLFF configs' rgbnet_width=64, configs/llff/llff_default.py:30) run on
+    the same 128-wide kernels with the weights zero-padded: a padded unit has z = 0, ReLU output 0 and ReLU
+    derivative 0, so it contributes nothing forward or backward, its gradients are exactly 0 and Adam leaves it
+    at 0 -- the padded network IS the narrow one."""
     WIDTH = 128
 
     def __init__(self, rgbnet, device, train=False):
         lin = [m for m in rgbnet.modules() if isinstance(m, torch.nn.Linear)]
-        if len(lin) != 3 or lin[0].out_features != self.WIDTH or lin[1].in_features != self.WIDTH or \
-                lin[1].out_features != self.WIDTH or lin[2].out_features != 3:
-            raise NotImplementedError("tensor-core rgbnet: depth 3, width 128, 3 outputs (the configs' default)")
+        if len(lin) != 3 or lin[0].out_features > self.WIDTH or lin[1].in_features != lin[0].out_features or \
+                lin[1].out_features != lin[0].out_features or lin[2].out_features != 3:
+            raise NotImplementedError("tensor-core rgbnet: depth 3, width <= 128, 3 outputs (the configs' defaults)")
         self.d_in = lin[0].in_features
+        self.width = lin[0].out_features
         self.lin = lin
-        flat = [t.detach().reshape(-1) for l in lin for t in (l.weight, l.bias)]
-        self.params = torch.cat(flat).to(device=device, dtype=torch.float32).contiguous()
+        W, d = self.WIDTH, self.d_in
+        self._sizes = [W * d, W, W * W, W, 3 * W, 3]
+        self.params = torch.zeros(sum(self._sizes), device=device, dtype=torch.float32)
+        self.refresh_from_module()
         self.train = train
         if train:
             self.grad_flat = torch.zeros_like(self.params)
             self.exp_avg = torch.zeros_like(self.params)
             self.exp_avg_sq = torch.zeros_like(self.params)
 
+    def unflatten(self, flat):
+        """Views of a flat padded buffer with the shapes of [W1, b1, W2, b2, W3, b3] of the real (narrow) network."""
+        W, d, w = self.WIDTH, self.d_in, self.width
+        o = [0]
+        for n in self._sizes:
+            o.append(o[-1] + n)
+        return [flat[o[0]:o[1]].view(W, d)[:w], flat[o[1]:o[2]][:w], flat[o[2]:o[3]].view(W, W)[:w, :w],
+                flat[o[3]:o[4]][:w], flat[o[4]:o[5]].view(3, W)[:, :w], flat[o[5]:o[6]]]
+
+    @torch.no_grad()
     def refresh_from_module(self):
-        flat = [t.detach().reshape(-1) for l in self.lin for t in (l.weight, l.bias)]
-        self.params.copy_(torch.cat(flat))
+        for dst, src in zip(self.unflatten(self.params), [t for l in self.lin for t in (l.weight, l.bias)]):
+            dst.copy_(src.detach())
 
     def pad_embedding(self, pe):
         """[N,P] view embedding -> [N,P_pad] table: column P = 1 (carries b1 through the first GEMM), then
@@ -54,15 +71,6 @@ class TensorCoreMLP:
 
     def adam_step(self, step, beta1, beta2, lr, eps):
         adam_upd_cuda.adam_upd(self.params, self.grad_flat, self.exp_avg, self.exp_avg_sq, step, beta1, beta2, lr, eps)
-
-    def unflatten(self, flat):
-        out, o = [], 0
-        for l in self.lin:
-            for t in (l.weight, l.bias):
-                n = t.numel()
-                out.append(flat[o:o + n].view_as(t))
-                o += n
-        return out
 
     @torch.no_grad()
     def sync_to_module(self, rgbnet=None):

@@ -205,6 +205,12 @@ def test_fused_dmpigo_render_and_step(golden_dir):
     np.testing.assert_allclose(to_np(out["rgb_marched"]), g["out_rgb_marched"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(to_np(out["alphainv_last"]), g["out_alphainv_last"], rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(to_np(out["depth"]), g["out_depth"], rtol=1e-5, atol=1e-3)
+    # the 64-wide rgbnet on the tensor-core kernels (zero-padded to 128): fp16-operand tolerance
+    r_tc = FusedRenderer(m, dict(near=0, far=1, bg=0.0, stepsize=0.5))
+    assert r_tc.mlp_mode == "tc"
+    out_tc = r_tc.render(ro, rd, vd)
+    np.testing.assert_allclose(to_np(out_tc["rgb_marched"]), g["out_rgb_marched"], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(to_np(out_tc["alphainv_last"]), g["out_alphainv_last"], rtol=1e-5, atol=2e-6)
 
 
 @pytest.mark.parametrize("n_rays", [1, 33, 1000])

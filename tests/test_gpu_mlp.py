@@ -35,12 +35,12 @@ def test_tcgen05_descriptor_orientations(N, K, a_mn, b_mn):
     assert err < 2e-6, (N, K, a_mn, b_mn, err)
 
 
-def _make_mlp(seed, d_in=39):
+def _make_mlp(seed, d_in=39, width=128):
     torch.manual_seed(seed)
     net = torch.nn.Sequential(
-        torch.nn.Linear(d_in, 128), torch.nn.ReLU(inplace=True),
-        torch.nn.Sequential(torch.nn.Linear(128, 128), torch.nn.ReLU(inplace=True)),
-        torch.nn.Linear(128, 3))
+        torch.nn.Linear(d_in, width), torch.nn.ReLU(inplace=True),
+        torch.nn.Sequential(torch.nn.Linear(width, width), torch.nn.ReLU(inplace=True)),
+        torch.nn.Linear(width, 3))
     with torch.no_grad():
         for p in net.parameters():
             p.add_(torch.randn_like(p) * 0.05)   # non-zero biases everywhere
@@ -77,6 +77,44 @@ def test_tc_mlp_forward(M, C, P):
     assert torch.all(rgb[M:] == -7.0)                                    # nothing written past the count
     np.testing.assert_allclose(to_np(rgb[:M]), to_np(emu), rtol=0, atol=1e-4)   # same rounding model (fp16 ties may flip)
     np.testing.assert_allclose(to_np(rgb[:M]), to_np(ref), rtol=0, atol=2e-3)   # stated tolerance vs exact fp32
+
+
+def test_tc_mlp_narrow_width_runs_zero_padded():
+    """rgbnet_width=64 (configs/llff/llff_default.py:30), 9 features + 3 view dims: the 128-wide kernels on
+    zero-padded weights.  Forward within the fp16-operand tolerance of exact fp32; gradients of the real entries
+    within the usual relative-L2 bound; gradients of every padded entry EXACTLY zero; one Adam step leaves the
+    padding at zero."""
+    from directvoxgo_b200.fused_mlp import TensorCoreMLP
+    M, C, P, n_global = 5000, 9, 3, 4096
+    net = _make_mlp(11, C + P, width=64)
+    feat, pe, s_ray, counters, cap = _stream(M, 200, C, P, 5)
+    tc = TensorCoreMLP(net, DEV, train=True)
+    rgb = torch.zeros(cap, 3, device=DEV)
+    d_feat = torch.zeros(cap, C, device=DEV)
+    pe_pad = tc.pad_embedding(pe)
+    tc.forward(feat, s_ray, pe_pad, counters, rgb)
+    x = torch.cat([feat[:M], pe[s_ray[:M].long()]], -1).requires_grad_()
+    ref = torch.sigmoid(net(x))
+    np.testing.assert_allclose(to_np(rgb[:M]), to_np(ref.detach()), rtol=0, atol=2e-3)
+    g = torch.Generator().manual_seed(1)
+    d_rgb = (torch.randn(cap, 3, generator=g) / (3 * n_global)).to(DEV)
+    tc.backward(feat, s_ray, pe_pad, counters, rgb, d_rgb, d_feat, n_global)
+    for p in net.parameters():
+        p.grad = None
+    ref.backward(d_rgb[:M])
+    real = tc.unflatten(tc.grad_flat)
+    for gt, pr in zip(real, net.parameters()):
+        assert gt.shape == pr.grad.shape
+        assert float((gt - pr.grad).norm() / pr.grad.norm()) < 5e-2
+    assert float((d_feat[:M] - x.grad[:, :C]).norm() / x.grad[:, :C].norm()) < 5e-2
+    pad_mask = torch.ones_like(tc.grad_flat, dtype=torch.bool)
+    for v in tc.unflatten(pad_mask):
+        v.fill_(False)
+    assert pad_mask.sum() > 0 and torch.all(tc.grad_flat[pad_mask] == 0)
+    tc.adam_step(1, 0.9, 0.99, 1e-3, 1e-8)
+    assert torch.all(tc.params[pad_mask] == 0)
+    tc.sync_to_module()
+    assert all(torch.isfinite(p).all() for p in net.parameters())
 
 
 def _emulate_backward(net, x, d_rgb, rgb, scale):
