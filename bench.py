@@ -140,7 +140,7 @@ def algorithmic_bytes(model, batch, rk):
             "total": U * (1 + C) * 4 * 3 + E * 4 + G * (1 + C) * 28}
 
 
-def render_metric(model, rk, device, n_frames=2, chunk=65536, sphere=False):
+def render_metric(model, rk, device, n_frames=2, chunk=65536, sphere=False, rank=0, world=1):
     """Secondary metric of BASELINE.json: ms per rendered 800x800 frame (run.py:57-110: rays of a view ->
     chunks -> forward, render_depth=True), device-timed with CUDA events, rays generated on the device.
     sphere=True: the 'procedural occupancy' variant of SURVEY.md 8d (density +5 inside a ball of radius 0.6
@@ -163,30 +163,31 @@ def render_metric(model, rk, device, n_frames=2, chunk=65536, sphere=False):
     renderer = FusedRenderer(m, rk)
     H = W = syn.BLENDER["H"]
     K = syn.intrinsics(H, W)
-    poses = syn.random_poses(n_frames + 1, seed=4242)
-    samples = 0
-
-    def frame(c2w):
-        nonlocal samples
-        ro, rd, vd = syn.rays_of_view(H, W, K, c2w, device=device)
-        ro, rd, vd = ro.reshape(-1, 3), rd.reshape(-1, 3), vd.reshape(-1, 3)
-        out = []
-        for i in range(0, ro.shape[0], chunk):
-            o = renderer.render(ro[i:i + chunk].contiguous(), rd[i:i + chunk].contiguous(), vd[i:i + chunk].contiguous())
-            out.append(o["rgb_marched"])
-        return torch.cat(out)
-
-    frame(poses[0])  # warm-up (allocates the workspace)
+    # BASELINE config 3: whole views are sharded over the ranks (view i -> rank i mod world), no communication;
+    # every rank renders n_frames views, the aggregate is (n_frames * world) frames in the max-over-ranks time.
+    from directvoxgo_b200.parallel import shard_views
+    poses = syn.random_poses(n_frames * world + 1, seed=4242)
+    mine = [poses[1 + i] for i in shard_views(n_frames * world, rank, world)]
+    renderer.render_view(H, W, K, poses[0], chunk=chunk)  # warm-up (allocates the workspace)
     torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for c2w in poses[1:]:
-        img = frame(c2w)
+    for c2w in mine:   # rays generated on the device per 65 536-pixel chunk (dvgo_rays_of_view), then rendered
+        img = renderer.render_view(H, W, K, c2w, chunk=chunk)["rgb_marched"]
     ev1.record()
     torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
     ws = renderer._workspace(min(chunk, H * W), False)
-    return {"ms_per_frame": ev0.elapsed_time(ev1) / n_frames, "frames": n_frames, "rays_per_call": chunk,
-            "resolution": "%dx%d" % (H, W), "grid": "sphere-occupancy (extra)" if sphere else "random-init N(0,1), nothing culled",
+    return {"ms_per_frame": ms / (n_frames * world), "ms_per_frame_per_gpu": ms / n_frames, "frames": n_frames * world,
+            "frames_per_s": n_frames * world / ms * 1e3, "sharding": "view i -> rank i mod %d, no communication" % world,
+            "rays_per_call": chunk, "resolution": "%dx%d" % (H, W),
+            "grid": "sphere-occupancy (extra)" if sphere else "random-init N(0,1), nothing culled",
             "survivors_last_call": int(ws.counters[0].item()), "mean_rgb": float(img.mean())}
 
 
@@ -328,7 +329,21 @@ def run_ours(args):
             trainer.step(*dev_batches[i % N_BATCHES])
         torch.cuda.synchronize()
         stages = trainer.stage_times_ms()
+        if "sweep_grids" in stages:     # multi-GPU: grid sweeps and the rgbnet Adam are marked separately
+            stages["sweep"] = stages["sweep"] + stages.pop("sweep_grids")
         trainer.stage_events = None
+    barrier()
+    render = None
+    if not args.no_render:      # every rank renders its share of the views
+        try:
+            if hasattr(trainer, "sync_to_model"):
+                trainer.sync_to_model()
+            render = {"dense": render_metric(model, rk, device, 2, 65536, False, rank, world),
+                      "sphere": render_metric(model, rk, device, 2, 65536, True, rank, world)}
+        except Exception as e:  # secondary metric: never let it break the headline line
+            if world > 1:
+                raise
+            render = {"error": repr(e)[:200]}
     barrier()
     if rank != 0:
         if world > 1:
@@ -363,12 +378,15 @@ def run_ours(args):
         # command (profiles/r01_ncu_final_kernels.md); valid for the default workload only.
         ncu_traffic = {"march_fwd": 35.3e6 + 457.4e6, "mlp_fwd": 145.2e6, "mlp_bwd": 272.3e6, "march_bwd": 64.9e6 + 599.3e6, "sweep": 1465.5e6 + 75.6e6}
         traffic = ncu_traffic.get(dom) if (args.grid == 160 and world == 1) else None
+        comm = {k: stages[k] for k in ("grad_exchange", "param_gather") if k in stages}
         roof = {"bound": kind, "kernel": kernel_names[dom], "achieved": ach, "peak": peak, "unit": unit,
                 "frac": ach / peak, "traffic": traffic, "peak_kind": peak_kind + (" (bf16 sustained; fp16 runs at the same rate)" if kind == "tensor" else ""),
                 "kernel_ms": stages[dom], "algorithmic_work_per_launch": work,
                 "all_stages": {k: {"ms": stages[k], "bound": alg[k][0],
                                    "frac": (alg[k][1] / (stages[k] * 1e-3) / (1e9 * hbm_peak if alg[k][0] == "hbm" else 1e12 * tensor_peak))}
                                for k in stages if k in alg}}
+        if comm:
+            roof["collectives_ms"] = comm
     if roof is None:
         # module path: the grid-optimiser sweep (masked Adam over density+k0) is the one pure-HBM kernel
         from directvoxgo_b200 import adam_upd_cuda
@@ -390,15 +408,6 @@ def run_ours(args):
                 "peak": hbm_peak, "unit": "GB/s", "frac": bytes_alg / (k_ms * 1e-3) / 1e9 / hbm_peak,
                 "traffic": None, "peak_kind": peak_kind, "kernel_ms": k_ms, "algorithmic_bytes": bytes_alg}
 
-    render = None
-    if world == 1 and not args.no_render:
-        try:
-            if hasattr(trainer, "sync_to_model"):
-                trainer.sync_to_model()
-            render = {"dense": render_metric(model, rk, device, 2, 65536, False),
-                      "sphere": render_metric(model, rk, device, 2, 65536, True)}
-        except Exception as e:  # secondary metric: never let it break the headline line
-            render = {"error": repr(e)[:200]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -406,6 +406,7 @@ class FusedTrainer(_FusedBase):
                 setattr(self, name + "_next", cur)
             updated.append(name)
         if slab is not None:
+            self._mark("sweep_grids")     # slab-sharded grid sweeps end here; "sweep" then only holds the rgbnet Adam
             self._gather_params(slab, updated)
             self._mark("param_gather")
         if self.model.rgbnet is not None and self.lr["rgbnet"] > 0:
