@@ -34,14 +34,21 @@ __device__ __forceinline__ void adam_elem_nolr(float& p, float g, float& m, floa
   p = fsub(p, fdiv(fmul(step_size, m), fadd(sqrtf(v), eps)));
 }
 
-// VEC = 4: C % 4 == 0, each thread owns one float4 = 4 channels of one voxel.
-// VEC = 1: generic (density: C == 1; C == 3 or 9 grids).
-template <int VEC, bool kTV>
+// VEC = 4, kZ = false: C % 4 == 0, each thread owns one float4 = 4 channels of one voxel.
+// VEC = 4, kZ = true : C == 1 and Z % 4 == 0 (density): one float4 = 4 consecutive z voxels; the z neighbours are the
+//                      vector shifted by one lane plus one scalar load at each end.
+// VEC = 1: generic (C == 3 or 9 grids, odd Z).
+// kEager: every element will be updated (dense TV, or Adam without the zero-gradient mask), so p, g, m, v and the six
+//         neighbour vectors are all loaded up front, independent of each other: ~10 loads in flight per thread instead
+//         of three dependent phases (p,g -> neighbours -> m,v).  The lazy variant keeps the phases: on sparse scenes
+//         (masked Adam, sparse TV) most elements stop after reading g (4 B/elem).
+template <int VEC, bool kTV, bool kEager, bool kZ>
 __global__ void __launch_bounds__(256) sweep_kernel(
     const float* __restrict__ pin, float* __restrict__ pout, float* __restrict__ grad,
     float* __restrict__ m_, float* __restrict__ v_, const float* __restrict__ perlr, int X, int Y,
     int Z, int C, int x_begin, int x_end, int tv_dense, float wy, float wz, int masked,
     float step_size, float beta1, float beta2, float eps) {
+  static_assert(!kZ || VEC == 4, "z-vectorised variant uses float4");
   // this launch owns the x-slab [x_begin, x_end) (the whole grid on one GPU, 1/n of it when the sweep is
   // sharded after a reduce-scatter); neighbours outside the slab are still read from the full buffers
   const int64_t e_begin = static_cast<int64_t>(x_begin) * Y * Z * C;
@@ -49,24 +56,42 @@ __global__ void __launch_bounds__(256) sweep_kernel(
   const int64_t sz = C;                                // element stride of z +- 1
   const int64_t sy = static_cast<int64_t>(Z) * C;      // y +- 1
   const int64_t sx = static_cast<int64_t>(Y) * Z * C;  // x +- 1
+  auto ld = [](const float* q, float* o) {
+    if constexpr (VEC == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(q);
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    } else {
+      o[0] = *q;
+    }
+  };
+  auto ldg = [](const float* q, float* o) {
+    if constexpr (VEC == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(q));
+      o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    } else {
+      o[0] = __ldg(q);
+    }
+  };
+  auto st = [](float* q, const float* o) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
+    else *q = o[0];
+  };
   for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < n_work;
        q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t e0 = e_begin + q * VEC;
-    float p[VEC], g[VEC], pn[VEC];
-    if constexpr (VEC == 4) {
-      const float4 a = *reinterpret_cast<const float4*>(pin + e0);
-      const float4 b = *reinterpret_cast<const float4*>(grad + e0);
-      p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;
-      g[0] = b.x; g[1] = b.y; g[2] = b.z; g[3] = b.w;
-    } else {
-      p[0] = pin[e0];
-      g[0] = grad[e0];
+    float p[VEC], g[VEC], m[VEC], v[VEC], l[VEC];
+    ld(pin + e0, p);
+    ld(grad + e0, g);
+    if constexpr (kEager) {
+      ld(m_ + e0, m);
+      ld(v_ + e0, v);
+      if (perlr) ldg(perlr + e0, l);
     }
     bool dirty = false;  // original gradient non-zero somewhere -> must be re-zeroed
 #pragma unroll
     for (int k = 0; k < VEC; ++k) dirty = dirty || (g[k] != 0.f);
     if (kTV) {
-      bool any = tv_dense != 0;
+      bool any = kEager || tv_dense != 0;
 #pragma unroll
       for (int k = 0; k < VEC; ++k) any = any || (g[k] != 0.f);
       if (any) {
@@ -77,24 +102,40 @@ __global__ void __launch_bounds__(256) sweep_kernel(
         float add[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) add[k] = 0.f;
-        auto axis = [&](bool ok, int64_t stride, float w) {
-          if (ok) {
-            if constexpr (VEC == 4) {
-              const float4 nb = __ldg(reinterpret_cast<const float4*>(pin + e0 + stride));
-              pn[0] = nb.x; pn[1] = nb.y; pn[2] = nb.z; pn[3] = nb.w;
-            } else {
-              pn[0] = __ldg(pin + e0 + stride);
-            }
+        // all neighbour loads first (independent), then the adds in the reference's term order k-,k+,j-,j+,i-,i+
+        float nzm[VEC], nzp[VEC], nym[VEC], nyp[VEC], nxm[VEC], nxp[VEC];
+        const bool oym = y > 0, oyp = y < Y - 1, oxm = x > 0, oxp = x < X - 1;
+        bool ozm[VEC], ozp[VEC];
+        if constexpr (kZ) {
+          const float before = z > 0 ? __ldg(pin + e0 - 1) : 0.f;
+          const float after = z + VEC < Z ? __ldg(pin + e0 + VEC) : 0.f;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) add[k] = fadd(add[k], tvt(w, p[k], pn[k]));
+          for (int k = 0; k < VEC; ++k) {
+            nzm[k] = k == 0 ? before : p[k - 1];
+            nzp[k] = k == VEC - 1 ? after : p[k + 1];
+            ozm[k] = z + k > 0;
+            ozp[k] = z + k < Z - 1;
           }
-        };
-        axis(z > 0, -sz, wz);
-        axis(z < Z - 1, sz, wz);
-        axis(y > 0, -sy, wy);
-        axis(y < Y - 1, sy, wy);
-        axis(x > 0, -sx, wz);      // reference quirk: the x axis uses wz
-        axis(x < X - 1, sx, wz);
+        } else {
+          const bool a = z > 0, b2 = z < Z - 1;
+          if (a) ldg(pin + e0 - sz, nzm);
+          if (b2) ldg(pin + e0 + sz, nzp);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) { ozm[k] = a; ozp[k] = b2; }
+        }
+        if (oym) ldg(pin + e0 - sy, nym);
+        if (oyp) ldg(pin + e0 + sy, nyp);
+        if (oxm) ldg(pin + e0 - sx, nxm);
+        if (oxp) ldg(pin + e0 + sx, nxp);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          if (ozm[k]) add[k] = fadd(add[k], tvt(wz, p[k], nzm[k]));
+          if (ozp[k]) add[k] = fadd(add[k], tvt(wz, p[k], nzp[k]));
+          if (oym) add[k] = fadd(add[k], tvt(wy, p[k], nym[k]));
+          if (oyp) add[k] = fadd(add[k], tvt(wy, p[k], nyp[k]));
+          if (oxm) add[k] = fadd(add[k], tvt(wz, p[k], nxm[k]));      // reference quirk: the x axis uses wz
+          if (oxp) add[k] = fadd(add[k], tvt(wz, p[k], nxp[k]));
+        }
 #pragma unroll
         for (int k = 0; k < VEC; ++k)
           if (tv_dense || g[k] != 0.f) g[k] = fadd(g[k], add[k]);
@@ -104,20 +145,10 @@ __global__ void __launch_bounds__(256) sweep_kernel(
 #pragma unroll
     for (int k = 0; k < VEC; ++k) upd = upd || (g[k] != 0.f);
     if (upd) {
-      float m[VEC], v[VEC], l[VEC];
-      if constexpr (VEC == 4) {
-        const float4 a = *reinterpret_cast<const float4*>(m_ + e0);
-        const float4 b = *reinterpret_cast<const float4*>(v_ + e0);
-        m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
-        v[0] = b.x; v[1] = b.y; v[2] = b.z; v[3] = b.w;
-        if (perlr) {
-          const float4 c = __ldg(reinterpret_cast<const float4*>(perlr + e0));
-          l[0] = c.x; l[1] = c.y; l[2] = c.z; l[3] = c.w;
-        }
-      } else {
-        m[0] = m_[e0];
-        v[0] = v_[e0];
-        if (perlr) l[0] = __ldg(perlr + e0);
+      if constexpr (!kEager) {
+        ld(m_ + e0, m);
+        ld(v_ + e0, v);
+        if (perlr) ldg(perlr + e0, l);
       }
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
@@ -125,23 +156,17 @@ __global__ void __launch_bounds__(256) sweep_kernel(
         if (perlr) adam_elem(p[k], g[k], m[k], v[k], l[k], step_size, beta1, beta2, eps);
         else adam_elem_nolr(p[k], g[k], m[k], v[k], step_size, beta1, beta2, eps);
       }
-      if constexpr (VEC == 4) {
-        *reinterpret_cast<float4*>(m_ + e0) = make_float4(m[0], m[1], m[2], m[3]);
-        *reinterpret_cast<float4*>(v_ + e0) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-        m_[e0] = m[0];
-        v_[e0] = v[0];
-      }
+      st(m_ + e0, m);
+      st(v_ + e0, v);
     }
     // new parameters: always written when ping-ponging (pout != pin), only when changed in place
-    if (upd || pout != pin) {
-      if constexpr (VEC == 4) *reinterpret_cast<float4*>(pout + e0) = make_float4(p[0], p[1], p[2], p[3]);
-      else pout[e0] = p[0];
-    }
+    if (upd || pout != pin) st(pout + e0, p);
     // re-zero the gradient accumulator for the next step (only where it was non-zero)
     if (dirty) {
-      if constexpr (VEC == 4) *reinterpret_cast<float4*>(grad + e0) = make_float4(0.f, 0.f, 0.f, 0.f);
-      else grad[e0] = 0.f;
+      float zero[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) zero[k] = 0.f;
+      st(grad + e0, zero);
     }
   }
 }
@@ -204,15 +229,30 @@ DVGO_API int dvgo_fused_sweep(const float* param_in, float* param_out, float* gr
   cudaStream_t s = as_stream(stream);
 #define SWEEP_ARGS param_in, param_out, grad, exp_avg, exp_avg_sq, perlr, X, Y, Z, C, x_begin, x_end, tv_dense, wy, wz, \
                    masked, step_size, beta1, beta2, eps
-  if (vec) {
-    const int blocks = sweep_grid(n / 4, 256);
-    if (tv) sweep_kernel<4, true><<<blocks, 256, 0, s>>>(SWEEP_ARGS);
-    else sweep_kernel<4, false><<<blocks, 256, 0, s>>>(SWEEP_ARGS);
-  } else {
-    const int blocks = sweep_grid(n, 256);
-    if (tv) sweep_kernel<1, true><<<blocks, 256, 0, s>>>(SWEEP_ARGS);
-    else sweep_kernel<1, false><<<blocks, 256, 0, s>>>(SWEEP_ARGS);
-  }
+  const bool eager = !masked || (tv && tv_dense);   // every element is updated: issue all loads up front
+  const bool zvec = !vec && C == 1 && Z % 4 == 0 && al16(param_in) && al16(param_out) && al16(grad) && al16(exp_avg) &&
+                    al16(exp_avg_sq) && (!perlr || al16(perlr));
+  // one resident wave looping grid-stride (profiles/r01_sweep_grid.txt): grid = SMs x CTAs that fit per SM
+#define SWEEP_ONE(V, TV, EAGER, KZ, N)                                                                \
+  do {                                                                                                \
+    int occ = 4;                                                                                      \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<V, TV, EAGER, KZ>, 256, 0);      \
+    const int64_t want = ((N) + 255) / 256, cap = static_cast<int64_t>(kNumSMs) * (occ > 0 ? occ : 1); \
+    const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);                    \
+    sweep_kernel<V, TV, EAGER, KZ><<<blocks, 256, 0, s>>>(SWEEP_ARGS);                                \
+  } while (0)
+#define SWEEP_LAUNCH(V, KZ, N)                                                                        \
+  do {                                                                                                \
+    if (tv && eager) SWEEP_ONE(V, true, true, KZ, N);                                                 \
+    else if (tv) SWEEP_ONE(V, true, false, KZ, N);                                                    \
+    else if (eager) SWEEP_ONE(V, false, true, KZ, N);                                                 \
+    else SWEEP_ONE(V, false, false, KZ, N);                                                           \
+  } while (0)
+  if (vec) SWEEP_LAUNCH(4, false, n / 4);
+  else if (zvec) SWEEP_LAUNCH(4, true, n / 4);
+  else SWEEP_LAUNCH(1, false, n);
+#undef SWEEP_LAUNCH
+#undef SWEEP_ONE
 #undef SWEEP_ARGS
   return launch_status();
 }
