@@ -858,6 +858,54 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// Issue-rate probe: one thread issues `reps` x `ksteps` MMAs (M = 128, N given) from zero-filled shared memory with
+// caller-chosen descriptors; out[cta] = clock64 cycles from the first issue to the completion of the last one.
+__global__ void __launch_bounds__(128) tc_rate_kernel(int N, int ksteps, int reps, int a_mn, int b_mn, uint32_t a_lbo,
+                                                      uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo,
+                                                      uint32_t b_kstep, uint32_t layout, int n_accum,
+                                                      long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint8_t* sB = sA + 64 * 1024;
+  for (int i = tid; i < 32 * 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(sA)[i] = 0u;   // 128 KB of zeros
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init_fence(); }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_f16(128, N, a_mn, b_mn);
+    const uint64_t lay = static_cast<uint64_t>(layout) << 61;
+    uint64_t ad[8], bd[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      ad[k] = make_desc(smem_u32(sA) + k * a_kstep, a_lbo, a_sbo) | lay;
+      bd[k] = make_desc(smem_u32(sB) + k * b_kstep, b_lbo, b_sbo) | lay;
+    }
+    const uint32_t d1 = tmem + static_cast<uint32_t>(((n_accum > 1) ? 1 : 0) * N);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r += 2) {     // descriptors precomputed: the loop body is MMAs only
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < ksteps) mma_f16(tmem, ad[k], bd[k], idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < ksteps) mma_f16(d1, ad[k], bd[k], idesc, k > 0 ? 1u : 0u);
+    }
+    mma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    out[blockIdx.x] = clock64() - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace dvgo
 
 using namespace dvgo;
@@ -958,5 +1006,17 @@ DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, 
   MlpG g{gW1, gb1, gW2, gb2, gW3, gb3};
   mlp_bwd_kernel<<<grid, kBwdThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, pe_stride,
                                                                  rgb, d_rgb, grad_scale, d_feat, g, timeline);
+  return launch_status();
+}
+
+DVGO_API int dvgo_tc_rate(int ctas, int N, int ksteps, int reps, int a_mn, int b_mn, int a_lbo, int a_sbo, int a_kstep,
+                          int b_lbo, int b_sbo, int b_kstep, int layout, int n_accum, long long* out, dvgo_stream_t stream) {
+  if (ctas < 1 || N < 16 || N > 256 || N % 16 || ksteps < 1 || reps < 1 || n_accum < 1 || n_accum * N > 512 || !out)
+    return DVGO_EINVAL;
+  const size_t bytes = 129 * 1024 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  tc_rate_kernel<<<ctas, 128, bytes, as_stream(stream)>>>(N, ksteps, reps, a_mn, b_mn, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo,
+                                                          b_kstep, layout, n_accum, out);
   return launch_status();
 }

@@ -38,6 +38,14 @@ Tensor tc_probe(Tensor A, Tensor Braw, int N, int K, bool b_mn, int lbo, int sbo
   return D;
 }
 
+Tensor tc_rate(int ctas, int N, int ksteps, int reps, bool a_mn, bool b_mn, int a_lbo, int a_sbo, int a_kstep, int b_lbo,
+               int b_sbo, int b_kstep, int layout, int n_accum) {
+  auto out = torch::zeros({ctas}, torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA));
+  rc_check(dvgo_tc_rate(ctas, N, ksteps, reps, a_mn, b_mn, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, layout, n_accum,
+                        reinterpret_cast<long long*>(out.data_ptr<int64_t>()), cur_stream()), "tc_rate");
+  return out;
+}
+
 inline void chki(const Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == torch::kInt32, name,
               " must be a contiguous int32 CUDA tensor");
@@ -119,6 +127,7 @@ Tensor mlp_bwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor coun
 void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("tc_selftest", &tc_selftest);
   m.def("tc_probe", &tc_probe);
+  m.def("tc_rate", &tc_rate);
   m.def("mlp_fwd", &mlp_fwd);
   m.def("mlp_fwd_timeline", &mlp_fwd_timeline);
   m.def("mlp_bwd", &mlp_bwd);

@@ -206,6 +206,10 @@ int dvgo_tc_selftest(const float* A, const float* B, float* D, int N, int K, int
 
 /* Descriptor probe (debug aid for the kernel author): A [128][K] K-major, the B operand region is
  * filled verbatim from Braw [nwords] and described with the given LBO/SBO/k-step (bytes). */
+/* Tensor-core issue-rate probe (tools/mma_rate.py): `reps` x `ksteps` M=128 MMAs of width N issued by one thread per
+ * CTA from zero-filled shared memory with the given descriptor fields; out[cta] = cycles. */
+int dvgo_tc_rate(int ctas, int N, int ksteps, int reps, int a_mn, int b_mn, int a_lbo, int a_sbo, int a_kstep,
+                 int b_lbo, int b_sbo, int b_kstep, int layout, int n_accum, long long* out, dvgo_stream_t stream);
 int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, int K, int b_mn, int lbo, int sbo,
                   int kstep, int nwords, dvgo_stream_t stream);
 
