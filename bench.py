@@ -242,7 +242,9 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        # a desynchronised collective must abort the run quickly instead of hanging the box
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=120))
     import directvoxgo_b200 as pkg
     from directvoxgo_b200.trainer import ModuleTrainer
 
@@ -274,11 +276,18 @@ def run_ours(args):
     # ---- device-resident timing -----------------------------------------------------------------
     # Untimed clock ramp: a B200 idling at its floor clock needs ~1 s of load to reach its boost clock; W warm-up
     # steps (a few ms) are not enough and the first timed steps would otherwise run at a lower clock.
+    # The steps contain collectives when world > 1, so every rank must run the SAME number of rounds: the ranks
+    # agree on "done" with a MAX all-reduce after each round (a per-rank wall-clock test would desynchronise them).
     t_ramp = time.time()
-    while time.time() - t_ramp < args.ramp_s:
+    while args.ramp_s > 0:
         for i in range(50):
             trainer.step(*dev_batches[i % N_BATCHES])
         torch.cuda.synchronize()
+        done = torch.tensor([1.0 if time.time() - t_ramp >= args.ramp_s else 0.0], device=device)
+        if world > 1:
+            dist.all_reduce(done, op=dist.ReduceOp.MAX)
+        if float(done.item()) > 0:
+            break
     for i in range(args.warmup):
         trainer.step(*dev_batches[i % N_BATCHES])
     barrier()
