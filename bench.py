@@ -333,6 +333,10 @@ def run_ours(args):
     # (outside the timed regions).  EVERY rank runs them -- the steps contain collectives when world > 1.
     stages = None
     if path == "fused" and hasattr(trainer, "stage_events"):
+        barrier()
+        for i in range(3):              # re-align the ranks after the end-to-end loop before recording events
+            trainer.step(*dev_batches[i % N_BATCHES])
+        barrier()
         trainer.stage_events = {}
         for i in range(10):
             trainer.step(*dev_batches[i % N_BATCHES])
