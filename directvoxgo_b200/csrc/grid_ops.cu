@@ -124,6 +124,68 @@ static inline int grid_for(int64_t n, int threads) {
   return static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// ---- 2-D tri-plane sampling (lib/tri_dvgo.py:456-464): ATen grid_sampler_2d, bilinear, align_corners, zero pad --
+struct Bil { int x0, y0; float w[4]; };   // corner order nw, ne, sw, se as ATen accumulates them
+__device__ __forceinline__ Bil bil_setup(const float* __restrict__ p3, const float* __restrict__ lo,
+                                         const float* __restrict__ hi, int axis_w, int axis_h, int W, int H) {
+  const float ix = unnorm_coord(p3[axis_w], lo[axis_w], hi[axis_w], W);
+  const float iy = unnorm_coord(p3[axis_h], lo[axis_h], hi[axis_h], H);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  Bil b;
+  b.x0 = static_cast<int>(x0f);
+  b.y0 = static_cast<int>(y0f);
+  const float ex = fsub(x0f + 1.f, ix), wx = fsub(ix, x0f);   // (ix_se - ix), (ix - ix_nw)
+  const float ey = fsub(y0f + 1.f, iy), wy = fsub(iy, y0f);
+  b.w[0] = fmul(ex, ey);   // nw
+  b.w[1] = fmul(wx, ey);   // ne
+  b.w[2] = fmul(ex, wy);   // sw
+  b.w[3] = fmul(wx, wy);   // se
+  return b;
+}
+
+__global__ void __launch_bounds__(256) grid_sample_2d_kernel(
+    const float* __restrict__ plane, int C, int H, int W, const float* __restrict__ xyz,
+    const float* __restrict__ xyz_min, const float* __restrict__ xyz_max, int axis_w, int axis_h, int64_t n_pts,
+    float* __restrict__ out) {
+  const int64_t hw = static_cast<int64_t>(H) * W;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n_pts;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const Bil b = bil_setup(xyz + 3 * p, xyz_min, xyz_max, axis_w, axis_h, W, H);
+    int64_t off[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
+      off[k] = (x >= 0 && x < W && y >= 0 && y < H) ? static_cast<int64_t>(y) * W + x : -1;
+    }
+    for (int c = 0; c < C; ++c) {
+      const float* __restrict__ g = plane + c * hw;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (off[k] >= 0) acc = fma_(__ldg(g + off[k]), b.w[k], acc);
+      out[p * C + c] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) grid_sample_2d_backward_kernel(
+    const float* __restrict__ grad_out, int C, int H, int W, const float* __restrict__ xyz,
+    const float* __restrict__ xyz_min, const float* __restrict__ xyz_max, int axis_w, int axis_h, int64_t n_pts,
+    float* __restrict__ grad_plane) {
+  const int64_t hw = static_cast<int64_t>(H) * W;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n_pts;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const Bil b = bil_setup(xyz + 3 * p, xyz_min, xyz_max, axis_w, axis_h, W, H);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
+      if (x < 0 || x >= W || y < 0 || y >= H) continue;
+      const int64_t off = static_cast<int64_t>(y) * W + x;
+      for (int c = 0; c < C; ++c) atomicAdd(grad_plane + c * hw + off, fmul(b.w[k], grad_out[p * C + c]));
+    }
+  }
+}
+
 }  // namespace dvgo
 
 using namespace dvgo;
@@ -168,5 +230,27 @@ DVGO_API int dvgo_gather_rows(const float* table, const int64_t* index, int64_t 
   if (!table || !index || !out) return DVGO_EINVAL;
   gather_rows_kernel<<<grid_for(n_pts * D, 256), 256, 0, as_stream(stream)>>>(table, index, n_pts,
                                                                               D, out);
+  return launch_status();
+}
+
+DVGO_API int dvgo_grid_sample_2d(const float* plane, int C, int H, int W, const float* xyz, const float* xyz_min,
+                                 const float* xyz_max, int axis_w, int axis_h, int64_t n_pts, float* out,
+                                 dvgo_stream_t stream) {
+  if (C <= 0 || H <= 0 || W <= 0 || n_pts < 0 || axis_w < 0 || axis_w > 2 || axis_h < 0 || axis_h > 2) return DVGO_EINVAL;
+  if (n_pts == 0) return 0;
+  if (!plane || !xyz || !xyz_min || !xyz_max || !out) return DVGO_EINVAL;
+  grid_sample_2d_kernel<<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(plane, C, H, W, xyz, xyz_min, xyz_max,
+                                                                             axis_w, axis_h, n_pts, out);
+  return launch_status();
+}
+
+DVGO_API int dvgo_grid_sample_2d_backward(const float* grad_out, int C, int H, int W, const float* xyz,
+                                          const float* xyz_min, const float* xyz_max, int axis_w, int axis_h,
+                                          int64_t n_pts, float* grad_plane, dvgo_stream_t stream) {
+  if (C <= 0 || H <= 0 || W <= 0 || n_pts < 0 || axis_w < 0 || axis_w > 2 || axis_h < 0 || axis_h > 2) return DVGO_EINVAL;
+  if (n_pts == 0) return 0;
+  if (!grad_out || !xyz || !xyz_min || !xyz_max || !grad_plane) return DVGO_EINVAL;
+  grid_sample_2d_backward_kernel<<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
+      grad_out, C, H, W, xyz, xyz_min, xyz_max, axis_w, axis_h, n_pts, grad_plane);
   return launch_status();
 }

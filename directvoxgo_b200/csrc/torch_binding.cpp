@@ -292,6 +292,33 @@ void grid_sample_3d_backward(Tensor grad_out, Tensor xyz, Tensor xyz_min, Tensor
            "grid_sample_3d_backward");
 }
 
+// tri-plane: plane [1,C,H,W], xyz [P,3] -> [P,C]; axis_w / axis_h as in include/dvgo_b200.h
+Tensor grid_sample_2d(Tensor plane, Tensor xyz, Tensor xyz_min, Tensor xyz_max, int axis_w, int axis_h) {
+  CHECK_INPUT(plane); CHECK_INPUT(xyz); CHECK_INPUT(xyz_min); CHECK_INPUT(xyz_max);
+  CHECK_F32(plane); CHECK_F32(xyz); CHECK_F32(xyz_min); CHECK_F32(xyz_max);
+  TORCH_CHECK(plane.dim() == 4 && plane.size(0) == 1, "plane must be [1,C,H,W]");
+  TORCH_CHECK(xyz.dim() == 2 && xyz.size(1) == 3, "xyz must be [P,3]");
+  const c10::cuda::CUDAGuard guard(plane.device());
+  const int C = plane.size(1);
+  auto out = torch::empty({xyz.size(0), C}, xyz.options());
+  check_rc(dvgo_grid_sample_2d(fp(plane), C, plane.size(2), plane.size(3), fp(xyz), fp(xyz_min), fp(xyz_max), axis_w,
+                               axis_h, xyz.size(0), fpm(out), cur_stream()), "grid_sample_2d");
+  return out;
+}
+
+void grid_sample_2d_backward(Tensor grad_out, Tensor xyz, Tensor xyz_min, Tensor xyz_max, int axis_w, int axis_h,
+                             Tensor grad_plane) {
+  CHECK_INPUT(grad_out); CHECK_INPUT(xyz); CHECK_INPUT(xyz_min); CHECK_INPUT(xyz_max); CHECK_INPUT(grad_plane);
+  CHECK_F32(grad_out); CHECK_F32(xyz); CHECK_F32(xyz_min); CHECK_F32(xyz_max); CHECK_F32(grad_plane);
+  TORCH_CHECK(grad_plane.dim() == 4 && grad_plane.size(0) == 1, "grad_plane must be [1,C,H,W]");
+  const int C = grad_plane.size(1);
+  TORCH_CHECK(grad_out.dim() == 2 && grad_out.size(0) == xyz.size(0) && grad_out.size(1) == C, "grad_out must be [P,C]");
+  const c10::cuda::CUDAGuard guard(grad_plane.device());
+  check_rc(dvgo_grid_sample_2d_backward(fp(grad_out), C, grad_plane.size(2), grad_plane.size(3), fp(xyz), fp(xyz_min),
+                                        fp(xyz_max), axis_w, axis_h, xyz.size(0), fpm(grad_plane), cur_stream()),
+           "grid_sample_2d_backward");
+}
+
 // out[index[p], :] += src[p, :]   (src [P] or [P,D]; index sorted; out [N] or [N,D], in place)
 void segment_coo_sum(Tensor src, Tensor index, Tensor out) {
   CHECK_INPUT(src); CHECK_INPUT(index); CHECK_INPUT(out);
@@ -355,6 +382,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   auto ext = m.def_submodule("ext");
   ext.def("grid_sample_3d", &grid_sample_3d);
   ext.def("grid_sample_3d_backward", &grid_sample_3d_backward);
+  ext.def("grid_sample_2d", &grid_sample_2d);
+  ext.def("grid_sample_2d_backward", &grid_sample_2d_backward);
   ext.def("segment_coo_sum", &segment_coo_sum);
   ext.def("gather_rows", &gather_rows);
   dvgo_bind_fused(ext);

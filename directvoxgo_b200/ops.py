@@ -68,6 +68,43 @@ class _GridSampleTrilinear(torch.autograd.Function):
         return grad_grid, None, None, None
 
 
+class _GridSamplePlane(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plane, xyz, xyz_min, xyz_max, axis_w, axis_h):
+        out = ext.grid_sample_2d(plane, xyz, xyz_min, xyz_max, axis_w, axis_h)
+        if plane.requires_grad:
+            ctx.save_for_backward(xyz, xyz_min, xyz_max)
+            ctx.meta = (plane.shape, axis_w, axis_h)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        xyz, xyz_min, xyz_max = ctx.saved_tensors
+        shape, axis_w, axis_h = ctx.meta
+        grad_plane = torch.zeros(shape, dtype=grad_out.dtype, device=grad_out.device)
+        ext.grid_sample_2d_backward(grad_out.contiguous(), xyz, xyz_min, xyz_max, axis_w, axis_h, grad_plane)
+        return grad_plane, None, None, None, None, None
+
+
+# which world axis indexes the W / H dimension of each plane: the reference samples plane 'ab' with
+# ind_norm[..., [i, j]] where ind_norm = (z_n, y_n, x_n) (lib/tri_dvgo.py:460-464)
+TRIPLANE_AXES = {"xy": (2, 1), "yz": (1, 0), "zx": (0, 2)}
+
+
+def grid_sample_triplane(grids, xyz, xyz_min, xyz_max, aggregation="concat"):
+    """Tri-plane feature lookup, the reference's `grid_sampler2D` (lib/tri_dvgo.py:456-471):
+    grids = {'xy','yz','zx'} of [1,C,H,W] planes, xyz [P,3] world coords -> [P,3C] ('concat') or [P,C] ('sum').
+    One kernel per plane: ind_norm arithmetic + ATen's bilinear blend (align_corners=True, zero padding)."""
+    x = xyz.reshape(-1, 3).contiguous()
+    feats = [_GridSamplePlane.apply(grids[k], x, xyz_min, xyz_max, *TRIPLANE_AXES[k]) for k in ("xy", "yz", "zx")]
+    if aggregation == "concat":
+        return torch.cat(feats, dim=-1)
+    if aggregation == "sum":
+        return feats[0] + feats[1] + feats[2]
+    raise NotImplementedError(aggregation)
+
+
 def grid_sample_trilinear(grid, xyz, xyz_min, xyz_max):
     """DenseGrid sampling: grid [1,C,X,Y,Z], xyz [...,3] world coords -> [...,C] ([...] if C==1).
 

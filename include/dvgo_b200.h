@@ -121,6 +121,20 @@ int dvgo_grid_sample_3d_backward(const float* grad_out, int C, int X, int Y, int
                                  const float* xyz, const float* xyz_min, const float* xyz_max,
                                  int64_t n_pts, float* grad_grid, dvgo_stream_t stream);
 
+/* a7 (2-D)  tri-plane bilinear sampling   lib/tri_dvgo.py:456-464 (grid_sampler2D):
+ *     F.grid_sample(plane[1,C,H,W], ind_norm[..., [a, b]], 'bilinear', align_corners=True), zero padding.
+ * The reference feeds the FLIPPED normalised coordinate ind_norm = (z_n, y_n, x_n); axis_w / axis_h name the
+ * world axis (0 = x, 1 = y, 2 = z) whose normalised coordinate indexes the plane's W / H dimension:
+ *     'xy': ind_norm[..., [0,1]] -> axis_w = 2, axis_h = 1;   'yz': [1,2] -> axis_w = 1, axis_h = 0;
+ *     'zx': [2,0] -> axis_w = 0, axis_h = 2.
+ * plane [C,H,W]; xyz [n_pts,3] world coordinates; out [n_pts,C].  backward: grad_plane += scatter(grad_out). */
+int dvgo_grid_sample_2d(const float* plane, int C, int H, int W, const float* xyz, const float* xyz_min,
+                        const float* xyz_max, int axis_w, int axis_h, int64_t n_pts, float* out,
+                        dvgo_stream_t stream);
+int dvgo_grid_sample_2d_backward(const float* grad_out, int C, int H, int W, const float* xyz,
+                                 const float* xyz_min, const float* xyz_max, int axis_w, int axis_h,
+                                 int64_t n_pts, float* grad_plane, dvgo_stream_t stream);
+
 /* a10 torch_scatter.segment_coo(src, index, out, reduce='sum')   lib/dvgo.py:554-558,571-575
  * src [n_pts,D] fp32, index [n_pts] int64 sorted ascending, out [n_seg,D] accumulated INTO (the
  * caller passes zeros, as the reference does).  Deterministic: one warp per run of equal indices.

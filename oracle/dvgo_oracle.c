@@ -280,6 +280,49 @@ EXPORT void orc_grid_sample_3d_backward(const float* grad_out /* [n_pts,C] */, i
   }
 }
 
+/* ---- T2: tri-plane bilinear sampling = ATen grid_sampler_2d as lib/tri_dvgo.py:456-464 calls it ----------------
+ * plane [C,H,W]; axis_w / axis_h: world axis whose normalised coordinate indexes W / H (the reference passes
+ * ind_norm[..., [i,j]] with ind_norm = flipped (z,y,x)).  Corner order and weights as ATen: nw, ne, sw, se. */
+static inline float unnorm1(float x, float lo, float hi, int size) {
+  const float u = (x - lo) / (hi - lo);
+  const float n = u * 2.f - 1.f;
+  return ((n + 1.f) * 0.5f) * (float)(size - 1);
+}
+EXPORT void orc_grid_sample_2d(const float* plane, int C, int H, int W, const float* xyz, const float* xyz_min,
+                               const float* xyz_max, int axis_w, int axis_h, int64_t n_pts, float* out) {
+  const int64_t hw = (int64_t)H * W;
+  for (int64_t p = 0; p < n_pts; ++p) {
+    const float ix = unnorm1(xyz[3 * p + axis_w], xyz_min[axis_w], xyz_max[axis_w], W);
+    const float iy = unnorm1(xyz[3 * p + axis_h], xyz_min[axis_h], xyz_max[axis_h], H);
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float ex = (x0 + 1.f) - ix, wx = ix - x0, ey = (y0 + 1.f) - iy, wy = iy - y0;
+    const float w[4] = {ex * ey, wx * ey, ex * wy, wx * wy};
+    for (int c = 0; c < C; ++c) out[p * C + c] = 0.f;
+    for (int k = 0; k < 4; ++k) {
+      const int x = (int)x0 + (k & 1), y = (int)y0 + (k >> 1);
+      if (x < 0 || x >= W || y < 0 || y >= H) continue;
+      for (int c = 0; c < C; ++c) out[p * C + c] = fmaf(plane[c * hw + (int64_t)y * W + x], w[k], out[p * C + c]);
+    }
+  }
+}
+EXPORT void orc_grid_sample_2d_backward(const float* grad_out, int C, int H, int W, const float* xyz,
+                                        const float* xyz_min, const float* xyz_max, int axis_w, int axis_h,
+                                        int64_t n_pts, float* grad_plane) {
+  const int64_t hw = (int64_t)H * W;
+  for (int64_t p = 0; p < n_pts; ++p) {
+    const float ix = unnorm1(xyz[3 * p + axis_w], xyz_min[axis_w], xyz_max[axis_w], W);
+    const float iy = unnorm1(xyz[3 * p + axis_h], xyz_min[axis_h], xyz_max[axis_h], H);
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float ex = (x0 + 1.f) - ix, wx = ix - x0, ey = (y0 + 1.f) - iy, wy = iy - y0;
+    const float w[4] = {ex * ey, wx * ey, ex * wy, wx * wy};
+    for (int k = 0; k < 4; ++k) {
+      const int x = (int)x0 + (k & 1), y = (int)y0 + (k >> 1);
+      if (x < 0 || x >= W || y < 0 || y >= H) continue;
+      for (int c = 0; c < C; ++c) grad_plane[c * hw + (int64_t)y * W + x] += w[k] * grad_out[p * C + c];
+    }
+  }
+}
+
 /* ---- T3: torch_scatter.segment_coo(src, index, out, reduce='sum')  (lib/dvgo.py:554-558) ----- */
 EXPORT void orc_segment_coo_sum(const float* src, const int64_t* index, int64_t n_pts, int D,
                                 float* out /* [n_seg, D], accumulated into */) {

@@ -190,6 +190,23 @@ def grid_sample_3d_backward(grad_out, xyz, xyz_min, xyz_max, grad_grid):
                                       _p(_f32(xyz_max)), _L(x.shape[0]), _p(grad_grid))
 
 
+def grid_sample_2d(plane, xyz, xyz_min, xyz_max, axis_w, axis_h):
+    """plane [1,C,H,W], xyz [P,3] -> [P,C] (F.grid_sample 2-D as used at lib/tri_dvgo.py:456-464)."""
+    g, x = _f32(plane), _f32(xyz)
+    C, H, W = g.shape[1:]
+    out = torch.empty(x.shape[0], C)
+    lib().orc_grid_sample_2d(_p(g), _I(C), _I(H), _I(W), _p(x), _p(_f32(xyz_min)), _p(_f32(xyz_max)), _I(axis_w),
+                             _I(axis_h), _L(x.shape[0]), _p(out))
+    return out
+
+
+def grid_sample_2d_backward(grad_out, xyz, xyz_min, xyz_max, axis_w, axis_h, grad_plane):
+    go, x = _f32(grad_out), _f32(xyz)
+    C, H, W = grad_plane.shape[1:]
+    lib().orc_grid_sample_2d_backward(_p(go), _I(C), _I(H), _I(W), _p(x), _p(_f32(xyz_min)), _p(_f32(xyz_max)),
+                                      _I(axis_w), _I(axis_h), _L(x.shape[0]), _p(grad_plane))
+
+
 def segment_coo_sum(src, index, out):
     s = _f32(src)
     P = index.shape[0]

@@ -129,6 +129,34 @@ def test_trilinear_vs_aten_grid_sample(pkg):
         assert rel_to_max(gg, gr.grad) < 1e-4   # atomics: rel 1e-4 of max-abs
 
 
+def test_triplane_vs_aten_grid_sample_2d(pkg):
+    """Row a7, 2-D: the reference's grid_sampler2D (lib/tri_dvgo.py:456-464) = three ATen grid_sampler_2d calls on
+    flipped, normalised coordinates, against our per-plane kernel, forward and backward, on the GPU."""
+    import torch.nn.functional as F
+    from directvoxgo_b200.ops import grid_sample_triplane
+    g = torch.Generator().manual_seed(8)
+    lo = torch.tensor([-1.5, -1.2, -1.0], device=DEV)
+    hi = torch.tensor([1.5, 1.3, 0.9], device=DEV)
+    C = 8
+    shapes = {"xy": (160, 150), "yz": (140, 160), "zx": (150, 140)}
+    grids = {k: torch.randn(1, C, *s, generator=g).to(DEV).requires_grad_() for k, s in shapes.items()}
+    refs = {k: v.detach().clone().requires_grad_() for k, v in grids.items()}
+    xyz = (lo + (hi - lo) * (torch.rand(400000, 3, generator=g).to(DEV) * 1.2 - 0.1)).contiguous()
+    x = xyz.reshape(1, 1, -1, 3)
+    ind_norm = ((x - lo) / (hi - lo)).flip((-1,)) * 2 - 1
+    ref = torch.cat([F.grid_sample(refs[k], ind_norm[..., idx], mode="bilinear", align_corners=True)[0, :, 0, :].T
+                     for k, idx in (("xy", [0, 1]), ("yz", [1, 2]), ("zx", [2, 0]))], -1)
+    got = grid_sample_triplane(grids, xyz, lo, hi, "concat")
+    np.testing.assert_allclose(to_np(got), to_np(ref), rtol=1e-5, atol=2e-6)
+    go = torch.randn(got.shape, generator=g).to(DEV)
+    (got * go).sum().backward()
+    (ref * go).sum().backward()
+    for k in shapes:
+        assert rel_to_max(to_np(grids[k].grad), to_np(refs[k].grad)) < 1e-5, k
+    s = grid_sample_triplane(grids, xyz[:1000], lo, hi, "sum")
+    np.testing.assert_allclose(to_np(s), to_np(got[:1000, :C] + got[:1000, C:2 * C] + got[:1000, 2 * C:]), rtol=1e-6, atol=1e-6)
+
+
 def test_training_step_vs_reference_kernels_full_size(pkg, ref_gpu):
     """BASELINE config 2 at full size (160^3, 12-ch k0, rgbnet 128, 8192 rays): the reference's op sequence
     (oracle/model_ref.py: lib/dvgo.py:450-577 + run.py:377-397) served by the REFERENCE'S OWN CUDA KERNELS

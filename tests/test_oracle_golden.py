@@ -95,6 +95,37 @@ def test_oracle_trilinear_matches_aten_cpu():
     assert rel_to_max(gg, grid2.grad) < 1e-5
 
 
+def _ref_grid_sampler2d(xyz, grids, lo, hi):
+    """lib/tri_dvgo.py:456-464 restated with the real ATen F.grid_sample (2-D), 'concat' aggregation."""
+    import torch.nn.functional as F
+    x = xyz.reshape(1, 1, -1, 3)
+    ind_norm = ((x - lo) / (hi - lo)).flip((-1,)) * 2 - 1
+    fs = [F.grid_sample(grids[k], ind_norm[..., idx], mode="bilinear", align_corners=True)[0, :, 0, :].T
+          for k, idx in (("xy", [0, 1]), ("yz", [1, 2]), ("zx", [2, 0]))]
+    return torch.cat(fs, dim=-1)
+
+
+def test_oracle_triplane_matches_aten_cpu():
+    """Tri-plane 2-D sampling (row a7, lib/tri_dvgo.py:456-464) against ATen's grid_sampler_2d on the CPU."""
+    g = torch.Generator().manual_seed(3)
+    lo, hi = torch.tensor([-1.0, -2.0, 0.5]), torch.tensor([1.5, 1.0, 2.5])
+    grids = {"xy": torch.randn(1, 4, 7, 9, generator=g), "yz": torch.randn(1, 4, 6, 5, generator=g),
+             "zx": torch.randn(1, 4, 8, 11, generator=g)}
+    xyz = lo + (hi - lo) * (torch.rand(3000, 3, generator=g) * 1.3 - 0.15)
+    ref = _ref_grid_sampler2d(xyz, grids, lo, hi)
+    axes = {"xy": (2, 1), "yz": (1, 0), "zx": (0, 2)}
+    got = torch.cat([orc.grid_sample_2d(grids[k], xyz, lo, hi, *axes[k]) for k in ("xy", "yz", "zx")], -1)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2e-5, atol=2e-6)
+    go = torch.randn(3000, 4, generator=g)
+    for k in ("xy", "yz", "zx"):
+        gg = torch.zeros_like(grids[k])
+        orc.grid_sample_2d_backward(go, xyz, lo, hi, *axes[k], gg)
+        pl = {n: (v.clone().requires_grad_() if n == k else v) for n, v in grids.items()}
+        sl = {"xy": slice(0, 4), "yz": slice(4, 8), "zx": slice(8, 12)}[k]
+        (_ref_grid_sampler2d(xyz, pl, lo, hi)[:, sl] * go).sum().backward()
+        assert rel_to_max(gg, pl[k].grad) < 1e-5
+
+
 def test_oracle_alpha_closed_forms():
     """Known-answer material the reference's docstrings give (lib/dvgo.py:590, 621-626, 636-639)."""
     d = torch.linspace(-12, 12, 4001)
