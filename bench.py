@@ -389,7 +389,7 @@ def run_ours(args):
                         "march_bwd": "k0_scatter_kernel<12> + march_bwd_kernel<12>", "sweep": "sweep_kernel<4,true> (+density sweep, rgbnet Adam)"}
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture of this
         # command (profiles/r01_ncu_final_kernels.md); valid for the default workload only.
-        ncu_traffic = {"march_fwd": 35.3e6 + 457.4e6, "mlp_fwd": 145.2e6, "mlp_bwd": 272.3e6, "march_bwd": 64.9e6 + 599.3e6, "sweep": 1465.5e6 + 75.6e6}
+        ncu_traffic = {"march_fwd": 35.9e6 + 457.6e6, "mlp_fwd": 142.6e6, "mlp_bwd": 268.7e6, "march_bwd": 65.5e6 + 598.1e6, "sweep": 1473.3e6 + 75.6e6}
         traffic = ncu_traffic.get(dom) if (args.grid == 160 and world == 1) else None
         comm = {k: stages[k] for k in ("grad_exchange", "param_gather") if k in stages}
         roof = {"bound": kind, "kernel": kernel_names[dom], "achieved": ach, "peak": peak, "unit": unit,
