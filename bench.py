@@ -140,6 +140,44 @@ def algorithmic_bytes(model, batch, rk):
             "total": U * (1 + C) * 4 * 3 + E * 4 + G * (1 + C) * 28}
 
 
+def sphere_scene(model, device):
+    """The 'procedural occupancy' scene of SURVEY.md 8d: density +5 inside a ball of radius 0.6 half-extents,
+    -5 outside, occupancy mask derived from it by the reference rule (lib/dvgo.py:254-259).  Labelled an extra."""
+    import copy
+    import torch
+    from directvoxgo_b200.dvgo import MaskCache
+    m = copy.deepcopy(model)
+    with torch.no_grad():
+        X, Y, Z = m.density.shape[2:]
+        ax = [torch.linspace(-1, 1, n, device=device) for n in (X, Y, Z)]
+        r = torch.stack(torch.meshgrid(*ax, indexing="ij"), -1).norm(dim=-1)
+        m.density.copy_(torch.where(r < 0.6, 5.0, -5.0)[None, None])
+        alpha = torch.nn.functional.max_pool3d(m.activate_density(m.density), 3, 1, 1)[0, 0]
+        m.mask_cache = MaskCache(mask=(alpha > m.fast_color_thres), xyz_min=m.xyz_min, xyz_max=m.xyz_max).to(device)
+    return m
+
+
+def train_sphere_metric(model, rk, cfg, dev_batches, device, steps=100):
+    """Extra (not the headline): the same fused training step on the sphere-occupancy scene, where the four-mask
+    cascade and the early stop cull most samples as on a real scene (the random-init grids cull nothing)."""
+    import torch
+    from directvoxgo_b200.fused import FusedTrainer
+    tr = FusedTrainer(sphere_scene(model, device), cfg, rk)
+    for i in range(50):
+        tr.step(*dev_batches[i % len(dev_batches)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        tr.step(*dev_batches[i % len(dev_batches)])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n = dev_batches[0][0].shape[0]
+    return {"ms_per_step": ms, "rays_per_s": n / ms * 1e3, "survivors_last_step": int(tr._workspace(n, True).counters[0].item()),
+            "grid": "sphere-occupancy (extra)", "steps": steps}
+
+
 def render_metric(model, rk, device, n_frames=2, chunk=65536, sphere=False, rank=0, world=1):
     """Secondary metric of BASELINE.json: ms per rendered 800x800 frame (run.py:57-110: rays of a view ->
     chunks -> forward, render_depth=True), device-timed with CUDA events, rays generated on the device.
@@ -150,16 +188,7 @@ def render_metric(model, rk, device, n_frames=2, chunk=65536, sphere=False, rank
     from directvoxgo_b200 import synthetic as syn
     from directvoxgo_b200.dvgo import MaskCache
     from directvoxgo_b200.fused import FusedRenderer
-    m = model
-    if sphere:
-        m = copy.deepcopy(model)
-        with torch.no_grad():
-            X, Y, Z = m.density.shape[2:]
-            ax = [torch.linspace(-1, 1, n, device=device) for n in (X, Y, Z)]
-            r = torch.stack(torch.meshgrid(*ax, indexing="ij"), -1).norm(dim=-1)
-            m.density.copy_(torch.where(r < 0.6, 5.0, -5.0)[None, None])
-            alpha = torch.nn.functional.max_pool3d(m.activate_density(m.density), 3, 1, 1)[0, 0]
-            m.mask_cache = MaskCache(mask=(alpha > m.fast_color_thres), xyz_min=m.xyz_min, xyz_max=m.xyz_max).to(device)
+    m = sphere_scene(model, device) if sphere else model
     renderer = FusedRenderer(m, rk)
     H = W = syn.BLENDER["H"]
     K = syn.intrinsics(H, W)
@@ -353,6 +382,8 @@ def run_ours(args):
                 trainer.sync_to_model()
             render = {"dense": render_metric(model, rk, device, 2, 65536, False, rank, world),
                       "sphere": render_metric(model, rk, device, 2, 65536, True, rank, world)}
+            if world == 1 and path == "fused":
+                render["train_sphere_extra"] = train_sphere_metric(model, rk, cfg, dev_batches, device)
         except Exception as e:  # secondary metric: never let it break the headline line
             if world > 1:
                 raise
@@ -448,6 +479,7 @@ def run_ours(args):
         "roofline": roof,
         "step_hbm_frac": balg["total"] / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
         "cpu_baseline": cpu,
+        "train_sphere_extra": (render or {}).pop("train_sphere_extra", None),
         "render_800x800": render,
     }
     print(json.dumps(line), flush=True)
