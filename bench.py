@@ -468,6 +468,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD % args.grid,
                    "rays_per_step_per_gpu": N_RAYS, "path": path, "rgbnet": getattr(trainer, "mlp_mode", "torch"), "parallelism": "ray-sharded dp%d" % world,
+                   "grad_exchange": getattr(trainer, "exchange", "nccl all-reduce" if world > 1 else "none"),
                    "samples_per_step": balg["M0"], "unique_voxels_touched": balg["U"],
                    "l2_policy": "working set (params+grads+Adam state = %.2f GB) larger than the 126 MB L2; "
                                 "%d distinct ray batches cycled" % (balg["G"] * 13 * 16 / 1e9, N_BATCHES),

@@ -188,6 +188,36 @@ void sweep(Tensor param_in, Tensor param_out, Tensor grad, Tensor exp_avg, Tenso
            "sweep");
 }
 
+// The sweep with the gradient exchange folded in (include/dvgo_b200_fused.h: dvgo_fused_sweep_peer).  The peer lists
+// hold raw device addresses of every rank's buffer as mapped in THIS process (torch symmetric memory); param_in,
+// grad_local, exp_avg, exp_avg_sq are this rank's tensors (grad_local / the local output are only size-checked).
+void sweep_peer(Tensor param_in, std::vector<int64_t> param_out_ptrs, std::vector<int64_t> grad_ptrs, int self_rank,
+                Tensor grad_local, Tensor exp_avg, Tensor exp_avg_sq, c10::optional<Tensor> perlr, int X, int Y, int Z,
+                int C, bool tv, bool tv_dense, double wx, double wy, double wz, bool masked, int step, double beta1,
+                double beta2, double lr, double eps, int x_begin, int x_end) {
+  F32(param_in); F32(grad_local); F32(exp_avg); F32(exp_avg_sq);
+  const int64_t n = (int64_t)X * Y * Z * C;
+  const int np = static_cast<int>(grad_ptrs.size());
+  TORCH_CHECK(np >= 1 && np <= 8 && param_out_ptrs.size() == grad_ptrs.size(), "sweep_peer: 1..8 peers");
+  TORCH_CHECK(self_rank >= 0 && self_rank < np, "sweep_peer: bad rank");
+  TORCH_CHECK(param_in.numel() == n && grad_local.numel() == n && exp_avg.numel() == n && exp_avg_sq.numel() == n,
+              "sweep_peer: all buffers must have X*Y*Z*C elements");
+  TORCH_CHECK(reinterpret_cast<int64_t>(grad_local.data_ptr<float>()) == grad_ptrs[self_rank],
+              "sweep_peer: grad_ptrs[self_rank] must be the local gradient buffer");
+  float* pout[8];
+  float* grads[8];
+  for (int r = 0; r < np; ++r) {
+    pout[r] = reinterpret_cast<float*>(param_out_ptrs[r]);
+    grads[r] = reinterpret_cast<float*>(grad_ptrs[r]);
+  }
+  const c10::cuda::CUDAGuard guard(param_in.device());
+  rc_check(dvgo_fused_sweep_peer(fp(param_in), pout, grads, np, self_rank, fpm(exp_avg), fpm(exp_avg_sq), fp_opt(perlr),
+                                 X, Y, Z, C, x_begin, x_end, tv, tv_dense, static_cast<float>(wx),
+                                 static_cast<float>(wy), static_cast<float>(wz), masked, step,
+                                 static_cast<float>(beta1), static_cast<float>(beta2), static_cast<float>(lr),
+                                 static_cast<float>(eps), cur_stream()), "sweep_peer");
+}
+
 Tensor ncdhw_to_cl(Tensor src) {  // [1,C,X,Y,Z] -> [X,Y,Z,C]
   F32(src);
   TORCH_CHECK(src.dim() == 5 && src.size(0) == 1, "expected [1,C,X,Y,Z]");
@@ -347,6 +377,7 @@ void dvgo_bind_fused(pybind11::module_& m) {
         pybind11::arg("wx"), pybind11::arg("wy"), pybind11::arg("wz"), pybind11::arg("masked"), pybind11::arg("step"),
         pybind11::arg("beta1"), pybind11::arg("beta2"), pybind11::arg("lr"), pybind11::arg("eps"),
         pybind11::arg("x_begin") = 0, pybind11::arg("x_end") = -1);
+  m.def("sweep_peer", &sweep_peer);
   m.def("ncdhw_to_cl", &ncdhw_to_cl);
   m.def("cl_to_ncdhw", &cl_to_ncdhw);
   m.def("zero_", &zero_);

@@ -34,6 +34,17 @@ __device__ __forceinline__ void adam_elem_nolr(float& p, float g, float& m, floa
   p = fsub(p, fdiv(fmul(step_size, m), fadd(sqrtf(v), eps)));
 }
 
+// Ray-sharded data parallel over NVLink peer memory (dvgo_fused_sweep_peer): every rank owns an x-slab; for the
+// elements of its slab it reads the gradient of ALL ranks straight from their buffers (peer loads), sums them in
+// rank order, does TV + Adam, and stores the new parameters into ALL ranks' parameter buffers (peer stores).  The
+// reduce-scatter, the sweep and the all-gather are ONE kernel: no staging pass over local HBM, and the NVLink
+// transfers overlap the HBM streaming of p, m, v element by element.
+struct SweepPeers {
+  int n;                  // 0: local mode (single GPU, or gradients already reduced by NCCL)
+  const float* grad[8];   // grad[r]: rank r's gradient accumulator (same layout everywhere)
+  float* pout[8];         // pout[r]: rank r's output parameter buffer
+};
+
 // VEC = 4, kZ = false: C % 4 == 0, each thread owns one float4 = 4 channels of one voxel.
 // VEC = 4, kZ = true : C == 1 and Z % 4 == 0 (density): one float4 = 4 consecutive z voxels; the z neighbours are the
 //                      vector shifted by one lane plus one scalar load at each end.
@@ -42,12 +53,12 @@ __device__ __forceinline__ void adam_elem_nolr(float& p, float g, float& m, floa
 //         neighbour vectors are all loaded up front, independent of each other: ~10 loads in flight per thread instead
 //         of three dependent phases (p,g -> neighbours -> m,v).  The lazy variant keeps the phases: on sparse scenes
 //         (masked Adam, sparse TV) most elements stop after reading g (4 B/elem).
-template <int VEC, bool kTV, bool kEager, bool kZ>
+template <int VEC, bool kTV, bool kEager, bool kZ, bool kPeer>
 __global__ void __launch_bounds__(256) sweep_kernel(
     const float* __restrict__ pin, float* __restrict__ pout, float* __restrict__ grad,
     float* __restrict__ m_, float* __restrict__ v_, const float* __restrict__ perlr, int X, int Y,
     int Z, int C, int x_begin, int x_end, int tv_dense, float wy, float wz, int masked,
-    float step_size, float beta1, float beta2, float eps) {
+    float step_size, float beta1, float beta2, float eps, SweepPeers peers) {
   static_assert(!kZ || VEC == 4, "z-vectorised variant uses float4");
   // this launch owns the x-slab [x_begin, x_end) (the whole grid on one GPU, 1/n of it when the sweep is
   // sharded after a reduce-scatter); neighbours outside the slab are still read from the full buffers
@@ -87,9 +98,23 @@ __global__ void __launch_bounds__(256) sweep_kernel(
       ld(v_ + e0, v);
       if (perlr) ldg(perlr + e0, l);
     }
-    bool dirty = false;  // original gradient non-zero somewhere -> must be re-zeroed
+    bool dirty = false;  // original (local) gradient non-zero somewhere -> must be re-zeroed
 #pragma unroll
     for (int k = 0; k < VEC; ++k) dirty = dirty || (g[k] != 0.f);
+    if constexpr (kPeer) {   // g = sum over ranks, in rank order (peers.grad[self] is the local buffer)
+      float gr[8][VEC];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < peers.n) ld(peers.grad[r] + e0, gr[r]);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) g[k] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < peers.n) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) g[k] = fadd(g[k], gr[r][k]);
+        }
+    }
     if (kTV) {
       bool any = kEager || tv_dense != 0;
 #pragma unroll
@@ -160,7 +185,15 @@ __global__ void __launch_bounds__(256) sweep_kernel(
       st(v_ + e0, v);
     }
     // new parameters: always written when ping-ponging (pout != pin), only when changed in place
-    if (upd || pout != pin) st(pout + e0, p);
+    if (upd || pout != pin) {
+      if constexpr (kPeer) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < peers.n) st(peers.pout[r] + e0, p);
+      } else {
+        st(pout + e0, p);
+      }
+    }
     // re-zero the gradient accumulator for the next step (only where it was non-zero)
     if (dirty) {
       float zero[VEC];
@@ -207,11 +240,11 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 
 using namespace dvgo;
 
-DVGO_API int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float* exp_avg,
-                              float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C,
-                              int x_begin, int x_end, int tv, int tv_dense, float wx, float wy, float wz,
-                              int masked, int step, float beta1, float beta2, float lr, float eps,
-                              dvgo_stream_t stream) {
+static int sweep_launch(const float* param_in, float* param_out, float* grad, float* exp_avg,
+                        float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C,
+                        int x_begin, int x_end, int tv, int tv_dense, float wx, float wy, float wz,
+                        int masked, int step, float beta1, float beta2, float lr, float eps,
+                        const SweepPeers& peers, dvgo_stream_t stream) {
   (void)wx;
   if (X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || step <= 0) return DVGO_EINVAL;
   if (x_end < 0) x_end = X;
@@ -228,18 +261,23 @@ DVGO_API int dvgo_fused_sweep(const float* param_in, float* param_out, float* gr
                    al16(exp_avg_sq) && (!perlr || al16(perlr));
   cudaStream_t s = as_stream(stream);
 #define SWEEP_ARGS param_in, param_out, grad, exp_avg, exp_avg_sq, perlr, X, Y, Z, C, x_begin, x_end, tv_dense, wy, wz, \
-                   masked, step_size, beta1, beta2, eps
+                   masked, step_size, beta1, beta2, eps, peers
   const bool eager = !masked || (tv && tv_dense);   // every element is updated: issue all loads up front
   const bool zvec = !vec && C == 1 && Z % 4 == 0 && al16(param_in) && al16(param_out) && al16(grad) && al16(exp_avg) &&
                     al16(exp_avg_sq) && (!perlr || al16(perlr));
   // one resident wave looping grid-stride (profiles/r01_sweep_grid.txt): grid = SMs x CTAs that fit per SM
-#define SWEEP_ONE(V, TV, EAGER, KZ, N)                                                                \
+#define SWEEP_ONE2(V, TV, EAGER, KZ, PEER, N)                                                         \
   do {                                                                                                \
     int occ = 4;                                                                                      \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<V, TV, EAGER, KZ>, 256, 0);      \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_kernel<V, TV, EAGER, KZ, PEER>, 256, 0); \
     const int64_t want = ((N) + 255) / 256, cap = static_cast<int64_t>(kNumSMs) * (occ > 0 ? occ : 1); \
     const int blocks = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);                    \
-    sweep_kernel<V, TV, EAGER, KZ><<<blocks, 256, 0, s>>>(SWEEP_ARGS);                                \
+    sweep_kernel<V, TV, EAGER, KZ, PEER><<<blocks, 256, 0, s>>>(SWEEP_ARGS);                          \
+  } while (0)
+#define SWEEP_ONE(V, TV, EAGER, KZ, N)                                                                \
+  do {                                                                                                \
+    if (peers.n > 0) SWEEP_ONE2(V, TV, EAGER, KZ, true, N);                                           \
+    else SWEEP_ONE2(V, TV, EAGER, KZ, false, N);                                                      \
   } while (0)
 #define SWEEP_LAUNCH(V, KZ, N)                                                                        \
   do {                                                                                                \
@@ -253,8 +291,39 @@ DVGO_API int dvgo_fused_sweep(const float* param_in, float* param_out, float* gr
   else SWEEP_LAUNCH(1, false, n);
 #undef SWEEP_LAUNCH
 #undef SWEEP_ONE
+#undef SWEEP_ONE2
 #undef SWEEP_ARGS
   return launch_status();
+}
+
+DVGO_API int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float* exp_avg,
+                              float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C,
+                              int x_begin, int x_end, int tv, int tv_dense, float wx, float wy, float wz,
+                              int masked, int step, float beta1, float beta2, float lr, float eps,
+                              dvgo_stream_t stream) {
+  SweepPeers none;
+  none.n = 0;
+  return sweep_launch(param_in, param_out, grad, exp_avg, exp_avg_sq, perlr, X, Y, Z, C, x_begin, x_end, tv, tv_dense,
+                      wx, wy, wz, masked, step, beta1, beta2, lr, eps, none, stream);
+}
+
+DVGO_API int dvgo_fused_sweep_peer(const float* param_in, float* const* param_out_peers_host,
+                                   float* const* grad_peers_host, int n_peers, int self_rank, float* exp_avg,
+                                   float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C, int x_begin,
+                                   int x_end, int tv, int tv_dense, float wx, float wy, float wz, int masked, int step,
+                                   float beta1, float beta2, float lr, float eps, dvgo_stream_t stream) {
+  if (!param_out_peers_host || !grad_peers_host || n_peers < 1 || n_peers > 8 || self_rank < 0 || self_rank >= n_peers)
+    return DVGO_EINVAL;
+  SweepPeers peers;
+  peers.n = n_peers;
+  for (int r = 0; r < 8; ++r) {
+    peers.grad[r] = r < n_peers ? grad_peers_host[r] : nullptr;
+    peers.pout[r] = r < n_peers ? param_out_peers_host[r] : nullptr;
+    if (r < n_peers && (!peers.grad[r] || !peers.pout[r])) return DVGO_EINVAL;
+  }
+  return sweep_launch(param_in, peers.pout[self_rank], const_cast<float*>(peers.grad[self_rank]), exp_avg, exp_avg_sq,
+                      perlr, X, Y, Z, C, x_begin, x_end, tv, tv_dense, wx, wy, wz, masked, step, beta1, beta2, lr, eps,
+                      peers, stream);
 }
 
 DVGO_API int dvgo_grid_ncdhw_to_cl(const float* src, float* dst, int C, int64_t G,

@@ -212,7 +212,7 @@ class FusedRenderer(_FusedBase):
 
 class FusedTrainer(_FusedBase):
     def __init__(self, model, cfg_train, render_kwargs, world_size=1, dist_group=None, mlp="auto",
-                 betas=(0.9, 0.99), eps=1e-8, rank=None, shard_sweep=True, global_step=0):
+                 betas=(0.9, 0.99), eps=1e-8, rank=None, shard_sweep=True, global_step=0, exchange="auto"):
         super().__init__(model, render_kwargs, mlp)
         self.cfg = dict(cfg_train)
         self.world_size = world_size
@@ -243,6 +243,48 @@ class FusedTrainer(_FusedBase):
         if model.rgbnet is not None and self.mlp_mode == "tc":
             from .fused_mlp import TensorCoreMLP
             self._tc = TensorCoreMLP(model.rgbnet, self.device, train=True)
+        # gradient exchange of ray-sharded data parallel training:
+        #   "peer": ONE kernel per grid = reduce-scatter + TV/Adam sweep + all-gather over NVLink peer memory
+        #           (torch symmetric memory gives every rank the device addresses of every rank's buffers);
+        #   "nccl": reduce_scatter -> slab sweep -> all_gather (or plain all-reduce when shard_sweep=False).
+        self._pp = None
+        self.exchange = "none"
+        if world_size > 1:
+            self.exchange = "nccl"
+            if exchange in ("auto", "peer") and shard_sweep and world_size <= 8:
+                self._setup_peer(required=(exchange == "peer"))
+
+    def _setup_peer(self, required=False):
+        """Re-home the six exchanged buffers (both parameter ping-pong buffers and the gradient accumulators of
+        density and k0) in symmetric memory and collect every rank's device addresses of them."""
+        import torch.distributed as dist
+        ok, pp, keep, err = True, {}, [], None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.dist_group if self.dist_group is not None else dist.group.WORLD
+            new = {}
+            for name in ("density", "density_next", "k0", "k0_next", "g_density", "g_k0"):
+                old = getattr(self, name)
+                t = symm.empty(tuple(old.shape), dtype=old.dtype, device=self.device)
+                t.copy_(old)
+                hdl = symm.rendezvous(t, group)
+                pp[name] = [int(p) for p in hdl.buffer_ptrs]
+                assert len(pp[name]) == self.world_size and pp[name][self.rank] == t.data_ptr()
+                keep.append(hdl)
+                new[name] = t
+        except Exception as e:  # symmetric memory unavailable on this system: keep the NCCL exchange
+            ok, err = False, e
+        flag = torch.tensor([1.0 if ok else 0.0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.dist_group)
+        if float(flag.item()) < 1.0:
+            if required:
+                raise RuntimeError("peer-memory gradient exchange unavailable: %r" % (err,))
+            return
+        for name, t in new.items():
+            setattr(self, name, t)
+        self._pp, self._symm_handles = pp, keep
+        self._bar = torch.zeros(1, device=self.device)
+        self.exchange = "peer"
 
     def set_pervoxel_lr(self, count):
         """View-count learning-rate table for the density grid (lib/masked_adam.py:35-37)."""
@@ -331,13 +373,22 @@ class FusedTrainer(_FusedBase):
             return self.rank * n, (self.rank + 1) * n
         return None
 
+    def _rgbnet_grads(self):
+        """Autograd-mode rgbnet gradients, materialised as zeros where a rank had no surviving sample: every rank
+        must enter the same collectives."""
+        out = []
+        for p in self.model.rgbnet.parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            out.append(p.grad)
+        return out
+
     def _reduce_grads(self, slab):
         import torch.distributed as dist
         from .parallel import allreduce_sum_
         small = []
         if self.model.rgbnet is not None:
-            small = [self._tc.grad_flat] if self.mlp_mode == "tc" else \
-                [p.grad for p in self.model.rgbnet.parameters() if p.grad is not None]
+            small = [self._tc.grad_flat] if self.mlp_mode == "tc" else self._rgbnet_grads()
         if slab is None:
             allreduce_sum_([self.g_density, self.g_k0] + small, self.dist_group)
             return
@@ -369,13 +420,32 @@ class FusedTrainer(_FusedBase):
             on, dense = True, bool(cfg.get("tv_dense", True))
         return on, dense
 
+    def _peer_barrier(self, with_small_grads=False):
+        """Cross-rank ordering point on the current stream: a (tiny) NCCL all-reduce completes on a rank only after
+        every rank has reached it in ITS stream order.  Before the sweep it also sums the rgbnet gradients."""
+        import torch.distributed as dist
+        from .parallel import allreduce_sum_
+        small = []
+        if with_small_grads and self.model.rgbnet is not None:
+            small = [self._tc.grad_flat] if self.mlp_mode == "tc" else self._rgbnet_grads()
+        if small:
+            allreduce_sum_(small, self.dist_group)
+        else:
+            dist.all_reduce(self._bar, group=self.dist_group)
+
     def _optimise(self, n_global):
         cfg = self.cfg
-        slab = self._slab()
-        if self.world_size > 1:
-            self._reduce_grads(slab)
+        peer = self.exchange == "peer"
+        slab = None if peer else self._slab()
+        if peer:
+            self._peer_barrier(with_small_grads=True)      # every rank's backward has finished
             self._mark("grad_exchange")
-        x0, x1 = slab if slab is not None else (0, self.X)
+            x0, x1 = (self.X * self.rank) // self.world_size, (self.X * (self.rank + 1)) // self.world_size
+        else:
+            if self.world_size > 1:
+                self._reduce_grads(slab)
+                self._mark("grad_exchange")
+            x0, x1 = slab if slab is not None else (0, self.X)
         updated = []
         self.opt_step += 1
         b1, b2 = self.betas
@@ -398,14 +468,31 @@ class FusedTrainer(_FusedBase):
             nxt = getattr(self, name + "_next") if tv else cur
             per_lr = self.per_lr if (name == "density" and self.per_lr is not None) else None
             masked = self.masked[name] and per_lr is None  # dispatch of lib/masked_adam.py:60-71
-            ext.sweep(cur, nxt, getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
-                      per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, self.opt_step,
-                      b1, b2, lr, self.eps, x0, x1)
+            if peer:
+                ext.sweep_peer(cur, self._pp[name + "_next" if tv else name], self._pp["g_" + name], self.rank,
+                               getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
+                               per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, self.opt_step,
+                               b1, b2, lr, self.eps, x0, x1)
+            else:
+                ext.sweep(cur, nxt, getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
+                          per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, self.opt_step,
+                          b1, b2, lr, self.eps, x0, x1)
             if tv:
                 setattr(self, name, nxt)
                 setattr(self, name + "_next", cur)
+                if peer:
+                    self._pp[name], self._pp[name + "_next"] = self._pp[name + "_next"], self._pp[name]
             updated.append(name)
-        if slab is not None:
+        if peer:
+            self._mark("sweep_grids")
+            self._peer_barrier()          # every rank has read my gradients and written my parameters
+            for g in (self.g_density, self.g_k0):   # the slabs other ranks own still hold my partial sums
+                if x0 > 0:
+                    ext.zero_(g[:x0])
+                if x1 < self.X:
+                    ext.zero_(g[x1:])
+            self._mark("param_gather")
+        elif slab is not None:
             self._mark("sweep_grids")     # slab-sharded grid sweeps end here; "sweep" then only holds the rgbnet Adam
             self._gather_params(slab, updated)
             self._mark("param_gather")

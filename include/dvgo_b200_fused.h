@@ -158,6 +158,19 @@ int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float
                      int x_end, int tv, int tv_dense, float wx, float wy, float wz, int masked, int step,
                      float beta1, float beta2, float lr, float eps, dvgo_stream_t stream);
 
+/* The same sweep as ONE kernel with the gradient exchange of ray-sharded data parallel training folded in
+ * (reduce-scatter + sweep + all-gather over NVLink peer memory): for the x-slab [x_begin, x_end) this rank owns,
+ * the gradient is the sum over r < n_peers of grad_peers_host[r][e] (peer loads, rank order), and the new
+ * parameters are stored to param_out_peers_host[r][e] for every r (peer stores).  The two host arrays hold
+ * n_peers DEVICE pointers, all mapped in this process (torch symmetric memory / CUDA IPC), index self_rank being
+ * the local buffers; exp_avg / exp_avg_sq / perlr are local.  The caller orders the kernel after every rank's
+ * backward pass and must not touch the gradient / output buffers again before every rank's sweep has finished. */
+int dvgo_fused_sweep_peer(const float* param_in, float* const* param_out_peers_host,
+                          float* const* grad_peers_host, int n_peers, int self_rank, float* exp_avg,
+                          float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C, int x_begin,
+                          int x_end, int tv, int tv_dense, float wx, float wy, float wz, int masked, int step,
+                          float beta1, float beta2, float lr, float eps, dvgo_stream_t stream);
+
 /* Layout converters at the state_dict boundary: [C,X,Y,Z] <-> [X,Y,Z,C]. */
 int dvgo_grid_ncdhw_to_cl(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);
 int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G, dvgo_stream_t stream);

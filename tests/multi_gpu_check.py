@@ -1,5 +1,6 @@
-"""Run under torchrun on >= 2 GPUs: ray-sharded FusedTrainer (reduce-scatter -> slab-sharded sweep ->
-all-gather, and the plain all-reduce variant) must reproduce the single-GPU step on the full batch.
+"""Run under torchrun on >= 2 GPUs: the ray-sharded FusedTrainer must reproduce the single-GPU step on the full batch
+in all three gradient-exchange modes: "peer" (one kernel = reduce-scatter + sweep + all-gather over NVLink peer
+memory), NCCL reduce-scatter -> slab-sharded sweep -> all-gather, and the plain NCCL all-reduce variant.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29533 tests/multi_gpu_check.py
@@ -20,7 +21,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     from directvoxgo_b200 import synthetic as syn
     from directvoxgo_b200.dvgo import DirectVoxGO
     from directvoxgo_b200.fused import FusedTrainer
@@ -36,9 +38,11 @@ def main():
     base = base.to(dev)
     cfg, rk = dict(syn.FINE_TRAIN), dict(syn.RENDER_KWARGS)
     ok = True
-    for shard in (True, False):
+    for exchange, shard in (("auto", True), ("nccl", True), ("nccl", False)):
         m_dp, m_one = copy.deepcopy(base), copy.deepcopy(base)
-        t_dp = FusedTrainer(m_dp, cfg, rk, world_size=world, mlp="torch", shard_sweep=shard)
+        t_dp = FusedTrainer(m_dp, cfg, rk, world_size=world, mlp="torch", shard_sweep=shard, exchange=exchange)
+        if rank == 0:
+            print("requested exchange=%s shard_sweep=%s -> running %s" % (exchange, shard, t_dp.exchange))
         t_one = FusedTrainer(m_one, cfg, rk, world_size=1, mlp="torch")
         for it in range(3):
             batch = syn.random_training_rays(4096, n_views=20, seed=90 + it, device=dev)
@@ -48,7 +52,7 @@ def main():
             l_one = t_one.step(*batch)
             if abs(float(l_dp) - float(l_one)) > 2e-5 * max(1.0, abs(float(l_one))):
                 ok = False
-                print("rank", rank, "shard", shard, "it", it, "loss mismatch", float(l_dp), float(l_one))
+                print("rank", rank, t_dp.exchange, "shard", shard, "it", it, "loss mismatch", float(l_dp), float(l_one))
         t_dp.sync_to_model(); t_one.sync_to_model()
         for name in ("density", "k0"):
             d = (getattr(m_dp, name) - getattr(m_one, name)).abs()
@@ -56,7 +60,7 @@ def main():
             if not (med < 1e-4 and q < 5e-3):
                 ok = False
             if rank == 0:
-                print("shard_sweep=%s %s: median |d| %.2e, 99.9%% %.2e" % (shard, name, med, q))
+                print("%s shard_sweep=%s %s: median |d| %.2e, 99.9%% %.2e" % (t_dp.exchange, shard, name, med, q))
         # every rank must hold identical parameters after the gather
         chk = t_dp.k0.double().sum()
         lo_, hi_ = chk.clone(), chk.clone()
