@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "peer_p2p", "nccl"],
+                    help="multi-GPU gradient exchange of the fused trainer (see DESIGN.md section 6)")
     ap.add_argument("--ramp-s", dest="ramp_s", type=float, default=1.5,
                     help="seconds of untimed steps before the W warm-up steps (GPU clock ramp)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -283,7 +285,7 @@ def run_ours(args):
     if path in ("auto", "fused"):
         try:
             from directvoxgo_b200.fused import FusedTrainer
-            trainer = FusedTrainer(model, cfg, rk, world_size=world)
+            trainer = FusedTrainer(model, cfg, rk, world_size=world, exchange=args.exchange)
             path = "fused"
         except ImportError:
             if path == "fused":
@@ -468,7 +470,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD % args.grid,
                    "rays_per_step_per_gpu": N_RAYS, "path": path, "rgbnet": getattr(trainer, "mlp_mode", "torch"), "parallelism": "ray-sharded dp%d" % world,
-                   "grad_exchange": getattr(trainer, "exchange", "nccl all-reduce" if world > 1 else "none"),
+                   "grad_exchange": getattr(trainer, "exchange", "nccl all-reduce" if world > 1 else "none") +
+                                    (" + NVLS multicast" if getattr(trainer, "multicast", False) else ""),
                    "samples_per_step": balg["M0"], "unique_voxels_touched": balg["U"],
                    "l2_policy": "working set (params+grads+Adam state = %.2f GB) larger than the 126 MB L2; "
                                 "%d distinct ray batches cycled" % (balg["G"] * 13 * 16 / 1e9, N_BATCHES),

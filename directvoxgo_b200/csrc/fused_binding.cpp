@@ -191,7 +191,8 @@ void sweep(Tensor param_in, Tensor param_out, Tensor grad, Tensor exp_avg, Tenso
 // The sweep with the gradient exchange folded in (include/dvgo_b200_fused.h: dvgo_fused_sweep_peer).  The peer lists
 // hold raw device addresses of every rank's buffer as mapped in THIS process (torch symmetric memory); param_in,
 // grad_local, exp_avg, exp_avg_sq are this rank's tensors (grad_local / the local output are only size-checked).
-void sweep_peer(Tensor param_in, std::vector<int64_t> param_out_ptrs, std::vector<int64_t> grad_ptrs, int self_rank,
+void sweep_peer(Tensor param_in, std::vector<int64_t> param_out_ptrs, std::vector<int64_t> grad_ptrs,
+                int64_t param_out_mc, int64_t grad_mc, int self_rank,
                 Tensor grad_local, Tensor exp_avg, Tensor exp_avg_sq, c10::optional<Tensor> perlr, int X, int Y, int Z,
                 int C, bool tv, bool tv_dense, double wx, double wy, double wz, bool masked, int step, double beta1,
                 double beta2, double lr, double eps, int x_begin, int x_end) {
@@ -211,7 +212,8 @@ void sweep_peer(Tensor param_in, std::vector<int64_t> param_out_ptrs, std::vecto
     grads[r] = reinterpret_cast<float*>(grad_ptrs[r]);
   }
   const c10::cuda::CUDAGuard guard(param_in.device());
-  rc_check(dvgo_fused_sweep_peer(fp(param_in), pout, grads, np, self_rank, fpm(exp_avg), fpm(exp_avg_sq), fp_opt(perlr),
+  rc_check(dvgo_fused_sweep_peer(fp(param_in), pout, grads, reinterpret_cast<float*>(param_out_mc),
+                                 reinterpret_cast<const float*>(grad_mc), np, self_rank, fpm(exp_avg), fpm(exp_avg_sq), fp_opt(perlr),
                                  X, Y, Z, C, x_begin, x_end, tv, tv_dense, static_cast<float>(wx),
                                  static_cast<float>(wy), static_cast<float>(wz), masked, step,
                                  static_cast<float>(beta1), static_cast<float>(beta2), static_cast<float>(lr),

@@ -43,7 +43,34 @@ struct SweepPeers {
   int n;                  // 0: local mode (single GPU, or gradients already reduced by NCCL)
   const float* grad[8];   // grad[r]: rank r's gradient accumulator (same layout everywhere)
   float* pout[8];         // pout[r]: rank r's output parameter buffer
+  // NVLink SHARP (NVLS) multicast addresses of the same two buffers, or null: one multimem.ld_reduce returns the
+  // gradient already summed over all ranks by the switch, one multimem.st writes all ranks' parameter buffers --
+  // the per-GPU NVLink traffic drops from (n-1)/n of the grid each way to 1/n.
+  const float* grad_mc;
+  float* pout_mc;
 };
+
+__device__ __forceinline__ float4 multimem_ld_reduce_add4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float multimem_ld_reduce_add1(const float* mc) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st1(float* mc, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
 
 // VEC = 4, kZ = false: C % 4 == 0, each thread owns one float4 = 4 channels of one voxel.
 // VEC = 4, kZ = true : C == 1 and Z % 4 == 0 (density): one float4 = 4 consecutive z voxels; the z neighbours are the
@@ -101,7 +128,14 @@ __global__ void __launch_bounds__(256) sweep_kernel(
     bool dirty = false;  // original (local) gradient non-zero somewhere -> must be re-zeroed
 #pragma unroll
     for (int k = 0; k < VEC; ++k) dirty = dirty || (g[k] != 0.f);
-    if constexpr (kPeer) {   // g = sum over ranks, in rank order (peers.grad[self] is the local buffer)
+    if (kPeer && peers.grad_mc) {   // summed by the switch
+      if constexpr (VEC == 4) {
+        const float4 a = multimem_ld_reduce_add4(peers.grad_mc + e0);
+        g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
+      } else {
+        g[0] = multimem_ld_reduce_add1(peers.grad_mc + e0);
+      }
+    } else if constexpr (kPeer) {   // g = sum over ranks, in rank order (peers.grad[self] is the local buffer)
       float gr[8][VEC];
 #pragma unroll
       for (int r = 0; r < 8; ++r)
@@ -186,7 +220,10 @@ __global__ void __launch_bounds__(256) sweep_kernel(
     }
     // new parameters: always written when ping-ponging (pout != pin), only when changed in place
     if (upd || pout != pin) {
-      if constexpr (kPeer) {
+      if (kPeer && peers.pout_mc) {
+        if constexpr (VEC == 4) multimem_st4(peers.pout_mc + e0, make_float4(p[0], p[1], p[2], p[3]));
+        else multimem_st1(peers.pout_mc + e0, p[0]);
+      } else if constexpr (kPeer) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
           if (r < peers.n) st(peers.pout[r] + e0, p);
@@ -202,6 +239,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(
       st(grad + e0, zero);
     }
   }
+  if constexpr (kPeer) __threadfence_system();   // peer / multicast stores performed before the kernel retires
 }
 
 __global__ void __launch_bounds__(256) ncdhw_to_cl_kernel(const float* __restrict__ src,
@@ -303,12 +341,15 @@ DVGO_API int dvgo_fused_sweep(const float* param_in, float* param_out, float* gr
                               dvgo_stream_t stream) {
   SweepPeers none;
   none.n = 0;
+  none.grad_mc = nullptr;
+  none.pout_mc = nullptr;
   return sweep_launch(param_in, param_out, grad, exp_avg, exp_avg_sq, perlr, X, Y, Z, C, x_begin, x_end, tv, tv_dense,
                       wx, wy, wz, masked, step, beta1, beta2, lr, eps, none, stream);
 }
 
 DVGO_API int dvgo_fused_sweep_peer(const float* param_in, float* const* param_out_peers_host,
-                                   float* const* grad_peers_host, int n_peers, int self_rank, float* exp_avg,
+                                   float* const* grad_peers_host, float* param_out_multicast,
+                                   const float* grad_multicast, int n_peers, int self_rank, float* exp_avg,
                                    float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C, int x_begin,
                                    int x_end, int tv, int tv_dense, float wx, float wy, float wz, int masked, int step,
                                    float beta1, float beta2, float lr, float eps, dvgo_stream_t stream) {
@@ -316,6 +357,8 @@ DVGO_API int dvgo_fused_sweep_peer(const float* param_in, float* const* param_ou
     return DVGO_EINVAL;
   SweepPeers peers;
   peers.n = n_peers;
+  peers.grad_mc = grad_multicast;
+  peers.pout_mc = param_out_multicast;
   for (int r = 0; r < 8; ++r) {
     peers.grad[r] = r < n_peers ? grad_peers_host[r] : nullptr;
     peers.pout[r] = r < n_peers ? param_out_peers_host[r] : nullptr;

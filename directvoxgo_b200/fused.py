@@ -251,14 +251,19 @@ class FusedTrainer(_FusedBase):
         self.exchange = "none"
         if world_size > 1:
             self.exchange = "nccl"
-            if exchange in ("auto", "peer") and shard_sweep and world_size <= 8:
-                self._setup_peer(required=(exchange == "peer"))
+            if exchange in ("auto", "peer", "peer_p2p") and shard_sweep and world_size <= 8:
+                # "peer_p2p": per-peer loads / stores only; "peer": NVLS multicast when the system has it; "auto":
+                # multicast from 4 ranks up -- measured on B200 (profiles/r01_peer_exchange.txt): at 2 ranks both
+                # move the same bytes per link and the plain peer accesses are faster (0.47 vs 0.56 ms), at 4 ranks
+                # multicast moves 2/3 of the bytes and wins (0.50 vs 0.53 ms), and the gap grows with n.
+                use_mc = exchange == "peer" or (exchange == "auto" and world_size >= 4)
+                self._setup_peer(required=(exchange != "auto"), multicast=use_mc)
 
-    def _setup_peer(self, required=False):
+    def _setup_peer(self, required=False, multicast=True):
         """Re-home the six exchanged buffers (both parameter ping-pong buffers and the gradient accumulators of
         density and k0) in symmetric memory and collect every rank's device addresses of them."""
         import torch.distributed as dist
-        ok, pp, keep, err = True, {}, [], None
+        ok, pp, mc, keep, err = True, {}, {}, [], None
         try:
             import torch.distributed._symmetric_memory as symm
             group = self.dist_group if self.dist_group is not None else dist.group.WORLD
@@ -270,6 +275,7 @@ class FusedTrainer(_FusedBase):
                 hdl = symm.rendezvous(t, group)
                 pp[name] = [int(p) for p in hdl.buffer_ptrs]
                 assert len(pp[name]) == self.world_size and pp[name][self.rank] == t.data_ptr()
+                mc[name] = int(hdl.multicast_ptr or 0) if multicast else 0
                 keep.append(hdl)
                 new[name] = t
         except Exception as e:  # symmetric memory unavailable on this system: keep the NCCL exchange
@@ -282,7 +288,13 @@ class FusedTrainer(_FusedBase):
             return
         for name, t in new.items():
             setattr(self, name, t)
-        self._pp, self._symm_handles = pp, keep
+        # multicast is used only if every buffer on every rank got a multicast mapping
+        have = torch.tensor([1.0 if all(mc.values()) else 0.0], device=self.device)
+        dist.all_reduce(have, op=dist.ReduceOp.MIN, group=self.dist_group)
+        if float(have.item()) < 1.0:
+            mc = {k: 0 for k in mc}
+        self._pp, self._mc, self._symm_handles = pp, mc, keep
+        self.multicast = bool(mc["k0"])
         self._bar = torch.zeros(1, device=self.device)
         self.exchange = "peer"
 
@@ -469,7 +481,8 @@ class FusedTrainer(_FusedBase):
             per_lr = self.per_lr if (name == "density" and self.per_lr is not None) else None
             masked = self.masked[name] and per_lr is None  # dispatch of lib/masked_adam.py:60-71
             if peer:
-                ext.sweep_peer(cur, self._pp[name + "_next" if tv else name], self._pp["g_" + name], self.rank,
+                out = name + "_next" if tv else name
+                ext.sweep_peer(cur, self._pp[out], self._pp["g_" + name], self._mc[out], self._mc["g_" + name], self.rank,
                                getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
                                per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, self.opt_step,
                                b1, b2, lr, self.eps, x0, x1)
@@ -481,7 +494,8 @@ class FusedTrainer(_FusedBase):
                 setattr(self, name, nxt)
                 setattr(self, name + "_next", cur)
                 if peer:
-                    self._pp[name], self._pp[name + "_next"] = self._pp[name + "_next"], self._pp[name]
+                    for tab in (self._pp, self._mc):
+                        tab[name], tab[name + "_next"] = tab[name + "_next"], tab[name]
             updated.append(name)
         if peer:
             self._mark("sweep_grids")

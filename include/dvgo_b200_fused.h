@@ -164,9 +164,12 @@ int dvgo_fused_sweep(const float* param_in, float* param_out, float* grad, float
  * parameters are stored to param_out_peers_host[r][e] for every r (peer stores).  The two host arrays hold
  * n_peers DEVICE pointers, all mapped in this process (torch symmetric memory / CUDA IPC), index self_rank being
  * the local buffers; exp_avg / exp_avg_sq / perlr are local.  The caller orders the kernel after every rank's
- * backward pass and must not touch the gradient / output buffers again before every rank's sweep has finished. */
+ * backward pass and must not touch the gradient / output buffers again before every rank's sweep has finished.
+ * param_out_multicast / grad_multicast: NVLS multicast addresses of the same buffers (one multimem.st reaches every
+ * rank, one multimem.ld_reduce returns the switch-summed gradient), or NULL to use the per-peer loads / stores. */
 int dvgo_fused_sweep_peer(const float* param_in, float* const* param_out_peers_host,
-                          float* const* grad_peers_host, int n_peers, int self_rank, float* exp_avg,
+                          float* const* grad_peers_host, float* param_out_multicast,
+                          const float* grad_multicast, int n_peers, int self_rank, float* exp_avg,
                           float* exp_avg_sq, const float* perlr, int X, int Y, int Z, int C, int x_begin,
                           int x_end, int tv, int tv_dense, float wx, float wy, float wz, int masked, int step,
                           float beta1, float beta2, float lr, float eps, dvgo_stream_t stream);

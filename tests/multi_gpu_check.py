@@ -38,11 +38,12 @@ def main():
     base = base.to(dev)
     cfg, rk = dict(syn.FINE_TRAIN), dict(syn.RENDER_KWARGS)
     ok = True
-    for exchange, shard in (("auto", True), ("nccl", True), ("nccl", False)):
+    for exchange, shard in (("auto", True), ("peer_p2p", True), ("nccl", True), ("nccl", False)):
         m_dp, m_one = copy.deepcopy(base), copy.deepcopy(base)
         t_dp = FusedTrainer(m_dp, cfg, rk, world_size=world, mlp="torch", shard_sweep=shard, exchange=exchange)
         if rank == 0:
-            print("requested exchange=%s shard_sweep=%s -> running %s" % (exchange, shard, t_dp.exchange))
+            print("requested exchange=%s shard_sweep=%s -> running %s (multicast %s)" % (
+                exchange, shard, t_dp.exchange, getattr(t_dp, "multicast", False)))
         t_one = FusedTrainer(m_one, cfg, rk, world_size=1, mlp="torch")
         for it in range(3):
             batch = syn.random_training_rays(4096, n_views=20, seed=90 + it, device=dev)
