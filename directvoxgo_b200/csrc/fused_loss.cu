@@ -183,6 +183,33 @@ static inline int stream_grid(int64_t cap, int threads) {
   return static_cast<int>(want < lim ? (want > 0 ? want : 1) : lim);
 }
 
+// View-direction positional encoding for the tensor-core rgbnet, written straight into its padded table
+// (lib/dvgo.py:524-525: emb = (viewdirs[..., None] * viewfreq).flatten(-2); cat[viewdirs, sin(emb), cos(emb)]):
+// columns [0,3) viewdirs, [3, 3+3F) sin, [3+3F, 3+6F) cos, column P = 3+6F holds 1 (carries b1 through the first
+// GEMM), the rest up to `stride` is 0.  One launch instead of ~8 elementwise torch kernels per step / render chunk.
+__global__ void __launch_bounds__(256) view_embedding_kernel(const float* __restrict__ viewdirs,
+                                                             const float* __restrict__ freq, int F, int64_t n,
+                                                             int stride, float* __restrict__ out) {
+  const int P = 3 + 6 * F;
+  const int64_t total = n * stride;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / stride;
+    const int c = static_cast<int>(i - r * stride);
+    float v;
+    if (c < 3) {
+      v = viewdirs[3 * r + c];
+    } else if (c < P) {
+      const int k = (c - 3) % (3 * F);          // index into emb = [x*f0..x*fF-1, y*f0.., z*f0..]
+      const float e = fmul(viewdirs[3 * r + k / F], __ldg(freq + k % F));
+      v = (c - 3) < 3 * F ? sinf(e) : cosf(e);
+    } else {
+      v = c == P ? 1.f : 0.f;
+    }
+    out[i] = v;
+  }
+}
+
 }  // namespace dvgo
 
 using namespace dvgo;
@@ -247,5 +274,16 @@ DVGO_API int dvgo_fused_zero(void* ptr, int64_t n_words, dvgo_stream_t stream) {
   if (!ptr) return DVGO_EINVAL;
   zero_words_kernel<<<stream_grid(n_words, 256), 256, 0, as_stream(stream)>>>(
       static_cast<uint32_t*>(ptr), n_words);
+  return launch_status();
+}
+
+DVGO_API int dvgo_view_embedding(const float* viewdirs, const float* freq, int n_freq, int64_t n_rays, int stride,
+                                 float* out, dvgo_stream_t stream) {
+  if (n_rays < 0 || n_freq < 0 || stride < 3 + 6 * n_freq + 1 || !out) return DVGO_EINVAL;
+  if (n_rays == 0) return 0;
+  if (!viewdirs || (n_freq > 0 && !freq)) return DVGO_EINVAL;
+  const int64_t want = (n_rays * stride + 255) / 256;
+  const int blocks = static_cast<int>(want < kNumSMs * 8 ? want : kNumSMs * 8);
+  view_embedding_kernel<<<blocks, 256, 0, as_stream(stream)>>>(viewdirs, freq, n_freq, n_rays, stride, out);
   return launch_status();
 }

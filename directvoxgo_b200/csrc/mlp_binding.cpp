@@ -46,6 +46,17 @@ Tensor tc_rate(int ctas, int N, int ksteps, int reps, bool a_mn, bool b_mn, int 
   return out;
 }
 
+Tensor view_embedding(Tensor viewdirs, Tensor freq, int stride) {
+  chkf(viewdirs, "viewdirs"); chkf(freq, "freq");
+  TORCH_CHECK(viewdirs.dim() == 2 && viewdirs.size(1) == 3, "viewdirs must be [N,3]");
+  const c10::cuda::CUDAGuard guard(viewdirs.device());
+  auto out = torch::empty({viewdirs.size(0), stride}, viewdirs.options());
+  rc_check(dvgo_view_embedding(viewdirs.data_ptr<float>(), freq.numel() ? freq.data_ptr<float>() : nullptr,
+                               static_cast<int>(freq.numel()), viewdirs.size(0), stride, out.data_ptr<float>(),
+                               cur_stream()), "view_embedding");
+  return out;
+}
+
 inline void chki(const Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == torch::kInt32, name,
               " must be a contiguous int32 CUDA tensor");
@@ -128,6 +139,7 @@ void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("tc_selftest", &tc_selftest);
   m.def("tc_probe", &tc_probe);
   m.def("tc_rate", &tc_rate);
+  m.def("view_embedding", &view_embedding);
   m.def("mlp_fwd", &mlp_fwd);
   m.def("mlp_fwd_timeline", &mlp_fwd_timeline);
   m.def("mlp_bwd", &mlp_bwd);

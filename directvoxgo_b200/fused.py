@@ -104,6 +104,10 @@ class _FusedBase:
         self.k0 = ext.ncdhw_to_cl(model.k0.detach().contiguous())
         self._ws = {}
 
+    def _viewfreq(self):
+        vf = getattr(self.model, "viewfreq", None)     # DirectMPIGO with viewbase_pe=0 has an empty table
+        return vf if vf is not None else torch.zeros(0, device=self.device)
+
     @staticmethod
     def _tc_supported(model):
         lin = [m for m in model.rgbnet.modules() if isinstance(m, torch.nn.Linear)]
@@ -206,7 +210,7 @@ class FusedRenderer(_FusedBase):
         from .fused_mlp import TensorCoreMLP
         if not hasattr(self, "_tc"):
             self._tc = TensorCoreMLP(self.model.rgbnet, self.device)
-        pe = self._tc.pad_embedding(view_embedding(viewdirs, self.model.viewfreq))
+        pe = self._tc.embed(viewdirs, self._viewfreq())
         self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
 
 
@@ -346,7 +350,7 @@ class FusedTrainer(_FusedBase):
             after_rgb()
             ext.rgb_direct_bwd(ws.rgb, ws.d_rgb, ws.counters, ws.d_feat)
         elif self.mlp_mode == "tc":
-            pe = self._tc.pad_embedding(view_embedding(viewdirs, model.viewfreq))
+            pe = self._tc.embed(viewdirs, self._viewfreq())
             self._mark("embed")
             self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
             self._mark("mlp_fwd")

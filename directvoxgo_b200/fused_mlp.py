@@ -58,6 +58,12 @@ class TensorCoreMLP:
         self._P = P
         return out
 
+    def embed(self, viewdirs, viewfreq):
+        """The padded view-embedding table of `pad_embedding(view_embedding(...))` in one kernel."""
+        P = 3 + 6 * int(viewfreq.numel())
+        self._P = P
+        return ext.view_embedding(viewdirs.contiguous(), viewfreq, (P + 1 + 3) // 4 * 4)
+
     def forward(self, feat, s_ray, pe_pad, counters, rgb):
         ext.mlp_fwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb)
 

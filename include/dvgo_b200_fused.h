@@ -222,6 +222,11 @@ int dvgo_tc_selftest(const float* A, const float* B, float* D, int N, int K, int
 
 /* Descriptor probe (debug aid for the kernel author): A [128][K] K-major, the B operand region is
  * filled verbatim from Braw [nwords] and described with the given LBO/SBO/k-step (bytes). */
+/* View-direction encoding of lib/dvgo.py:524-525 written into the padded table the rgbnet kernels read:
+ * out [n_rays, stride] = [viewdirs | sin(v*f) | cos(v*f) | 1 | 0...], stride >= 3 + 6*n_freq + 1. */
+int dvgo_view_embedding(const float* viewdirs, const float* freq, int n_freq, int64_t n_rays, int stride,
+                        float* out, dvgo_stream_t stream);
+
 /* Tensor-core issue-rate probe (tools/mma_rate.py): `reps` x `ksteps` M=128 MMAs of width N issued by one thread per
  * CTA from zero-filled shared memory with the given descriptor fields; out[cta] = cycles. */
 int dvgo_tc_rate(int ctas, int N, int ksteps, int reps, int a_mn, int b_mn, int a_lbo, int a_sbo, int a_kstep,

@@ -79,6 +79,24 @@ def test_tc_mlp_forward(M, C, P):
     np.testing.assert_allclose(to_np(rgb[:M]), to_np(ref), rtol=0, atol=2e-3)   # stated tolerance vs exact fp32
 
 
+@pytest.mark.parametrize("n_freq", [4, 0])
+def test_view_embedding_kernel_matches_torch_composition(n_freq):
+    """lib/dvgo.py:524-525 in one kernel, written into the padded table (column P = 1, zero tail)."""
+    from directvoxgo_b200.fused import view_embedding
+    from directvoxgo_b200.fused_mlp import TensorCoreMLP
+    g = torch.Generator().manual_seed(2)
+    vd = torch.randn(5000, 3, generator=g)
+    vd = (vd / vd.norm(dim=-1, keepdim=True)).to(DEV)
+    freq = torch.tensor([2.0 ** i for i in range(n_freq)], device=DEV)
+    net = _make_mlp(1, 12 + 3 + 6 * n_freq)
+    tc = TensorCoreMLP(net, DEV)
+    ref = tc.pad_embedding(view_embedding(vd, freq))
+    got = tc.embed(vd, freq)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(to_np(got), to_np(ref), rtol=0, atol=1.2e-7)     # sinf / cosf: same libdevice routines
+    print("bit-identical:", bool(torch.equal(got, ref)))
+
+
 def test_tc_mlp_narrow_width_runs_zero_padded():
     """rgbnet_width=64 (configs/llff/llff_default.py:30), 9 features + 3 view dims: the 128-wide kernels on
     zero-padded weights.  Forward within the fp16-operand tolerance of exact fp32; gradients of the real entries
