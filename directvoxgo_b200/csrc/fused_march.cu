@@ -465,7 +465,9 @@ DVGO_API int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, cons
       !slot_expd || !slot_code || !s_ray || !s_slot || !s_weight || !alphainv_last || !counters ||
       (k0_cl && !feat))
     return DVGO_EINVAL;
-  const int wpb = 8;
+  // 2 rays (warps) per CTA: a CTA holds its slot until its longest ray ends, so small CTAs pack the SMs better
+  // (measured on B200, 8192 rays: 8 warps/CTA 0.205 + 0.243 ms for the two march stages, 2 warps/CTA 0.198 + 0.231 ms)
+  const int wpb = 2;
   DVGO_DISPATCH_C(scene->C, (march_fwd_kernel<kC><<<ray_blocks(n_rays, wpb), wpb * 32, 0,
                                                     as_stream(stream)>>>(
       rays_o, rays_d, to_args(scene), density, k0_cl, n_rays, t_min, n_steps, ray_off, slot_cap,
@@ -485,7 +487,7 @@ DVGO_API int dvgo_fused_march_bwd(const float* rays_o, const float* rays_d, cons
   if (!rays_o || !rays_d || !t_min || !n_steps || !ray_off || !slot_alpha || !slot_T || !slot_expd ||
       !slot_code || !d_w || !alphainv_last || !g_last || !grad_density || (grad_k0_cl && !d_feat))
     return DVGO_EINVAL;
-  const int wpb = 8;
+  const int wpb = 2;
   DVGO_DISPATCH_C(scene->C, (march_bwd_kernel<kC><<<ray_blocks(n_rays, wpb), wpb * 32, 0,
                                                     as_stream(stream)>>>(
       rays_o, rays_d, to_args(scene), n_rays, t_min, n_steps, ray_off, slot_alpha, slot_T, slot_expd,
