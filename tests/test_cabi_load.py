@@ -88,3 +88,43 @@ def test_product_does_not_import_the_oracle():
         assert "libdvgo_oracle" not in src, path
     for path in glob.glob(os.path.join(pkg_dir, "csrc", "*")):
         assert "oracle/" not in open(path).read().replace("see oracle/dvgo_oracle.c", ""), path
+
+
+def test_tensor_core_mlp_host_layout_zero_pads_narrow_widths():
+    """Host logic of the tensor-core rgbnet wrapper (no kernel call): a 64-wide rgbnet is laid out as a 128-wide one
+    with zero padding, the views returned by `unflatten` address exactly the real entries, and the module round-trips."""
+    from directvoxgo_b200.fused_mlp import TensorCoreMLP
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(12, 64), torch.nn.ReLU(),
+                              torch.nn.Sequential(torch.nn.Linear(64, 64), torch.nn.ReLU()), torch.nn.Linear(64, 3))
+    tc = TensorCoreMLP(net, "cpu", train=True)
+    W = TensorCoreMLP.WIDTH
+    assert tc.params.numel() == W * 12 + W + W * W + W + 3 * W + 3
+    real = tc.unflatten(tc.params)
+    for v, p in zip(real, net.parameters()):
+        assert v.shape == p.shape and torch.equal(v, p.detach())
+    mask = torch.ones_like(tc.params, dtype=torch.bool)
+    for v in tc.unflatten(mask):
+        v.fill_(False)
+    assert int(mask.sum()) == tc.params.numel() - sum(p.numel() for p in net.parameters())
+    assert torch.all(tc.params[mask] == 0)
+    with torch.no_grad():
+        for v in tc.unflatten(tc.params):
+            v.add_(1.0)
+    tc.sync_to_module()
+    for v, p in zip(tc.unflatten(tc.params), net.parameters()):
+        assert torch.equal(v, p.detach())
+    with pytest.raises(NotImplementedError):
+        TensorCoreMLP(torch.nn.Sequential(torch.nn.Linear(12, 256), torch.nn.ReLU(),
+                                          torch.nn.Sequential(torch.nn.Linear(256, 256), torch.nn.ReLU()),
+                                          torch.nn.Linear(256, 3)), "cpu")
+
+
+def test_ray_sharding_helpers():
+    from directvoxgo_b200.parallel import shard_bounds, shard_views
+    for n, world in ((8192, 8), (1000, 3), (5, 8)):
+        spans = [shard_bounds(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+        assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+    assert sorted(sum((shard_views(10, r, 4) for r in range(4)), [])) == list(range(10))
