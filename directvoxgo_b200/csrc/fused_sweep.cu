@@ -80,8 +80,11 @@ __device__ __forceinline__ void multimem_st1(float* mc, float v) {
 //         neighbour vectors are all loaded up front, independent of each other: ~10 loads in flight per thread instead
 //         of three dependent phases (p,g -> neighbours -> m,v).  The lazy variant keeps the phases: on sparse scenes
 //         (masked Adam, sparse TV) most elements stop after reading g (4 B/elem).
+#ifndef DVGO_PEER_MINB
+#define DVGO_PEER_MINB 4
+#endif
 template <int VEC, bool kTV, bool kEager, bool kZ, bool kPeer>
-__global__ void __launch_bounds__(256) sweep_kernel(
+__global__ void __launch_bounds__(256, kPeer ? DVGO_PEER_MINB : 1) sweep_kernel(
     const float* __restrict__ pin, float* __restrict__ pout, float* __restrict__ grad,
     float* __restrict__ m_, float* __restrict__ v_, const float* __restrict__ perlr, int X, int Y,
     int Z, int C, int x_begin, int x_end, int tv_dense, float wy, float wz, int masked,
@@ -136,18 +139,23 @@ __global__ void __launch_bounds__(256) sweep_kernel(
         g[0] = multimem_ld_reduce_add1(peers.grad_mc + e0);
       }
     } else if constexpr (kPeer) {   // g = sum over ranks, in rank order (peers.grad[self] is the local buffer)
-      float gr[8][VEC];
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r < peers.n) ld(peers.grad[r] + e0, gr[r]);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) g[k] = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r < peers.n) {
+      for (int b = 0; b < 8; b += 4) {       // four peers' vectors in flight at a time
+        if (b < peers.n) {
+          float gr[4][VEC];
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) g[k] = fadd(g[k], gr[r][k]);
+          for (int r = 0; r < 4; ++r)
+            if (b + r < peers.n) ld(peers.grad[b + r] + e0, gr[r]);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (b + r < peers.n) {
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) g[k] = fadd(g[k], gr[r][k]);
+            }
         }
+      }
     }
     if (kTV) {
       bool any = kEager || tv_dense != 0;
