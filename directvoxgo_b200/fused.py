@@ -256,11 +256,11 @@ class FusedTrainer(_FusedBase):
         if world_size > 1:
             self.exchange = "nccl"
             if exchange in ("auto", "peer", "peer_p2p") and shard_sweep and world_size <= 8:
-                # "peer_p2p": per-peer loads / stores only; "peer": NVLS multicast when the system has it; "auto":
-                # multicast from 4 ranks up -- measured on B200 (profiles/r01_peer_exchange.txt): at 2 ranks both
-                # move the same bytes per link and the plain peer accesses are faster (0.47 vs 0.56 ms), at 4 ranks
-                # multicast moves 2/3 of the bytes and wins (0.50 vs 0.53 ms), and the gap grows with n.
-                use_mc = exchange == "peer" or (exchange == "auto" and world_size >= 4)
+                # "peer_p2p" / "auto": per-peer loads and stores; "peer": NVLS multicast (multimem.ld_reduce / st) when
+                # the system has it.  Measured on B200 (profiles/r01_peer_exchange.txt): multicast moves fewer bytes per
+                # link from 4 ranks up, but the multimem accesses run at about half the link rate, so the plain peer
+                # accesses (latency hidden by 4 resident CTAs per SM) are the default at every rank count.
+                use_mc = exchange == "peer"
                 self._setup_peer(required=(exchange != "auto"), multicast=use_mc)
 
     def _setup_peer(self, required=False, multicast=True):
