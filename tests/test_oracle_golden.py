@@ -223,3 +223,44 @@ def test_oracle_matches_reference_cuda_kernels(golden_dir):
         assert ulp_diff(p.numpy(), g["adam_out_p_%s" % name]).max() <= 2, name
         assert ulp_diff(m.numpy(), g["adam_out_m_%s" % name]).max() <= 1, name
         assert ulp_diff(v.numpy(), g["adam_out_v_%s" % name]).max() <= 1, name
+
+
+# ---- rows N1-N3: the CPU restatement in oracle/prep_ref.py against the reference's own Python --------
+@pytest.fixture(scope="module")
+def prep_gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "refpy_prep.npz"))
+
+
+def test_prep_oracle_rays_of_a_view(prep_gold):
+    from oracle import prep_ref
+    g = prep_gold
+    H, W = (int(v) for v in g["view_HW"])
+    for k, (ndc, inverse_y, flip_x, flip_y, center) in enumerate(g["view_combos"]):
+        got = prep_ref.rays_of_view(H, W, g["view_K"], g["view_c2w"], bool(ndc), bool(inverse_y), bool(flip_x),
+                                    bool(flip_y), "center" if center else "lefttop")
+        for x, name in zip(got, "odv"):
+            ref = g["view%d_%s" % (k, name)]
+            np.testing.assert_allclose(x, ref, rtol=0, atol=2e-6 * np.abs(ref).max(), err_msg="combo %d %s" % (k, name))
+
+
+def test_prep_oracle_hit_count_refresh_resize(prep_gold):
+    from oracle import prep_ref
+    g = prep_gold
+    H, W = (int(v) for v in g["tr_HW"][0])
+    rk = dict(near=0.5, far=6.0, stepsize=0.5)
+    lo, hi = g["xyz_min"], g["xyz_max"]
+    shape = g["density0"].shape[2:]
+    voxel_size = float((np.prod(hi - lo) / 20 ** 3) ** (1 / 3))
+    ro, rd, _ = prep_ref.rays_of_view(H, W, g["tr_K"], g["tr_poses"][0])
+    hit = prep_ref.hit_coarse_geo(ro, rd, lo, hi, g["mask0"], rk["near"], rk["far"], rk["stepsize"] * voxel_size)
+    assert (hit == g["hit0"]).mean() >= 0.999      # rays differ from torch's in the last bit at most
+    views = [prep_ref.rays_of_view(H, W, g["tr_K"], p)[:2] for p in g["tr_poses"]]
+    cnt = prep_ref.voxel_count_views([v[0] for v in views], [v[1] for v in views], lo, hi, shape, rk["near"], rk["far"],
+                                     rk["stepsize"], voxel_size)
+    d = np.abs(cnt - g["count_views"])
+    assert d.max() <= 1 and (d == 0).mean() >= 0.999
+    m = prep_ref.alpha_maxpool_mask(g["density0"][0, 0], float(g["act_shift"]), 1.0, 1e-4, g["mask0"])
+    np.testing.assert_array_equal(m, g["mask_refreshed"])
+    size = tuple(int(v) for v in g["scaled_world_size"])
+    np.testing.assert_allclose(prep_ref.resize_trilinear(g["prescale_density"][0], size), g["scaled_density"][0], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(prep_ref.resize_trilinear(g["prescale_k0"][0], size), g["scaled_k0"][0], rtol=0, atol=1e-5)
