@@ -157,6 +157,22 @@ def test_triplane_vs_aten_grid_sample_2d(pkg):
     np.testing.assert_allclose(to_np(s), to_np(got[:1000, :C] + got[:1000, C:2 * C] + got[:1000, 2 * C:]), rtol=1e-6, atol=1e-6)
 
 
+def test_triplane_vs_reference_python_golden(pkg, golden_dir):
+    """Row a7 (2-D) against outputs of the reference's OWN `grid_sampler2D` (tests/golden/refpy_triplane.npz)."""
+    import os
+    from directvoxgo_b200.ops import grid_sample_triplane
+    g = np.load(os.path.join(golden_dir, "refpy_triplane.npz"))
+    lo, hi, xyz = (torch.tensor(g[k]).to(DEV) for k in ("xyz_min", "xyz_max", "xyz"))
+    go = torch.tensor(g["grad_out"]).to(DEV)
+    for agg in ("concat", "sum"):
+        planes = {k: torch.tensor(g["plane_" + k]).to(DEV).requires_grad_() for k in ("xy", "yz", "zx")}
+        out = grid_sample_triplane(planes, xyz, lo, hi, agg)
+        np.testing.assert_allclose(to_np(out), g["out_" + agg], rtol=2e-5, atol=4e-6)
+        (out * go[:, :out.shape[1]]).sum().backward()
+        for k in planes:
+            assert rel_to_max(to_np(planes[k].grad), g["grad_%s_%s" % (agg, k)]) < 1e-5, (agg, k)
+
+
 def test_training_step_vs_reference_kernels_full_size(pkg, ref_gpu):
     """BASELINE config 2 at full size (160^3, 12-ch k0, rgbnet 128, 8192 rays): the reference's op sequence
     (oracle/model_ref.py: lib/dvgo.py:450-577 + run.py:377-397) served by the REFERENCE'S OWN CUDA KERNELS

@@ -264,3 +264,24 @@ def test_prep_oracle_hit_count_refresh_resize(prep_gold):
     size = tuple(int(v) for v in g["scaled_world_size"])
     np.testing.assert_allclose(prep_ref.resize_trilinear(g["prescale_density"][0], size), g["scaled_density"][0], rtol=0, atol=1e-5)
     np.testing.assert_allclose(prep_ref.resize_trilinear(g["prescale_k0"][0], size), g["scaled_k0"][0], rtol=0, atol=1e-5)
+
+
+def test_oracle_triplane_matches_reference_python(golden_dir):
+    """Row a7 (2-D): the C oracle against outputs of the reference's OWN `grid_sampler2D` (lib/tri_dvgo.py:456-471,
+    recorded by oracle/make_golden_triplane.py), forward and grid gradients, both aggregations."""
+    g = np.load(os.path.join(golden_dir, "refpy_triplane.npz"))
+    lo, hi, xyz = (torch.tensor(g[k]) for k in ("xyz_min", "xyz_max", "xyz"))
+    axes = {"xy": (2, 1), "yz": (1, 0), "zx": (0, 2)}
+    planes = {k: torch.tensor(g["plane_" + k]) for k in axes}
+    feats = [orc.grid_sample_2d(planes[k], xyz, lo, hi, *axes[k]) for k in ("xy", "yz", "zx")]
+    np.testing.assert_allclose(torch.cat(feats, -1).numpy(), g["out_concat"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose((feats[0] + feats[1] + feats[2]).numpy(), g["out_sum"], rtol=2e-5, atol=4e-6)
+    go = torch.tensor(g["grad_out"])
+    C = planes["xy"].shape[1]
+    for i, k in enumerate(("xy", "yz", "zx")):
+        gg = torch.zeros_like(planes[k])
+        orc.grid_sample_2d_backward(go[:, i * C:(i + 1) * C].contiguous(), xyz, lo, hi, *axes[k], gg)
+        assert rel_to_max(gg.numpy(), g["grad_concat_" + k]) < 1e-5
+        gs = torch.zeros_like(planes[k])
+        orc.grid_sample_2d_backward(go[:, :C].contiguous(), xyz, lo, hi, *axes[k], gs)
+        assert rel_to_max(gs.numpy(), g["grad_sum_" + k]) < 1e-5
