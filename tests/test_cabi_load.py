@@ -128,3 +128,28 @@ def test_ray_sharding_helpers():
         assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
         assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
     assert sorted(sum((shard_views(10, r, 4) for r in range(4)), [])) == list(range(10))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's
+    keys; run here on a small grid so that it takes seconds."""
+    import json
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "24",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # under torchrun every rank but 0 exits without work
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    q = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "24"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert q.returncode == 0 and q.stdout.strip() == ""
