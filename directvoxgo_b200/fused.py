@@ -19,7 +19,6 @@ rgbnet modes
     'tc'     hand-written tcgen05 (TF32 tensor-core, fp32 accumulate) forward+backward kernels with
              in-TMEM weight-gradient accumulation; no host sync   [fused_mlp.cu]
 """
-import math
 
 import torch
 

@@ -2,8 +2,6 @@
 cfg 4 DirectMPIGO / LLFF shape, cfg 5 320^3 with 65 536 rays) on one B200, and check each against the op-by-op
 module path (drop-in ops + torch autograd) on the same inputs.  Usage: PYTHONPATH=. python tools/bench_configs.py"""
 import json
-import sys
-import time
 
 import numpy as np
 import torch
