@@ -247,7 +247,7 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     n_rays = 1024  # bounded sample of the 8192-ray step (same grid, same ops)
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 5))   # bounded: ~2 s per step on 16 host cores
     rays_s, dt = cpu_reference_run(args.grid, n_rays, steps, min(args.warmup, 1), threads)
     line = {"metric": METRIC, "value": rays_s, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -458,9 +458,9 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n_cpu = 1024
-        rays_s, dt = cpu_reference_run(args.grid, n_cpu, 2, 1, threads)
+        rays_s, dt = cpu_reference_run(args.grid, n_cpu, 4, 1, threads)
         cpu = {"value": rays_s, "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": "%d-ray slice of the 8192-ray step on the full %d^3 grid, 2 steps (oracle/model_ref.py: "
+               "sample": "%d-ray slice of the 8192-ray step on the full %d^3 grid, 4 steps (oracle/model_ref.py: "
                          "torch-CPU + C oracle; the reference's CUDA ops have no CPU path)" % (n_cpu, args.grid)}
 
     line = {
