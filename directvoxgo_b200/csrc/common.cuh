@@ -113,5 +113,21 @@ __device__ __forceinline__ Tri tri_setup(float px, float py, float pz,
   t.wz0 = fsub(z0f + 1.f, fz); t.wz1 = fsub(fz, z0f);
   return t;
 }
+// Same, for coordinates that are ALREADY normalised to [-1, 1] (the `grid` argument of F.grid_sample itself): only
+// ATen's align_corners=True un-normalisation ((n + 1) / 2) * (size - 1) is applied.
+__device__ __forceinline__ float unnorm_only(float n, int size) {
+  return fmul(fmul(fadd(n, 1.f), 0.5f), static_cast<float>(size - 1));
+}
+__device__ __forceinline__ Tri tri_from_index(float fx, float fy, float fz) {
+  Tri t;
+  const float x0f = floorf(fx), y0f = floorf(fy), z0f = floorf(fz);
+  t.x0 = static_cast<int>(x0f);
+  t.y0 = static_cast<int>(y0f);
+  t.z0 = static_cast<int>(z0f);
+  t.wx0 = fsub(x0f + 1.f, fx); t.wx1 = fsub(fx, x0f);
+  t.wy0 = fsub(y0f + 1.f, fy); t.wy1 = fsub(fy, y0f);
+  t.wz0 = fsub(z0f + 1.f, fz); t.wz1 = fsub(fz, z0f);
+  return t;
+}
 
 }  // namespace dvgo

@@ -246,6 +246,19 @@ void zero_(Tensor t) {
   rc_check(dvgo_fused_zero(t.data_ptr(), t.numel(), cur_stream()), "zero");
 }
 
+void step_begin(Tensor zblock, c10::optional<Tensor> stats) {
+  TORCH_CHECK(zblock.is_cuda() && zblock.is_contiguous() && zblock.element_size() == 4 && zblock.numel() >= 2,
+              "step_begin: 4-byte contiguous CUDA tensor with >= 2 words");
+  long long* st = nullptr;
+  if (stats.has_value()) {
+    TORCH_CHECK(stats->is_cuda() && stats->is_contiguous() && stats->scalar_type() == torch::kInt64 && stats->numel() >= 4,
+                "step_begin: stats must be an int64 CUDA tensor with 4 elements");
+    st = reinterpret_cast<long long*>(stats->data_ptr<int64_t>());
+  }
+  const c10::cuda::CUDAGuard guard(zblock.device());
+  rc_check(dvgo_fused_step_begin(zblock.data_ptr(), zblock.numel(), st, cur_stream()), "step_begin");
+}
+
 // ---- include/dvgo_b200_prep.h: ray generation, training-ray preparation, whole-grid sweeps -------------------
 struct View {
   dvgo_view_t v;
@@ -383,6 +396,7 @@ void dvgo_bind_fused(pybind11::module_& m) {
   m.def("ncdhw_to_cl", &ncdhw_to_cl);
   m.def("cl_to_ncdhw", &cl_to_ncdhw);
   m.def("zero_", &zero_);
+  m.def("step_begin", &step_begin);
   pybind11::class_<View>(m, "View")
       .def(pybind11::init<int, int, double, double, double, double, std::vector<double>, bool, bool, bool, int, bool,
                           double, double>());

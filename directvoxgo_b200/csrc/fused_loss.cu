@@ -52,7 +52,12 @@ __global__ void __launch_bounds__(256) composite_kernel(
     const bool valid = p < n;
     const int key = valid ? s_ray[p] : -1;
     const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = valid && (lane == 0 || key_prev != key);
+    const bool head_any = lane == 0 || key_prev != key;
+    const bool head = valid && head_any;
+    // Run identity, not key equality: chunks of one ray get their stream positions from an atomicAdd in
+    // march_fwd, so a window may read A.. B.. A.. and the two A runs must stay separate partial sums.
+    const unsigned heads = __ballot_sync(0xffffffffu, head_any);
+    const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (valid) {
       const float w = s_weight[p];
@@ -61,8 +66,8 @@ __global__ void __launch_bounds__(256) composite_kernel(
     }
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int kd = __shfl_down_sync(0xffffffffu, key, off);
-      const bool take = (lane + off < 32) && (kd == key);
+      const int sd = __shfl_down_sync(0xffffffffu, seg, off);
+      const bool take = (lane + off < 32) && (sd == seg);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float vd = __shfl_down_sync(0xffffffffu, v[c], off);
@@ -176,6 +181,28 @@ __global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ 
     p[i] = 0u;
 }
 
+// Start of a fused step: fold the previous call's counters into the running statistics, then zero the block.
+// zblock = counters[2] (survivor count, overflow flag) | accumulators...; stats (int64): [0] += survivors of the
+// previous call, [1] += 1 (calls), [2] |= overflow flag, [3] = max survivors of a call.  No host synchronisation:
+// the host reads `stats` only where it synchronises anyway (bench roofline, sync_to_model, checkpoints).
+__global__ void __launch_bounds__(256) step_begin_kernel(uint32_t* __restrict__ z, int64_t n,
+                                                         long long* __restrict__ stats) {
+  const int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i0 == 0) {   // words 0 and 1 (the counters) belong to thread 0 alone: read, fold, then zero, in program order
+    if (stats) {
+      const long long surv = static_cast<int32_t>(z[0]);
+      stats[0] += surv;
+      stats[1] += 1;
+      stats[2] |= static_cast<long long>(z[1]);   // bit 0: capacity overflow, bit 1: non-finite rgbnet value
+      if (surv > stats[3]) stats[3] = surv;
+    }
+    z[0] = 0u;
+    z[1] = 0u;
+  }
+  for (int64_t i = i0; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (i >= 2) z[i] = 0u;
+}
+
 // Survivor-stream kernels size their grid for the capacity (the count lives on the device).
 static inline int stream_grid(int64_t cap, int threads) {
   const int64_t want = (cap + threads - 1) / threads;
@@ -274,6 +301,13 @@ DVGO_API int dvgo_fused_zero(void* ptr, int64_t n_words, dvgo_stream_t stream) {
   if (!ptr) return DVGO_EINVAL;
   zero_words_kernel<<<stream_grid(n_words, 256), 256, 0, as_stream(stream)>>>(
       static_cast<uint32_t*>(ptr), n_words);
+  return launch_status();
+}
+
+DVGO_API int dvgo_fused_step_begin(void* zblock, int64_t n_words, long long* stats, dvgo_stream_t stream) {
+  if (n_words < 2 || !zblock) return DVGO_EINVAL;
+  step_begin_kernel<<<stream_grid(n_words, 256), 256, 0, as_stream(stream)>>>(static_cast<uint32_t*>(zblock), n_words,
+                                                                              stats);
   return launch_status();
 }
 

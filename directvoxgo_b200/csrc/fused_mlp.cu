@@ -38,10 +38,22 @@ struct MlpG {            // fp32 gradient accumulators, same shapes
   float* W1; float* b1; float* W2; float* b2; float* W3; float* b3;
 };
 
+// fp32 pair -> packed fp16 pair, round-to-nearest, SATURATING to +-65504 (one F2FP.SATFINITE instruction): a
+// feature / activation / scaled gradient beyond FP16's range clamps instead of becoming inf and poisoning the
+// training state through Adam (the reference's fp32 nn.Linear has no such range limit).  NaN stays NaN and is
+// reported through the status word (counters[1] bit 1).
+__device__ __forceinline__ __half2 pack2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ __half half_sat(float x) {
+  return __low2half(pack2_sat(x, 0.f));
+}
 __device__ __forceinline__ uint4 pack8(const float* v) {
   __half2 h[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+  for (int q = 0; q < 4; ++q) h[q] = pack2_sat(v[2 * q], v[2 * q + 1]);
   return *reinterpret_cast<uint4*>(h);
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
@@ -55,7 +67,7 @@ __device__ __forceinline__ uint4 pack8_relu(const float* v) {
   __half2 h[4];
   const __half2 z = __float2half2_rn(0.f);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) h[q] = __hmax2(__floats2half2_rn(v[2 * q], v[2 * q + 1]), z);
+  for (int q = 0; q < 4; ++q) h[q] = __hmax2(pack2_sat(v[2 * q], v[2 * q + 1]), z);
   return *reinterpret_cast<uint4*>(h);
 }
 // out = (act > 0) ? v : 0 on packed halves: HSET2.GT gives 1.0/0.0, one HMUL2 applies the mask
@@ -64,7 +76,7 @@ __device__ __forceinline__ uint4 pack8_masked(const float* v, const uint4& act) 
   const __half2* a = reinterpret_cast<const __half2*>(&act);
   const __half2 z = __float2half2_rn(0.f);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) h[q] = __hmul2(__floats2half2_rn(v[2 * q], v[2 * q + 1]), __hgt2(a[q], z));
+  for (int q = 0; q < 4; ++q) h[q] = __hmul2(pack2_sat(v[2 * q], v[2 * q + 1]), __hgt2(a[q], z));
   return *reinterpret_cast<uint4*>(h);
 }
 
@@ -75,12 +87,12 @@ __device__ void load_weights(const MlpW& w, int d_in, int K1, uint8_t* sW1, uint
   for (int i = threadIdx.x; i < kHid * K1; i += blockDim.x) {
     const int n = i / K1, c = i % K1;
     const float v = c < d_in ? w.W1[n * d_in + c] : (c == d_in ? w.b1[n] : 0.f);
-    *reinterpret_cast<__half*>(sW1 + tile_off(n, c, K1)) = __float2half_rn(v);
+    *reinterpret_cast<__half*>(sW1 + tile_off(n, c, K1)) = half_sat(v);
   }
   for (int i = threadIdx.x; i < kHid * w2_cols; i += blockDim.x) {  // w2_cols = 144: column 128 holds b2
     const int n = i / w2_cols, c = i % w2_cols;
     const float v = c < kHid ? w.W2[n * kHid + c] : (c == kHid ? w.b2[n] : 0.f);
-    *reinterpret_cast<__half*>(sW2 + tile_off(n, c, w2_cols)) = __float2half_rn(v);
+    *reinterpret_cast<__half*>(sW2 + tile_off(n, c, w2_cols)) = half_sat(v);
   }
   for (int i = threadIdx.x; i < 3 * kHid; i += blockDim.x) sW3[i] = w.W3[i];
   for (int i = threadIdx.x; i < kHid; i += blockDim.x) sB2[i] = w.b2[i];
@@ -249,7 +261,7 @@ __device__ __forceinline__ size_t align1k(size_t x) { return (x + 1023) & ~stati
 // ---- forward ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride, float* __restrict__ rgb,
+    int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride, float* __restrict__ rgb,
     long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
@@ -366,6 +378,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
       o[0] = 1.f / (1.f + expf(-z0));
       o[1] = 1.f / (1.f + expf(-z1));
       o[2] = 1.f / (1.f + expf(-z2));
+      if (!(fabsf(z0) + fabsf(z1) + fabsf(z2) < 3.0e38f)) counters[1] = counters[1] | 2;  // NaN / inf logit (benign race: every writer sets bit 1)
     }
     stamp();
     // sPart is rewritten by the next tile only after two more CTA-wide barriers
@@ -412,7 +425,7 @@ struct TileCtx {
 
 __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    const int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride,
+    int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride,
     const float* __restrict__ rgb, const float* __restrict__ d_rgb, float grad_scale, float* __restrict__ d_feat,
     MlpG g, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
@@ -450,7 +463,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3, kHidA);
   for (int i = tid; i < kTile * 16; i += blockDim.x) {
     const int j = i / 16, c = i % 16;
-    *reinterpret_cast<__half*>(sW3t + tile_off(j, c, 16)) = __float2half_rn(c < 3 ? w.W3[c * kHid + j] : 0.f);
+    *reinterpret_cast<__half*>(sW3t + tile_off(j, c, 16)) = half_sat(c < 3 ? w.W3[c * kHid + j] : 0.f);
     // columns 128..143 of both H1 tiles: the constant 1 (b2 rides the layer-2 GEMM, db2 the dW2 GEMM), then 0;
     // the epilogues only ever write columns < 128
     for (int cx_i = 0; cx_i < 2; ++cx_i) {
@@ -569,6 +582,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       tmem_ld16(c.tWork + lane_sel, v);
       tmem_ld_wait();
       if (c.valid) {
+        float chk = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) chk += fabsf(v[k]);
+        if (!(chk < 3.0e38f)) counters[1] = counters[1] | 2;   // NaN / inf feature gradient
         float* __restrict__ o = d_feat + (c.s0 + row) * C;
         if ((C & 3) == 0) {   // static register indexing + 16-byte stores (a runtime-indexed loop spills v[])
 #pragma unroll
@@ -937,12 +954,12 @@ DVGO_API int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, i
 
 static inline int mlp_k1(int C, int pe_stride) { return ((C + pe_stride + 15) / 16) * 16; }
 
-DVGO_API int dvgo_mlp_fwd_timed(const float*, int, const int32_t*, const float*, int, int, const int32_t*, int64_t, const float*,
+DVGO_API int dvgo_mlp_fwd_timed(const float*, int, const int32_t*, const float*, int, int, int32_t*, int64_t, const float*,
                                 const float*, const float*, const float*, const float*, const float*, int, float*, long long*,
                                 dvgo_stream_t);
 
 DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                          const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
+                          int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                           const float* W2, const float* b2, const float* W3, const float* b3, int width, float* rgb,
                           dvgo_stream_t stream) {
   return dvgo_mlp_fwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, W1, b1, W2, b2, W3, b3, width, rgb,
@@ -950,7 +967,7 @@ DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const 
 }
 
 DVGO_API int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                                const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
+                                int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                                 const float* W2, const float* b2, const float* W3, const float* b3, int width,
                                 float* rgb, long long* timeline, dvgo_stream_t stream) {
   if (width != kHid || C < 0 || P < 0 || C + P < 1 || C + P > 63 || surv_cap < 0 || pe_stride < P + 1) return DVGO_EINVAL;
@@ -969,13 +986,13 @@ DVGO_API int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, 
   return launch_status();
 }
 
-DVGO_API int dvgo_mlp_bwd_timed(const float*, int, const int32_t*, const float*, int, int, const int32_t*, int64_t, const float*,
+DVGO_API int dvgo_mlp_bwd_timed(const float*, int, const int32_t*, const float*, int, int, int32_t*, int64_t, const float*,
                                 const float*, const float*, const float*, const float*, const float*, int, const float*,
                                 const float*, float, float*, float*, float*, float*, float*, float*, float*, long long*,
                                 dvgo_stream_t);
 
 DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                          const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
+                          int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                           const float* W2, const float* b2, const float* W3, const float* b3, int width,
                           const float* rgb, const float* d_rgb, float grad_scale, float* d_feat, float* gW1,
                           float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, dvgo_stream_t stream) {
@@ -984,7 +1001,7 @@ DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const 
 }
 
 DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                                const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
+                                int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                                 const float* W2, const float* b2, const float* W3, const float* b3, int width,
                                 const float* rgb, const float* d_rgb, float grad_scale, float* d_feat, float* gW1,
                                 float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, long long* timeline,

@@ -34,6 +34,16 @@ __device__ __forceinline__ Corners corners_of(const Tri& t, int X, int Y, int Z)
   return c;
 }
 
+// NORM: `xyz` holds F.grid_sample's own normalised (w, h, d) = (z, y, x) coordinates instead of world points.
+template <bool NORM>
+__device__ __forceinline__ Tri tri_of(const float* __restrict__ xyz, int64_t p, const float* __restrict__ lo,
+                                      const float* __restrict__ hi, int X, int Y, int Z) {
+  if (NORM)
+    return tri_from_index(unnorm_only(xyz[3 * p + 2], X), unnorm_only(xyz[3 * p + 1], Y), unnorm_only(xyz[3 * p], Z));
+  return tri_setup(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], lo, hi, X, Y, Z);
+}
+
+template <bool NORM>
 __global__ void __launch_bounds__(256) grid_sample_3d_kernel(
     const float* __restrict__ grid, int C, int X, int Y, int Z, const float* __restrict__ xyz,
     const float* __restrict__ xyz_min, const float* __restrict__ xyz_max, int64_t n_pts,
@@ -41,7 +51,7 @@ __global__ void __launch_bounds__(256) grid_sample_3d_kernel(
   const int64_t plane = static_cast<int64_t>(X) * Y * Z;
   for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n_pts;
        p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const Tri t = tri_setup(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], xyz_min, xyz_max, X, Y, Z);
+    const Tri t = tri_of<NORM>(xyz, p, xyz_min, xyz_max, X, Y, Z);
     const Corners cn = corners_of(t, X, Y, Z);
     for (int c = 0; c < C; ++c) {
       const float* __restrict__ g = grid + c * plane;
@@ -57,6 +67,7 @@ __global__ void __launch_bounds__(256) grid_sample_3d_kernel(
   }
 }
 
+template <bool NORM>
 __global__ void __launch_bounds__(256) grid_sample_3d_backward_kernel(
     const float* __restrict__ grad_out, int C, int X, int Y, int Z, const float* __restrict__ xyz,
     const float* __restrict__ xyz_min, const float* __restrict__ xyz_max, int64_t n_pts,
@@ -64,7 +75,7 @@ __global__ void __launch_bounds__(256) grid_sample_3d_backward_kernel(
   const int64_t plane = static_cast<int64_t>(X) * Y * Z;
   for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n_pts;
        p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const Tri t = tri_setup(xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], xyz_min, xyz_max, X, Y, Z);
+    const Tri t = tri_of<NORM>(xyz, p, xyz_min, xyz_max, X, Y, Z);
     const Corners cn = corners_of(t, X, Y, Z);
     for (int c = 0; c < C; ++c) {
       const float g = grad_out[p * C + c];
@@ -91,14 +102,19 @@ __global__ void __launch_bounds__(256) segment_coo_sum_kernel(const float* __res
     const bool valid = p < n_pts;
     const int64_t key = valid ? index[p] : -1;
     const int64_t key_prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = valid && (lane == 0 || key_prev != key);
+    const bool head_any = lane == 0 || key_prev != key;
+    const bool head = valid && head_any;
+    // runs are identified by position (ballot of run heads), not by key equality at a shuffle distance, so an
+    // unsorted index (A.. B.. A..) degrades to more atomics instead of double-counting
+    const unsigned heads = __ballot_sync(0xffffffffu, head_any);
+    const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
     for (int d = 0; d < D; ++d) {
       float v = valid ? src[p * D + d] : 0.f;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const float vd = __shfl_down_sync(0xffffffffu, v, off);
-        const int64_t kd = __shfl_down_sync(0xffffffffu, key, off);
-        if (lane + off < 32 && kd == key) v += vd;
+        const int sd = __shfl_down_sync(0xffffffffu, seg, off);
+        if (lane + off < 32 && sd == seg) v += vd;
       }
       if (head) atomicAdd(out + key * D + d, v);
     }
@@ -126,10 +142,11 @@ static inline int grid_for(int64_t n, int threads) {
 
 // ---- 2-D tri-plane sampling (lib/tri_dvgo.py:456-464): ATen grid_sampler_2d, bilinear, align_corners, zero pad --
 struct Bil { int x0, y0; float w[4]; };   // corner order nw, ne, sw, se as ATen accumulates them
+template <bool NORM>   // NORM: p3 -> this point's (w, h) pair of F.grid_sample's own normalised coordinates
 __device__ __forceinline__ Bil bil_setup(const float* __restrict__ p3, const float* __restrict__ lo,
                                          const float* __restrict__ hi, int axis_w, int axis_h, int W, int H) {
-  const float ix = unnorm_coord(p3[axis_w], lo[axis_w], hi[axis_w], W);
-  const float iy = unnorm_coord(p3[axis_h], lo[axis_h], hi[axis_h], H);
+  const float ix = NORM ? unnorm_only(p3[0], W) : unnorm_coord(p3[axis_w], lo[axis_w], hi[axis_w], W);
+  const float iy = NORM ? unnorm_only(p3[1], H) : unnorm_coord(p3[axis_h], lo[axis_h], hi[axis_h], H);
   const float x0f = floorf(ix), y0f = floorf(iy);
   Bil b;
   b.x0 = static_cast<int>(x0f);
@@ -143,6 +160,7 @@ __device__ __forceinline__ Bil bil_setup(const float* __restrict__ p3, const flo
   return b;
 }
 
+template <bool NORM>
 __global__ void __launch_bounds__(256) grid_sample_2d_kernel(
     const float* __restrict__ plane, int C, int H, int W, const float* __restrict__ xyz,
     const float* __restrict__ xyz_min, const float* __restrict__ xyz_max, int axis_w, int axis_h, int64_t n_pts,
@@ -150,7 +168,7 @@ __global__ void __launch_bounds__(256) grid_sample_2d_kernel(
   const int64_t hw = static_cast<int64_t>(H) * W;
   for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n_pts;
        p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const Bil b = bil_setup(xyz + 3 * p, xyz_min, xyz_max, axis_w, axis_h, W, H);
+    const Bil b = bil_setup<NORM>(xyz + (NORM ? 2 : 3) * p, xyz_min, xyz_max, axis_w, axis_h, W, H);
     int64_t off[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -168,6 +186,7 @@ __global__ void __launch_bounds__(256) grid_sample_2d_kernel(
   }
 }
 
+template <bool NORM>
 __global__ void __launch_bounds__(256) grid_sample_2d_backward_kernel(
     const float* __restrict__ grad_out, int C, int H, int W, const float* __restrict__ xyz,
     const float* __restrict__ xyz_min, const float* __restrict__ xyz_max, int axis_w, int axis_h, int64_t n_pts,
@@ -175,7 +194,7 @@ __global__ void __launch_bounds__(256) grid_sample_2d_backward_kernel(
   const int64_t hw = static_cast<int64_t>(H) * W;
   for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n_pts;
        p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const Bil b = bil_setup(xyz + 3 * p, xyz_min, xyz_max, axis_w, axis_h, W, H);
+    const Bil b = bil_setup<NORM>(xyz + (NORM ? 2 : 3) * p, xyz_min, xyz_max, axis_w, axis_h, W, H);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int x = b.x0 + (k & 1), y = b.y0 + (k >> 1);
@@ -196,8 +215,29 @@ DVGO_API int dvgo_grid_sample_3d(const float* grid, int C, int X, int Y, int Z, 
   if (n_pts < 0 || C < 0 || X <= 0 || Y <= 0 || Z <= 0) return DVGO_EINVAL;
   if (n_pts == 0 || C == 0) return 0;
   if (!grid || !xyz || !xyz_min || !xyz_max || !out) return DVGO_EINVAL;
-  grid_sample_3d_kernel<<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
+  grid_sample_3d_kernel<false><<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
       grid, C, X, Y, Z, xyz, xyz_min, xyz_max, n_pts, out);
+  return launch_status();
+}
+
+DVGO_API int dvgo_grid_sample_3d_norm(const float* grid, int C, int X, int Y, int Z, const float* ind_norm,
+                                      int64_t n_pts, float* out, dvgo_stream_t stream) {
+  if (n_pts < 0 || C < 0 || X <= 0 || Y <= 0 || Z <= 0) return DVGO_EINVAL;
+  if (n_pts == 0 || C == 0) return 0;
+  if (!grid || !ind_norm || !out) return DVGO_EINVAL;
+  grid_sample_3d_kernel<true><<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
+      grid, C, X, Y, Z, ind_norm, nullptr, nullptr, n_pts, out);
+  return launch_status();
+}
+
+DVGO_API int dvgo_grid_sample_3d_norm_backward(const float* grad_out, int C, int X, int Y, int Z,
+                                               const float* ind_norm, int64_t n_pts, float* grad_grid,
+                                               dvgo_stream_t stream) {
+  if (n_pts < 0 || C < 0 || X <= 0 || Y <= 0 || Z <= 0) return DVGO_EINVAL;
+  if (n_pts == 0 || C == 0) return 0;
+  if (!grad_out || !ind_norm || !grad_grid) return DVGO_EINVAL;
+  grid_sample_3d_backward_kernel<true><<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
+      grad_out, C, X, Y, Z, ind_norm, nullptr, nullptr, n_pts, grad_grid);
   return launch_status();
 }
 
@@ -208,7 +248,7 @@ DVGO_API int dvgo_grid_sample_3d_backward(const float* grad_out, int C, int X, i
   if (n_pts < 0 || C < 0 || X <= 0 || Y <= 0 || Z <= 0) return DVGO_EINVAL;
   if (n_pts == 0 || C == 0) return 0;
   if (!grad_out || !xyz || !xyz_min || !xyz_max || !grad_grid) return DVGO_EINVAL;
-  grid_sample_3d_backward_kernel<<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
+  grid_sample_3d_backward_kernel<false><<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
       grad_out, C, X, Y, Z, xyz, xyz_min, xyz_max, n_pts, grad_grid);
   return launch_status();
 }
@@ -239,8 +279,28 @@ DVGO_API int dvgo_grid_sample_2d(const float* plane, int C, int H, int W, const 
   if (C <= 0 || H <= 0 || W <= 0 || n_pts < 0 || axis_w < 0 || axis_w > 2 || axis_h < 0 || axis_h > 2) return DVGO_EINVAL;
   if (n_pts == 0) return 0;
   if (!plane || !xyz || !xyz_min || !xyz_max || !out) return DVGO_EINVAL;
-  grid_sample_2d_kernel<<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(plane, C, H, W, xyz, xyz_min, xyz_max,
-                                                                             axis_w, axis_h, n_pts, out);
+  grid_sample_2d_kernel<false><<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(plane, C, H, W, xyz, xyz_min,
+                                                                                    xyz_max, axis_w, axis_h, n_pts, out);
+  return launch_status();
+}
+
+DVGO_API int dvgo_grid_sample_2d_norm(const float* plane, int C, int H, int W, const float* ind_norm, int64_t n_pts,
+                                      float* out, dvgo_stream_t stream) {
+  if (C <= 0 || H <= 0 || W <= 0 || n_pts < 0) return DVGO_EINVAL;
+  if (n_pts == 0) return 0;
+  if (!plane || !ind_norm || !out) return DVGO_EINVAL;
+  grid_sample_2d_kernel<true><<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(plane, C, H, W, ind_norm, nullptr,
+                                                                                   nullptr, 0, 1, n_pts, out);
+  return launch_status();
+}
+
+DVGO_API int dvgo_grid_sample_2d_norm_backward(const float* grad_out, int C, int H, int W, const float* ind_norm,
+                                               int64_t n_pts, float* grad_plane, dvgo_stream_t stream) {
+  if (C <= 0 || H <= 0 || W <= 0 || n_pts < 0) return DVGO_EINVAL;
+  if (n_pts == 0) return 0;
+  if (!grad_out || !ind_norm || !grad_plane) return DVGO_EINVAL;
+  grid_sample_2d_backward_kernel<true><<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
+      grad_out, C, H, W, ind_norm, nullptr, nullptr, 0, 1, n_pts, grad_plane);
   return launch_status();
 }
 
@@ -250,7 +310,7 @@ DVGO_API int dvgo_grid_sample_2d_backward(const float* grad_out, int C, int H, i
   if (C <= 0 || H <= 0 || W <= 0 || n_pts < 0 || axis_w < 0 || axis_w > 2 || axis_h < 0 || axis_h > 2) return DVGO_EINVAL;
   if (n_pts == 0) return 0;
   if (!grad_out || !xyz || !xyz_min || !xyz_max || !grad_plane) return DVGO_EINVAL;
-  grid_sample_2d_backward_kernel<<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
+  grid_sample_2d_backward_kernel<false><<<grid_for(n_pts, 256), 256, 0, as_stream(stream)>>>(
       grad_out, C, H, W, xyz, xyz_min, xyz_max, axis_w, axis_h, n_pts, grad_plane);
   return launch_status();
 }

@@ -319,6 +319,43 @@ void grid_sample_2d_backward(Tensor grad_out, Tensor xyz, Tensor xyz_min, Tensor
            "grid_sample_2d_backward");
 }
 
+// F.grid_sample's own signature pieces: input [1,C,D,H,W] or [1,C,H,W]; pts [P,3] / [P,2] normalised coordinates -> [P,C]
+Tensor grid_sample_norm(Tensor input, Tensor pts) {
+  CHECK_INPUT(input); CHECK_INPUT(pts); CHECK_F32(input); CHECK_F32(pts);
+  const int nd = input.dim() - 2;
+  TORCH_CHECK((nd == 2 || nd == 3) && input.size(0) == 1, "input must be [1,C,H,W] or [1,C,D,H,W]");
+  TORCH_CHECK(pts.dim() == 2 && pts.size(1) == nd, "pts must be [P,2] or [P,3]");
+  const c10::cuda::CUDAGuard guard(input.device());
+  const int C = input.size(1);
+  auto out = torch::empty({pts.size(0), C}, pts.options());
+  if (nd == 3)
+    check_rc(dvgo_grid_sample_3d_norm(fp(input), C, input.size(2), input.size(3), input.size(4), fp(pts), pts.size(0),
+                                      fpm(out), cur_stream()), "grid_sample_3d_norm");
+  else
+    check_rc(dvgo_grid_sample_2d_norm(fp(input), C, input.size(2), input.size(3), fp(pts), pts.size(0), fpm(out),
+                                      cur_stream()), "grid_sample_2d_norm");
+  return out;
+}
+
+void grid_sample_norm_backward(Tensor grad_out, Tensor pts, Tensor grad_input) {
+  CHECK_INPUT(grad_out); CHECK_INPUT(pts); CHECK_INPUT(grad_input);
+  CHECK_F32(grad_out); CHECK_F32(pts); CHECK_F32(grad_input);
+  const int nd = grad_input.dim() - 2;
+  TORCH_CHECK((nd == 2 || nd == 3) && grad_input.size(0) == 1, "grad_input must be [1,C,H,W] or [1,C,D,H,W]");
+  const int C = grad_input.size(1);
+  TORCH_CHECK(pts.dim() == 2 && pts.size(1) == nd && grad_out.dim() == 2 && grad_out.size(0) == pts.size(0) &&
+              grad_out.size(1) == C, "grad_out must be [P,C], pts [P,nd]");
+  const c10::cuda::CUDAGuard guard(grad_input.device());
+  if (nd == 3)
+    check_rc(dvgo_grid_sample_3d_norm_backward(fp(grad_out), C, grad_input.size(2), grad_input.size(3), grad_input.size(4),
+                                               fp(pts), pts.size(0), fpm(grad_input), cur_stream()),
+             "grid_sample_3d_norm_backward");
+  else
+    check_rc(dvgo_grid_sample_2d_norm_backward(fp(grad_out), C, grad_input.size(2), grad_input.size(3), fp(pts),
+                                               pts.size(0), fpm(grad_input), cur_stream()),
+             "grid_sample_2d_norm_backward");
+}
+
 // out[index[p], :] += src[p, :]   (src [P] or [P,D]; index sorted; out [N] or [N,D], in place)
 void segment_coo_sum(Tensor src, Tensor index, Tensor out) {
   CHECK_INPUT(src); CHECK_INPUT(index); CHECK_INPUT(out);
@@ -384,6 +421,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   ext.def("grid_sample_3d_backward", &grid_sample_3d_backward);
   ext.def("grid_sample_2d", &grid_sample_2d);
   ext.def("grid_sample_2d_backward", &grid_sample_2d_backward);
+  ext.def("grid_sample_norm", &grid_sample_norm);
+  ext.def("grid_sample_norm_backward", &grid_sample_norm_backward);
   ext.def("segment_coo_sum", &segment_coo_sum);
   ext.def("gather_rows", &gather_rows);
   dvgo_bind_fused(ext);

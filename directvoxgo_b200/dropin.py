@@ -20,11 +20,20 @@ _NAMES = ("render_utils_cuda", "total_variation_cuda", "adam_upd_cuda")
 _installed = False
 
 
-def install(modules=None):
+def install(modules=None, grid_sample=False):
     """`modules`: optional {name: module} override (the test-suite injects the CPU oracle here to run
-    the reference's Python orchestration on a GPU-less box; the product never does)."""
+    the reference's Python orchestration on a GPU-less box; the product never does).
+    `grid_sample=True` additionally routes `torch.nn.functional.grid_sample` -- which the reference calls by
+    name for DenseGrid sampling (lib/dvgo.py:321, lib/dmpigo.py:169) and tri-plane sampling
+    (lib/tri_dvgo.py:462-464) -- to `dvgo_grid_sample_3d_norm / _2d_norm` for the call shapes the reference
+    uses; any other call still reaches ATen."""
     global _installed
     import torch.utils.cpp_extension as cpp_ext
+    if grid_sample:
+        import torch.nn.functional as F
+        from .ops import make_grid_sample
+        if not hasattr(F.grid_sample, "_dvgo_real"):
+            F.grid_sample = make_grid_sample(F.grid_sample)
 
     if modules is None:
         import directvoxgo_b200 as pkg
@@ -52,6 +61,9 @@ def uninstall():
     real = getattr(cpp_ext.load, "_dvgo_real_load", None)
     if real is not None:
         cpp_ext.load = real
+    import torch.nn.functional as F
+    if hasattr(F.grid_sample, "_dvgo_real"):
+        F.grid_sample = F.grid_sample._dvgo_real
     mod = sys.modules.get("torch_scatter")
     if mod is not None and getattr(mod, "__name__", "").startswith("directvoxgo_b200"):
         del sys.modules["torch_scatter"]

@@ -80,6 +80,9 @@ def view_embedding(viewdirs, viewfreq):
     return torch.cat([viewdirs, emb.sin(), emb.cos()], -1)
 
 
+SUPPORTED_C = (3, 4, 6, 8, 9, 12, 16)   # k0 channel counts the fused kernels are instantiated for (DVGO_DISPATCH_C)
+
+
 class _FusedBase:
     def __init__(self, model, render_kwargs, mlp="auto"):
         self.model = model
@@ -90,6 +93,10 @@ class _FusedBase:
         self.scene = _scene_of(model, self.rk, self.ndc, ndc_samples)
         self.X, self.Y, self.Z = (int(s) for s in model.density.shape[2:])
         self.C = int(model.k0.shape[1])
+        if self.C not in SUPPORTED_C:
+            raise NotImplementedError(
+                "fused path: k0 with %d channels (rgbnet_dim) is not instantiated; supported: %s -- use the op-by-op "
+                "module path (directvoxgo_b200.dvgo.DirectVoxGO) for other widths" % (self.C, SUPPORTED_C))
         if mlp == "auto":
             mlp = "tc" if (model.rgbnet is not None and hasattr(ext, "mlp_fwd") and self._tc_supported(model)) else "torch"
         if mlp == "tc" and not hasattr(ext, "mlp_fwd"):
@@ -102,6 +109,10 @@ class _FusedBase:
         self.density = model.density.detach().reshape(self.X, self.Y, self.Z).contiguous().clone()
         self.k0 = ext.ncdhw_to_cl(model.k0.detach().contiguous())
         self._ws = {}
+        # device-side running statistics, folded in by step_begin (no host sync): [sum survivors, calls,
+        # status bits (1 = a capacity was too small, 2 = non-finite rgbnet value), max survivors of a call]
+        self.stats = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self._last_ws = None
 
     def _viewfreq(self):
         vf = getattr(self.model, "viewfreq", None)     # DirectMPIGO with viewbase_pe=0 has an empty table
@@ -119,8 +130,42 @@ class _FusedBase:
             self._ws[key] = _Workspace(self.scene, n_rays, self.C, self.device, train)
         return self._ws[key]
 
+    def stats_snapshot(self, reset=False):
+        """(survivors summed over the completed calls, number of calls, status bits, max survivors) -- one host read.
+        Includes the call whose counters have not been folded in yet.  Raises on a non-zero status."""
+        st = [int(v) for v in self.stats.tolist()]
+        if self._last_ws is not None:
+            c = [int(v) for v in self._last_ws.counters.tolist()]
+            st = [st[0] + c[0], st[1] + 1, st[2] | c[1], max(st[3], c[0])]
+            if reset:
+                self._last_ws.counters.zero_()
+                self._last_ws = None
+        if reset:
+            self.stats.zero_()
+        self._raise_on_status(st[2])
+        return tuple(st)
+
+    @staticmethod
+    def _raise_on_status(bits):
+        if bits & 1:
+            raise RuntimeError("fused path: a sample / survivor capacity was too small and samples were dropped "
+                               "(near / far / stepsize changed after the workspace was sized?)")
+        if bits & 2:
+            raise FloatingPointError("fused path: non-finite value in the tensor-core rgbnet (NaN input, or weights / "
+                                     "features far outside FP16 range); use mlp='torch' for the exact fp32 rgbnet")
+
+    def check_status(self):
+        """Host check of the device status bits; call where the host synchronises anyway."""
+        self.stats_snapshot()
+
     def _march(self, ws, rays_o, rays_d):
-        ext.zero_(ws.zblock)
+        ext.step_begin(ws.zblock, self.stats if self._last_ws is ws else None)
+        if self._last_ws is not None and self._last_ws is not ws:   # switching workspaces: fold the other one in now
+            c = self._last_ws.counters
+            self.stats[0] += c[0]; self.stats[1] += 1; self.stats[2] |= c[1].long()
+            self.stats[3] = torch.maximum(self.stats[3], c[0].long())
+            c.zero_()
+        self._last_ws = ws
         ext.ray_setup(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off)
         # density march (scan-bound, per ray) then the k0 gather over the compacted stream (fully parallel)
         ext.march_fwd(self.scene, rays_o, rays_d, self.density, None if self.split_k0 else self.k0, ws.t_min,
@@ -145,9 +190,32 @@ class _FusedBase:
 
     @torch.no_grad()
     def sync_to_model(self):
+        """Write the trainer-owned parameters back into the reference-layout module ([1,C,X,Y,Z]).  OWNERSHIP: between
+        construction and this call the trainer's buffers are the truth and `model.density / model.k0` are stale;
+        model-side edits made in between are NOT seen by the trainer (use `sync_from_model()` after them)."""
+        self.check_status()
         self.model.density.data.copy_(self.density.reshape(self.model.density.shape))
         self.model.k0.data.copy_(ext.cl_to_ncdhw(self.k0))
         return self.model
+
+    @torch.no_grad()
+    def sync_from_model(self):
+        """Re-read density / k0 (and the tensor-core rgbnet copy) from the module after a model-side edit
+        (maskout_near_cam_vox, density.data.sub_(1), load_state_dict ...).  Grid shapes must be unchanged."""
+        self.density.copy_(self.model.density.detach().reshape(self.X, self.Y, self.Z))
+        self.k0.copy_(ext.ncdhw_to_cl(self.model.k0.detach().contiguous()))
+        if getattr(self, "_tc", None) is not None:
+            self._tc.refresh_from_module()
+
+    @torch.no_grad()
+    def update_occupancy_cache(self):
+        """The periodic occupancy refresh of the training loop (run.py:330-332) on the TRAINER's live density
+        (the module's copy is stale during fused training): mask &= maxpool3(alpha(density)) > fast_color_thres,
+        in place in the mask tensor the fused kernels already read."""
+        m = self.model.mask_cache.mask
+        assert tuple(m.shape) == (self.X, self.Y, self.Z), "the refresh needs the mask at the density resolution"
+        m.copy_(ext.alpha_maxpool_mask(self.density.reshape(1, 1, self.X, self.Y, self.Z), float(self.model.act_shift),
+                                       float(self.model.voxel_size_ratio), float(self.model.fast_color_thres), m))
 
 
 class FusedRenderer(_FusedBase):
@@ -171,6 +239,8 @@ class FusedRenderer(_FusedBase):
         ext.composite(ws.rgb, ws.s_weight, ws.s_ray, ws.s_slot, ws.ray_off, ws.counters, ws.rgb_acc,
                       ws.depth_acc if render_depth else None)
         ext.ray_finish(ws.rgb_acc, ws.alphainv_last, None, float(self.rk["bg"]), n, n, 1.0, 0.0, None, None, None)
+        if getattr(self, "check_every_call", False):
+            self.check_status()
         out = {"rgb_marched": ws.rgb_acc.clone(), "alphainv_last": ws.alphainv_last.clone()}
         if render_depth:
             out["depth"] = ws.depth_acc.clone()
@@ -320,6 +390,33 @@ class FusedTrainer(_FusedBase):
             out[b] = sum(ts) / max(len(ts), 1)
         return out
 
+    # -- state snapshot / restore (bench.py: the clock ramp and warm-up must not train the model that is timed) -----
+    @torch.no_grad()
+    def snapshot(self):
+        snap = {"t": {n: getattr(self, n).clone() for n in ("density", "k0", "m_density", "v_density", "m_k0", "v_k0")},
+                "opt_step": self.opt_step, "global_step": self.global_step, "lr": dict(self.lr)}
+        if getattr(self, "_tc", None) is not None:
+            snap["tc"] = [self._tc.params.clone(), self._tc.exp_avg.clone(), self._tc.exp_avg_sq.clone()]
+        elif self.model.rgbnet is not None:
+            snap["rgbnet"] = [p.detach().clone() for p in self.model.rgbnet.parameters()]
+        return snap
+
+    @torch.no_grad()
+    def restore(self, snap):
+        """In place (the buffers may live in symmetric memory that peers hold addresses of)."""
+        for n, t in snap["t"].items():
+            getattr(self, n).copy_(t)
+        for g in (self.g_density, self.g_k0):
+            g.zero_()
+        self.opt_step, self.global_step, self.lr = snap["opt_step"], snap["global_step"], dict(snap["lr"])
+        if "tc" in snap:
+            for dst, src in zip((self._tc.params, self._tc.exp_avg, self._tc.exp_avg_sq), snap["tc"]):
+                dst.copy_(src)
+        elif "rgbnet" in snap:
+            for p, src in zip(self.model.rgbnet.parameters(), snap["rgbnet"]):
+                p.data.copy_(src)
+            self.rgbnet_state = {}
+
     # -- the step -----------------------------------------------------------------------------------
     def step(self, rays_o, rays_d, viewdirs, target):
         cfg, model = self.cfg, self.model
@@ -427,13 +524,8 @@ class FusedTrainer(_FusedBase):
                 ext.zero_(g[x1:])
 
     def _tv_now(self):
-        cfg, gs = self.cfg, self.global_step
-        if "tv_before" in cfg or "tv_after" in cfg:  # run.py:389 schedule
-            on = gs < cfg.get("tv_before", 0) and gs > cfg.get("tv_after", 0) and gs % cfg.get("tv_every", 1) == 0
-            dense = gs < cfg.get("tv_dense_before", 0)
-        else:
-            on, dense = True, bool(cfg.get("tv_dense", True))
-        return on, dense
+        from .trainer import tv_schedule
+        return tv_schedule(self.cfg, self.global_step)
 
     def _peer_barrier(self, with_small_grads=False):
         """Cross-rank ordering point on the current stream: a (tiny) NCCL all-reduce completes on a rank only after
@@ -543,6 +635,7 @@ class FusedTrainer(_FusedBase):
 
     @torch.no_grad()
     def optimizer_state_dict(self):
+        self.check_status()
         state, groups, idx = {}, [], 0
         for name, pnames in self._opt_entries():
             ids = []

@@ -87,6 +87,45 @@ class _GridSamplePlane(torch.autograd.Function):
         return grad_plane, None, None, None, None, None
 
 
+class _GridSampleNorm(torch.autograd.Function):
+    """F.grid_sample(input, grid, 'bilinear', 'zeros', align_corners=True) for batch 1 with the literal arguments."""
+
+    @staticmethod
+    def forward(ctx, inp, pts):
+        out = ext.grid_sample_norm(inp, pts)
+        if inp.requires_grad:
+            ctx.save_for_backward(pts)
+            ctx.in_shape = inp.shape
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (pts,) = ctx.saved_tensors
+        grad_in = torch.zeros(ctx.in_shape, dtype=grad_out.dtype, device=grad_out.device)
+        ext.grid_sample_norm_backward(grad_out.contiguous(), pts, grad_in)
+        return grad_in, None
+
+
+def make_grid_sample(real):
+    """A stand-in for torch.nn.functional.grid_sample that serves the call shapes of the unmodified reference
+    (lib/dvgo.py:321, lib/dmpigo.py:169, lib/tri_dvgo.py:462-464,618: batch 1, CUDA fp32, bilinear, zero padding,
+    align_corners=True, coordinates without grad) from our kernels and hands everything else to `real`."""
+
+    def grid_sample(input, grid, mode="bilinear", padding_mode="zeros", align_corners=None):
+        nd = input.dim() - 2
+        if (input.is_cuda and input.dtype == torch.float32 and grid.dtype == torch.float32 and mode == "bilinear"
+                and padding_mode == "zeros" and align_corners is True and nd in (2, 3) and input.shape[0] == 1
+                and grid.shape[0] == 1 and grid.shape[-1] == nd and not grid.requires_grad and input.is_contiguous()):
+            pts = grid.reshape(-1, nd).contiguous()
+            out = _GridSampleNorm.apply(input, pts)                       # [P, C]
+            return out.T.reshape(1, input.shape[1], *grid.shape[1:-1])   # the [1,C,...] ATen returns (a view)
+        return real(input, grid, mode=mode, padding_mode=padding_mode, align_corners=align_corners)
+
+    grid_sample._dvgo_real = real
+    return grid_sample
+
+
 # which world axis indexes the W / H dimension of each plane: the reference samples plane 'ab' with
 # ind_norm[..., [i, j]] where ind_norm = (z_n, y_n, x_n) (lib/tri_dvgo.py:460-464)
 TRIPLANE_AXES = {"xy": (2, 1), "yz": (1, 0), "zx": (0, 2)}

@@ -27,15 +27,26 @@ def training_loss(ret, target, n_rays, weight_main=1.0, weight_entropy_last=0.0,
     return loss
 
 
+def tv_schedule(cfg, global_step):
+    """(tv on?, dense mode?) at this iteration: the gate of run.py:389-395 when cfg carries the reference's
+    tv_before / tv_after / tv_every / tv_dense_before keys, else the simple `tv_dense` switch of the benchmarks."""
+    if "tv_before" in cfg or "tv_after" in cfg:
+        on = (global_step < cfg.get("tv_before", 0) and global_step > cfg.get("tv_after", 0)
+              and global_step % cfg.get("tv_every", 1) == 0)
+        return on, global_step < cfg.get("tv_dense_before", 0)
+    return True, bool(cfg.get("tv_dense", True))
+
+
 class ModuleTrainer:
-    def __init__(self, model, cfg_train, render_kwargs, dist_group=None, world_size=1):
+    def __init__(self, model, cfg_train, render_kwargs, dist_group=None, world_size=1, global_step=0):
         self.model = model
         self.cfg = dict(cfg_train)
         self.rk = dict(render_kwargs)
-        self.opt = create_optimizer_or_freeze_model(model, self.cfg, global_step=0)
-        self.global_step = 0
+        self.opt = create_optimizer_or_freeze_model(model, self.cfg, global_step=global_step)
+        self.global_step = global_step
         self.world_size = world_size
         self.dist_group = dist_group
+        self.decay = 0.1 ** (1.0 / (self.cfg.get("lrate_decay", 20) * 1000))   # run.py:401-403
 
     def _allreduce_grads(self):
         import torch.distributed as dist
@@ -56,10 +67,12 @@ class ModuleTrainer:
         loss.backward()
         if self.world_size > 1:
             self._allreduce_grads()
-        dense = cfg.get("tv_dense", True)
-        if cfg.get("weight_tv_density", 0) > 0:
+        tv_on, dense = tv_schedule(cfg, self.global_step)
+        if tv_on and cfg.get("weight_tv_density", 0) > 0:
             m.density_total_variation_add_grad(cfg["weight_tv_density"] / n_global, dense)
-        if cfg.get("weight_tv_k0", 0) > 0:
+        if tv_on and cfg.get("weight_tv_k0", 0) > 0:
             m.k0_total_variation_add_grad(cfg["weight_tv_k0"] / n_global, dense)
         self.opt.step()
+        for group in self.opt.param_groups:     # run.py:401-406: per-iteration exponential lr decay
+            group["lr"] = group["lr"] * self.decay
         return loss.detach()

@@ -135,6 +135,22 @@ int dvgo_grid_sample_2d_backward(const float* grad_out, int C, int H, int W, con
                                  const float* xyz_min, const float* xyz_max, int axis_w, int axis_h,
                                  int64_t n_pts, float* grad_plane, dvgo_stream_t stream);
 
+/* a7 (literal F.grid_sample signature)  The unmodified lib/*.py call torch.nn.functional.grid_sample themselves
+ * (lib/dvgo.py:321, lib/dmpigo.py:169, lib/tri_dvgo.py:462-464,618) with ALREADY-normalised coordinates.
+ * These variants take that `grid` argument as it is: ind_norm [n_pts,3] = (w, h, d) = (z_n, y_n, x_n) for the 5-D
+ * case, [n_pts,2] = (w, h) for the 4-D case; only ATen's align_corners=True un-normalisation is applied.
+ * Outputs / gradients as above ([n_pts,C]; the binding returns the [1,C,...] view ATen would).
+ * `directvoxgo_b200.dropin.install(grid_sample=True)` routes F.grid_sample here. */
+int dvgo_grid_sample_3d_norm(const float* grid, int C, int X, int Y, int Z, const float* ind_norm,
+                             int64_t n_pts, float* out, dvgo_stream_t stream);
+int dvgo_grid_sample_3d_norm_backward(const float* grad_out, int C, int X, int Y, int Z,
+                                      const float* ind_norm, int64_t n_pts, float* grad_grid,
+                                      dvgo_stream_t stream);
+int dvgo_grid_sample_2d_norm(const float* plane, int C, int H, int W, const float* ind_norm, int64_t n_pts,
+                             float* out, dvgo_stream_t stream);
+int dvgo_grid_sample_2d_norm_backward(const float* grad_out, int C, int H, int W, const float* ind_norm,
+                                      int64_t n_pts, float* grad_plane, dvgo_stream_t stream);
+
 /* a10 torch_scatter.segment_coo(src, index, out, reduce='sum')   lib/dvgo.py:554-558,571-575
  * src [n_pts,D] fp32, index [n_pts] int64 sorted ascending, out [n_seg,D] accumulated INTO (the
  * caller passes zeros, as the reference does).  Deterministic: one warp per run of equal indices.

@@ -187,13 +187,13 @@ int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G, dvgo_s
  * Weights are fp32 in torch nn.Linear layout ([out][in]); GEMM operands are rounded to FP16, accumulation
  * is fp32.  rgb [surv_cap,3].  width must be 128 (DVGO_EINVAL otherwise: the caller falls back). */
 int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                 const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
+                 int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
                  const float* b2, const float* W3, const float* b3, int width, float* rgb,
                  dvgo_stream_t stream);
 /* Same as dvgo_mlp_fwd; if `timeline` is non-NULL, CTA 0 records clock64() at every phase boundary of its
  * first tiles into timeline[0..63] (thread 0) and timeline[64..127] (thread 255) -- kernel-author tooling. */
 int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                       const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
+                       int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
                        const float* W2, const float* b2, const float* W3, const float* b3, int width, float* rgb,
                        long long* timeline, dvgo_stream_t stream);
 /* Backward with forward recompute: d_feat [surv_cap,C] = dL/dfeat, and gW*, gb* += weight gradients
@@ -201,7 +201,7 @@ int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const flo
  * the sigmoid).  grad_scale: power of two applied to the FP16 backward operands and removed exactly in
  * the fp32 epilogues. */
 int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                 const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
+                 int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
                  const float* b2, const float* W3, const float* b3, int width, const float* rgb,
                  const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
                  float* gb2, float* gW3, float* gb3, dvgo_stream_t stream);
@@ -209,7 +209,7 @@ int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe
 /* dvgo_mlp_bwd with an optional in-kernel timeline (CTA 0: epilogue thread 0 -> timeline[0..63], issuer ->
  * timeline[64..127], clock64 at every phase boundary of the first tile pair) -- kernel-author tooling. */
 int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                       const int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
+                       int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
                        const float* b2, const float* W3, const float* b3, int width, const float* rgb,
                        const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
                        float* gb2, float* gW3, float* gb3, long long* timeline, dvgo_stream_t stream);
@@ -236,6 +236,12 @@ int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, int K, int
 
 /* Zero `n` 4-byte words (counters, accumulators) on the stream. */
 int dvgo_fused_zero(void* ptr, int64_t n_words, dvgo_stream_t stream);
+
+/* Start of a fused call: zblock = counters[2] | accumulators (n_words 4-byte words, n_words >= 2).  Before zeroing,
+ * the previous call's counters are folded into stats (4 x int64, device; may be NULL): [0] += survivors,
+ * [1] += 1, [2] |= overflow flag, [3] = max(survivors).  Lets the host learn the data-dependent survivor count of
+ * the timed steps (the MLP work term of the roofline) and a capacity overflow without synchronising per step. */
+int dvgo_fused_step_begin(void* zblock, int64_t n_words, long long* stats, dvgo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ from . import oracle as orc
 def set_ops(ns):
     """Swap the provider of the reference's custom ops (default: the C oracle on the CPU).  The GPU tests pass a
     namespace built from oracle/_ref -- the reference's OWN CUDA kernels -- to run and time the reference's op
-    sequence on the same B200 (tests/test_gpu_vs_ref.py).  Returns the previous provider."""
+    sequence on the same B200 (tests/test_gpu_0_vs_ref.py).  Returns the previous provider."""
     global orc
     prev, orc = orc, ns
     return prev

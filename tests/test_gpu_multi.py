@@ -11,9 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_ray_sharded_fused_trainer_matches_single_gpu():
-    if torch.cuda.device_count() < 2:
+    n = torch.cuda.device_count()
+    if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)      # every GPU of the box (the 48^3 test grid splits into 2/4/8 slabs)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert "MULTI_GPU_CHECK PASS" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
