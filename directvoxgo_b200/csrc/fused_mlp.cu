@@ -331,9 +331,12 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     stamp();
     sync_for_mma();
     stamp();
-    if (tid == 0) {
-      gemm_kk(tD1, smem_u32(sX), K1, smem_u32(sW1), K1, kHid, K1, false);
-      mma_commit(ctx.bar);
+    if (warp == 0) {
+      if (elect_one()) {
+        gemm_kk(tD1, smem_u32(sX), K1, smem_u32(sW1), K1, kHid, K1, false);
+        mma_commit(ctx.bar);
+      }
+      __syncwarp();
     }
     stamp();
     mma_wait(ctx);
@@ -342,9 +345,12 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     stamp();
     sync_for_mma();
     stamp();
-    if (tid == 0) {
-      gemm_kk(tD2, smem_u32(sH1), kHid, smem_u32(sW2), kHid, kHid, kHid, false);
-      mma_commit(ctx.bar);
+    if (warp == 0) {
+      if (elect_one()) {
+        gemm_kk(tD2, smem_u32(sH1), kHid, smem_u32(sW2), kHid, kHid, kHid, false);
+        mma_commit(ctx.bar);
+      }
+      __syncwarp();
     }
     stamp();
     mma_wait(ctx);
@@ -646,7 +652,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       dbg[(is_issuer ? 64 : 0) + dbg_n++] = clock64();
   };
   if (is_issuer) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         stamp();
         acquire(A); stamp(); issue_l1(A); stamp();
@@ -803,7 +809,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     const uint32_t idesc = make_idesc_f16(128, N, a_mn, b_mn);
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
     const uint32_t a_step = a_mn ? 2 * group_stride(a_cols) : 256u;
@@ -854,7 +860,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     const uint32_t idesc = make_idesc_f16(128, N, 0, b_mn);
     for (int k = 0; k < K / kMmaK; ++k)
       mma_f16(tmem, desc_kmajor(smem_u32(sA) + k * 256u, K), make_desc(smem_u32(sB) + k * kstep, lbo, sbo),
@@ -895,7 +901,7 @@ __global__ void __launch_bounds__(128) tc_rate_kernel(int N, int ksteps, int rep
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {
     const uint32_t idesc = make_idesc_f16(128, N, a_mn, b_mn);
     const uint64_t lay = static_cast<uint64_t>(layout) << 61;
     uint64_t ad[8], bd[8];
@@ -923,9 +929,110 @@ __global__ void __launch_bounds__(128) tc_rate_kernel(int N, int ksteps, int rep
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// TMEM-sourced A operand probe: D[128,N] = A[128,K] * B^T with A written to tensor memory by tcgen05.st (fp16 pairs
+// packed along K) and B from shared memory; then `reps` x (K/16) MMAs of the same shape are timed in the TS form
+// (A from TMEM) and in the SS form (A from shared memory), cycles[0] / cycles[1].  Answers (i) is the packing
+// assumption right, (ii) what does an N = 16 MMA cost when A does not use shared-memory bandwidth.
+__global__ void __launch_bounds__(128) tc_ts_probe_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                          float* __restrict__ D, int N, int K, int b_mn, int reps,
+                                                          long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
+  uint8_t* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint8_t* sB = sA + ((tile_bytes(128, K) + 1023) / 1024) * 1024;
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init_fence(); }
+  for (int i = tid; i < 128 * K; i += blockDim.x)
+    *reinterpret_cast<__half*>(sA + tile_off(i / K, i % K, K)) = __float2half_rn(A[i]);
+  for (int i = tid; i < b_rows * b_cols; i += blockDim.x)
+    *reinterpret_cast<__half*>(sB + tile_off(i / b_cols, i % b_cols, b_cols)) = __float2half_rn(B[i]);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tA = tmem + 256;                       // A operand: columns [256, 256 + K/2)
+  const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+  for (int k0 = 0; k0 < K; k0 += 16) {                  // this thread's row, 16 halves -> 8 columns
+    uint32_t u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half2 h = __floats2half2_rn(A[tid * K + k0 + 2 * j], A[tid * K + k0 + 2 * j + 1]);
+      u[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    tmem_st8(tA + lane_sel + k0 / 2, u);
+  }
+  tmem_st_wait();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t idesc = make_idesc_f16(128, N, 0, b_mn);
+  const uint32_t b_step = b_mn ? 2 * group_stride(b_cols) : 256u;
+  const int ksteps = K / kMmaK;
+  uint32_t phase = 0;
+  if (warp == 0 && elect_one()) {
+    for (int k = 0; k < ksteps; ++k) {
+      const uint64_t db = b_mn ? desc_mnmajor(smem_u32(sB) + k * b_step, b_cols) : desc_kmajor(smem_u32(sB) + k * b_step, b_cols);
+      mma_f16_ts(tmem, tA + k * 8, db, idesc, k > 0 ? 1u : 0u);
+    }
+    mma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), phase); phase ^= 1u;
+  fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem + lane_sel + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[(warp * 32 + lane) * N + c0 + j] = v[j];
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (warp == 0 && reps > 0 && elect_one()) {
+    uint64_t bd[8];
+    for (int k = 0; k < 8; ++k)
+      bd[k] = b_mn ? desc_mnmajor(smem_u32(sB) + (k % ksteps) * b_step, b_cols) : desc_kmajor(smem_u32(sB) + (k % ksteps) * b_step, b_cols);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < ksteps) mma_f16_ts(tmem + 128, tA + k * 8, bd[k], idesc, (r | k) ? 1u : 0u);
+    mma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), phase); phase ^= 1u;
+    cycles[0] = clock64() - t0;
+    uint64_t ad[8];
+    for (int k = 0; k < 8; ++k) ad[k] = desc_kmajor(smem_u32(sA) + (k % ksteps) * 256u, K);
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < ksteps) mma_f16(tmem + 128, ad[k], bd[k], idesc, (r | k) ? 1u : 0u);
+    mma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), phase); phase ^= 1u;
+    cycles[1] = clock64() - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace dvgo
 
 using namespace dvgo;
+
+DVGO_API int dvgo_tc_ts_probe(const float* A, const float* B, float* D, int N, int K, int b_mn, int reps,
+                              long long* cycles, dvgo_stream_t stream) {
+  if (!A || !B || !D || !cycles || N < 16 || N > 128 || N % 16 || K < 16 || K > 128 || K % 16 || reps < 0) return DVGO_EINVAL;
+  const size_t bytes = ((tc::tile_bytes(128, K) + 1023) / 1024) * 1024 + tc::tile_bytes(b_mn ? K : N, b_mn ? N : K) + 2048;
+  cudaError_t e = cudaFuncSetAttribute(tc_ts_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  tc_ts_probe_kernel<<<1, 128, bytes, as_stream(stream)>>>(A, B, D, N, K, b_mn, reps, cycles);
+  return launch_status();
+}
 
 DVGO_API int dvgo_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn,
                               dvgo_stream_t stream) {

@@ -38,6 +38,17 @@ Tensor tc_probe(Tensor A, Tensor Braw, int N, int K, bool b_mn, int lbo, int sbo
   return D;
 }
 
+std::vector<Tensor> tc_ts_probe(Tensor A, Tensor B, int N, int K, bool b_mn, int reps) {
+  chkf(A, "A"); chkf(B, "B");
+  TORCH_CHECK(A.numel() == 128 * K && B.numel() == (int64_t)N * K, "A must hold 128*K, B N*K elements");
+  const c10::cuda::CUDAGuard guard(A.device());
+  auto D = torch::empty({128, N}, A.options());
+  auto cyc = torch::zeros({2}, torch::TensorOptions().dtype(torch::kInt64).device(A.device()));
+  rc_check(dvgo_tc_ts_probe(A.data_ptr<float>(), B.data_ptr<float>(), D.data_ptr<float>(), N, K, b_mn, reps,
+                            reinterpret_cast<long long*>(cyc.data_ptr<int64_t>()), cur_stream()), "tc_ts_probe");
+  return {D, cyc};
+}
+
 Tensor tc_rate(int ctas, int N, int ksteps, int reps, bool a_mn, bool b_mn, int a_lbo, int a_sbo, int a_kstep, int b_lbo,
                int b_sbo, int b_kstep, int layout, int n_accum) {
   auto out = torch::zeros({ctas}, torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA));
@@ -139,6 +150,7 @@ void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("tc_selftest", &tc_selftest);
   m.def("tc_probe", &tc_probe);
   m.def("tc_rate", &tc_rate);
+  m.def("tc_ts_probe", &tc_ts_probe);
   m.def("view_embedding", &view_embedding);
   m.def("mlp_fwd", &mlp_fwd);
   m.def("mlp_fwd_timeline", &mlp_fwd_timeline);

@@ -45,6 +45,22 @@ __host__ __device__ constexpr uint32_t tile_bytes(int rows, int cols) {
 __host__ __device__ constexpr uint32_t group_stride(int cols) { return static_cast<uint32_t>((cols / 8) * 128); }
 constexpr int kMmaK = 16;  // K elements consumed by one kind::f16 tcgen05.mma
 
+// One elected lane of a fully converged warp (elect.sync).  MMA issue MUST sit under this predicate inside a
+// warp-uniform branch: under a plain `if (threadIdx.x == 0)` nvcc cannot prove a single active thread and wraps EVERY
+// tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop (measured round 1 as "no MMA issues faster than 49-72 cycles");
+// under elect.sync the UTCHMMAs are emitted back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // 64-bit shared-memory matrix descriptor (sm_100 "version 1", no swizzle, base offset 0).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -81,6 +97,39 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows = TMEM lanes, K contiguous along the columns, two fp16
+// per 32-bit column, so one K = 16 step spans 8 columns) is read from tensor memory instead of shared memory.
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM: 32 lanes (this warp's quarter) x 8 consecutive 32-bit columns (= 16 packed fp16 per lane).
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* u) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+               :
+               : "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* u) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+      "%15, %16};\n"
+      :
+      : "r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]),
+        "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Make all previously issued MMAs arrive on an mbarrier when they complete.
 __device__ __forceinline__ void mma_commit(uint32_t bar_saddr) {

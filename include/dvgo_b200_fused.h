@@ -234,6 +234,12 @@ int dvgo_tc_rate(int ctas, int N, int ksteps, int reps, int a_mn, int b_mn, int 
 int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, int K, int b_mn, int lbo, int sbo,
                   int kstep, int nwords, dvgo_stream_t stream);
 
+/* Tensor-memory A-operand probe (tools/ts_probe.py): D[128,N] = A[128,K] * B^T with A staged in TMEM by tcgen05.st
+ * (fp16 pairs packed along K) and B in shared memory ([N][K], or [K][N] when b_mn); cycles[0] / cycles[1] = clock64
+ * cycles of `reps` x K/16 MMAs in the TMEM-A form and in the shared-memory-A form. */
+int dvgo_tc_ts_probe(const float* A, const float* B, float* D, int N, int K, int b_mn, int reps, long long* cycles,
+                     dvgo_stream_t stream);
+
 /* Zero `n` 4-byte words (counters, accumulators) on the stream. */
 int dvgo_fused_zero(void* ptr, int64_t n_words, dvgo_stream_t stream);
 

@@ -17,13 +17,21 @@ from oracle.make_golden_refpy import OUT, import_reference
 def stub_missing_imports():
     """Packages the reference imports at module top but never touches on the hot path, absent in this image."""
     import importlib.util
-    if importlib.util.find_spec("matplotlib") is None:
+
+    def missing(name):
+        if name in sys.modules:          # already imported, or already stubbed by an earlier call
+            return False
+        try:
+            return importlib.util.find_spec(name) is None
+        except (ValueError, ImportError):
+            return True
+    if missing("matplotlib"):
         mp, pp = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
         pp.step = lambda *a, **k: None
         mp.pyplot = pp
         sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mp, pp
     for n in ("imageio", "mmcv", "lpips"):
-        if n not in sys.modules and importlib.util.find_spec(n) is None:
+        if missing(n):
             sys.modules[n] = types.ModuleType(n)
 
 
