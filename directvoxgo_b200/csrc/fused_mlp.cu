@@ -80,33 +80,14 @@ __device__ __forceinline__ uint4 pack8_masked(const float* v, const uint4& act) 
   return *reinterpret_cast<uint4*>(h);
 }
 
-// Weights -> fp16 canonical tiles (sW1 [128 x K1] incl. the bias column, sW2 [128 x 128]) and the
-// small fp32 arrays used by the SIMT parts (W3 [3][128], b2 [128], b3 [3]).
-__device__ void load_weights(const MlpW& w, int d_in, int K1, uint8_t* sW1, uint8_t* sW2, float* sW3, float* sB2,
-                             float* sB3, int w2_cols = kHid) {
-  for (int i = threadIdx.x; i < kHid * K1; i += blockDim.x) {
-    const int n = i / K1, c = i % K1;
-    const float v = c < d_in ? w.W1[n * d_in + c] : (c == d_in ? w.b1[n] : 0.f);
-    *reinterpret_cast<__half*>(sW1 + tile_off(n, c, K1)) = half_sat(v);
-  }
-  for (int i = threadIdx.x; i < kHid * w2_cols; i += blockDim.x) {  // w2_cols = 144: column 128 holds b2
-    const int n = i / w2_cols, c = i % w2_cols;
-    const float v = c < kHid ? w.W2[n * kHid + c] : (c == kHid ? w.b2[n] : 0.f);
-    *reinterpret_cast<__half*>(sW2 + tile_off(n, c, w2_cols)) = half_sat(v);
-  }
-  for (int i = threadIdx.x; i < 3 * kHid; i += blockDim.x) sW3[i] = w.W3[i];
-  for (int i = threadIdx.x; i < kHid; i += blockDim.x) sB2[i] = w.b2[i];
-  if (threadIdx.x < 3) sB3[threadIdx.x] = w.b3[threadIdx.x];
-}
-
 // Augmented input tile [128 x K1]: cols [0,C) k0 features, [C,C+pe_stride) the ray's row of the padded
 // view-embedding table (P embedding values, then the constant 1 that carries b1, then zeros), rest 0;
 // rows past the survivor count are zero.  16-byte vector loads when C and pe_stride are multiples of 4.
 __device__ __forceinline__ void stage_x(uint8_t* sX, int K1, int64_t base, int64_t count,
                                         const float* __restrict__ feat, int C,
                                         const int32_t* __restrict__ s_ray, const float* __restrict__ pe,
-                                        int pe_stride) {
-  const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+                                        int pe_stride, int gtid) {   // gtid: thread index inside a 256-thread group
+  const int r = gtid & 127, h = gtid >> 7;
   const int64_t s = base + r;
   const bool valid = s < count;
   const float* __restrict__ f = feat + s * C;
@@ -138,7 +119,198 @@ __device__ __forceinline__ void stage_x(uint8_t* sX, int K1, int64_t base, int64
   }
 }
 
-// Software-pipelined staging (vector path: C and pe_stride multiples of 4): the raw fp32 inputs of the NEXT
+// ---- flat, coalesced, software-pipelined staging of the X~ tile (vector path: C and pe_stride multiples of 4) ----
+// A group of 256 threads fills one [128 rows][K1] fp16 tile.  Round 1 gave each thread one row and read 16 bytes per
+// lane from 32 different rows per instruction (feature rows 48 B apart, embedding rows gathered by ray): every warp
+// load touched 12-32 cache lines and the LSU, not the memory system, set the staging time (2000-5000 cycles per tile in
+// tools/mlp_timeline.py, more than all MMAs of the tile).  Here the 128 feature rows of a tile are ONE contiguous
+// 128*C*4-byte block read with consecutive float4 per lane, and the embedding rows are read with pe_stride/4
+// consecutive lanes per row.  The raw fp32 values of the NEXT tile are loaded into registers while the current tile
+// computes and only converted + stored at the next hand-off; the ray indices (head of the dependent chain
+// s_ray -> embedding row) are fetched one tile further ahead.
+// Prefetch loads as VOLATILE asm: a plain __ldg whose value is first used a whole tile later may legally be sunk by the
+// compiler to just before that use (it does: the consumer then eats the full memory latency -- 1200-1800 cycles per
+// tile in the timeline); volatile asm keeps its place between the (volatile) MMA-issue / barrier statements.
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldg_nc_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// Predicated loads that read-modify-write their destination (kept at its previous value when the predicate is off), and
+// a zero-cost "all of these registers are defined here" fence.  Prefetch pattern that does not stall on the per-warp
+// scoreboards (only six, shared by the compiler between all loads in flight): (1) zero every destination register --
+// the write-after-write waits against the loads of the PREVIOUS tile land here, where nothing is in flight;
+// (2) reg_fence(); (3) issue all loads back to back.  Interleaving (1) and (3) per register made every zeroing MOV
+// wait for the loads issued just before it: 4000-5000 cycles per tile pair in tools/mlp_timeline.py.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void ldg_nc_f4_if(float4& v, const float4* p, bool pred) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "}\n"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "l"(p), "r"(static_cast<int>(pred)));
+}
+__device__ __forceinline__ void ldg_nc_f32_if(float& v, const float* p, bool pred) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q ld.global.nc.f32 %0, [%1];\n\t"
+      "}\n"
+      : "+f"(v)
+      : "l"(p), "r"(static_cast<int>(pred)));
+}
+__device__ __forceinline__ void reg_fence(float4& a, float4& b, float4& c, float4& d) {
+  asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w),
+                    "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w), "+f"(d.x), "+f"(d.y), "+f"(d.z), "+f"(d.w));
+}
+__device__ __forceinline__ void reg_fence(float& a, float& b, float& c, float& d, float& e, float& f) {
+  asm volatile("" : "+f"(a), "+f"(b), "+f"(c), "+f"(d), "+f"(e), "+f"(f));
+}
+struct StageRegs {
+  float4 f[2];   // feature float4 ids gtid, gtid + 256           (< 128 * C/4 <= 512)
+  float4 p[4];   // embedding float4 ids gtid + 256 k, k < 4      (< 128 * pe_stride/4 <= 1024)
+  int ray[4];    // ray index of the rows of p[], for the tile AFTER the one held in f / p
+};
+// id / d for id < 1024, d <= 8 as one multiply + shift: inv = ceil(2^16 / d), computed ONCE per kernel (StageGeom).
+// (The first version divided by the runtime d at every use: a ~30-instruction dependent chain through I2F / MUFU.RCP /
+// F2I per load and per store, 16 times per tile -- 3000+ cycles of pure latency per tile in tools/mlp_timeline.py.)
+struct StageGeom {
+  int nf4, np4, inv_f, inv_p;
+};
+__device__ __forceinline__ StageGeom stage_geom(int C, int pe_stride) {
+  StageGeom g;
+  g.nf4 = C >> 2;
+  g.np4 = pe_stride >> 2;
+  g.inv_f = g.nf4 > 0 ? (65536 + g.nf4 - 1) / g.nf4 : 0;
+  g.inv_p = g.np4 > 0 ? (65536 + g.np4 - 1) / g.np4 : 0;
+  return g;
+}
+__device__ __forceinline__ int fast_div(int id, int inv) { return (id * inv) >> 16; }
+__device__ __forceinline__ void stage_rays(StageRegs& r, int gtid, int64_t s0, int64_t count,
+                                           const int32_t* __restrict__ s_ray, const StageGeom& g) {
+  const int np4 = g.np4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int id = gtid + 256 * k;
+    const int64_t sidx = s0 + fast_div(id, g.inv_p);
+    r.ray[k] = -1;
+    if (id < 128 * np4 && sidx < count) r.ray[k] = ldg_nc_s32(s_ray + sidx);
+  }
+}
+// loads of the tile at s0 with the ray indices already in r.ray
+__device__ __forceinline__ void stage_loads(StageRegs& r, int gtid, int64_t s0, int64_t count,
+                                            const float* __restrict__ feat, const float* __restrict__ pe,
+                                            const StageGeom& g) {
+  const int nf4 = g.nf4, np4 = g.np4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int id = gtid + 256 * k;
+    r.f[k] = zero;
+    if (id < 128 * nf4 && s0 + fast_div(id, g.inv_f) < count)
+      r.f[k] = ldg_nc_f4(reinterpret_cast<const float4*>(feat) + s0 * nf4 + id);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int id = gtid + 256 * k;
+    r.p[k] = zero;
+    if (r.ray[k] >= 0) {
+      const int c4 = id - fast_div(id, g.inv_p) * np4;
+      r.p[k] = ldg_nc_f4(reinterpret_cast<const float4*>(pe) + static_cast<int64_t>(r.ray[k]) * np4 + c4);
+    }
+  }
+}
+__device__ __forceinline__ uint2 pack4(const float4& v) {
+  const __half2 a = pack2_sat(v.x, v.y), b = pack2_sat(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ void stage_stores(const StageRegs& r, int gtid, int C, int K1, uint8_t* sX,
+                                             const StageGeom& g) {
+  const int nf4 = g.nf4, np4 = g.np4;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int id = gtid + 256 * k;
+    if (id < 128 * nf4) {
+      const int row = fast_div(id, g.inv_f), c4 = id - row * nf4;
+      *reinterpret_cast<uint2*>(sX + tile_off(row, 4 * c4, K1)) = pack4(r.f[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int id = gtid + 256 * k;
+    if (id < 128 * np4) {
+      const int row = fast_div(id, g.inv_p), c4 = id - row * np4;
+      *reinterpret_cast<uint2*>(sX + tile_off(row, C + 4 * c4, K1)) = pack4(r.p[k]);
+    }
+  }
+}
+
+// ---- fp16 weight tiles, converted once per call by mlp_pack_weights_kernel and bulk-copied by every CTA ----
+// (round 1: every CTA converted 22 K fp32 weights with scalar loads and integer divisions: 84 K cycles = 43 us of
+// prologue in the forward kernel, 24 us in the backward one -- tools/mlp_timeline.py)
+//   [W1~ : 128 x K1 canonical tile, column d_in = b1][W2~ : 128 x 144, column 128 = b2][W3 : 16 x 128 K-major tile]
+//   [W3 column pairs for the SIMT dZ2 = dZ3 W3: pair jj -> half2 {W3[c][2jj], W3[c][2jj+1]} for c = 0,1,2, pad]
+//   [b3: 3 floats + pad]
+struct WPack {
+  uint32_t offW2, offW3, offW3p, offW3t, offB3, total;
+};
+__host__ __device__ inline WPack wpack_layout(int K1) {
+  WPack l;
+  l.offW2 = (tile_bytes(kHid, K1) + 1023u) & ~1023u;
+  l.offW3 = l.offW2 + ((tile_bytes(kHid, kHidA) + 1023u) & ~1023u);
+  l.offW3p = l.offW3 + ((tile_bytes(16, kHid) + 1023u) & ~1023u);
+  l.offW3t = l.offW3p + 1024u;                                          // [128 j][16] = W3^T: K-major B of dH2 = dZ3 W3
+  l.offB3 = l.offW3t + ((tile_bytes(kHid, 16) + 1023u) & ~1023u);
+  l.total = l.offB3 + 16u;
+  return l;
+}
+__global__ void __launch_bounds__(256) mlp_pack_weights_kernel(MlpW w, int d_in, int K1, uint8_t* __restrict__ out) {
+  const WPack l = wpack_layout(K1);
+  const int n1 = kHid * K1, n2 = kHid * kHidA, n3 = 16 * kHid, n4 = (kHid / 2) * 8, n5 = kHid * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3 + n4 + n5 + 4; i += gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int n = i / K1, c = i % K1;
+      const float v = c < d_in ? w.W1[n * d_in + c] : (c == d_in ? w.b1[n] : 0.f);
+      *reinterpret_cast<__half*>(out + tile_off(n, c, K1)) = half_sat(v);
+    } else if (i < n1 + n2) {
+      const int k = i - n1, n = k / kHidA, c = k % kHidA;
+      const float v = c < kHid ? w.W2[n * kHid + c] : (c == kHid ? w.b2[n] : 0.f);
+      *reinterpret_cast<__half*>(out + l.offW2 + tile_off(n, c, kHidA)) = half_sat(v);
+    } else if (i < n1 + n2 + n3) {
+      const int k = i - n1 - n2, n = k / kHid, c = k % kHid;
+      *reinterpret_cast<__half*>(out + l.offW3 + tile_off(n, c, kHid)) = half_sat(n < 3 ? w.W3[n * kHid + c] : 0.f);
+    } else if (i < n1 + n2 + n3 + n4) {
+      const int k = i - n1 - n2 - n3, jj = k >> 3, e = k & 7;      // 8 halves per pair: (c = e/2, which = e%2)
+      const int c = e >> 1, j = 2 * jj + (e & 1);
+      *reinterpret_cast<__half*>(out + l.offW3p + jj * 16 + e * 2) = half_sat(c < 3 ? w.W3[c * kHid + j] : 0.f);
+    } else if (i < n1 + n2 + n3 + n4 + n5) {
+      const int k = i - n1 - n2 - n3 - n4, j = k / 16, c = k % 16;
+      *reinterpret_cast<__half*>(out + l.offW3t + tile_off(j, c, 16)) = half_sat(c < 3 ? w.W3[c * kHid + j] : 0.f);
+    } else {
+      const int k = i - n1 - n2 - n3 - n4 - n5;
+      reinterpret_cast<float*>(out + l.offB3)[k] = k < 3 ? w.b3[k] : 0.f;
+    }
+  }
+}
+// cooperative 16-byte copy global -> shared (bytes % 16 == 0)
+__device__ __forceinline__ void copy_to_smem(uint8_t* dst, const uint8_t* __restrict__ src, uint32_t bytes) {
+  for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+}
+__device__ __forceinline__ void group_sync(int ctx) {   // named barrier of one 256-thread epilogue group
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + ctx), "r"(256) : "memory");
+}
+
+// Row-wise software-pipelined staging (backward kernel) (vector path: C and pe_stride multiples of 4): the raw fp32 inputs of the NEXT
 // tile are loaded into registers while the current tile computes, and only converted + stored to shared
 // memory at the top of the next iteration.  The in-kernel timeline (tools/mlp_timeline.py) showed ~3300
 // of ~9000 cycles per tile exposed in the synchronous stage_x (two dependent global-load latencies:
@@ -228,166 +400,200 @@ __device__ __forceinline__ void gemm_mm(uint32_t d, uint32_t a, int a_cols, uint
              2u * group_stride(b_cols), make_idesc_f16(128, N, 1, 1), K / kMmaK, accumulate);
 }
 
-// TMEM [this thread's row][c_begin, c_begin+64) -> relu(v + bias) -> fp16 -> smem tile row.  bias may be
-// null.  All four 16-column TMEM loads are issued before the single wait so their latencies overlap.
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) tmem_ld16(taddr + cc * 16, v + cc * 16);
-  tmem_ld_wait();
-}
-__device__ __forceinline__ void epi_relu_to_smem(uint32_t tmem_d, int q, int row, int c_begin, const float* sBias,
-                                                 uint8_t* sOut, int out_cols) {
-  float v[64];
-  tmem_ld64(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + c_begin, v);
-#pragma unroll
-  for (int cc = 0; cc < 8; ++cc) {
-    const int c0 = c_begin + cc * 8;
-    float o[8];
-    if (sBias) {
-      const float4 b0 = *reinterpret_cast<const float4*>(sBias + c0);
-      const float4 b1 = *reinterpret_cast<const float4*>(sBias + c0 + 4);
-      o[0] = v[cc * 8 + 0] + b0.x; o[1] = v[cc * 8 + 1] + b0.y; o[2] = v[cc * 8 + 2] + b0.z; o[3] = v[cc * 8 + 3] + b0.w;
-      o[4] = v[cc * 8 + 4] + b1.x; o[5] = v[cc * 8 + 5] + b1.y; o[6] = v[cc * 8 + 6] + b1.z; o[7] = v[cc * 8 + 7] + b1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = v[cc * 8 + j];
-    }
-    *reinterpret_cast<uint4*>(sOut + tile_off(row, c0, out_cols)) = pack8_relu(o);
+__device__ __forceinline__ size_t align1k(size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); }
+
+// GEMM with the A operand in tensor memory (fp16 pairs packed along K, 8 columns per K = 16 step) and B in shared
+// memory.  Measured on B200 (tools/ts_probe.py): N/2 cycles per MMA (the math rate) against 36 + N/4 when A is read
+// from shared memory -- the A tile (4 KB per K step) is what bounds a small-N MMA from shared memory.
+__device__ __forceinline__ void gemm_ts(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t b_step, uint32_t idesc,
+                                        int ksteps, bool accumulate) {
+  const uint64_t b_inc = b_step >> 4;
+#pragma unroll 4
+  for (int k = 0; k < ksteps; ++k) {
+    mma_f16_ts(d, a_tmem + 8u * k, b_desc, idesc, (accumulate || k) ? 1u : 0u);
+    b_desc += b_inc;
   }
 }
 
-__device__ __forceinline__ size_t align1k(size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); }
+// TMEM [this thread's row][c_begin, c_begin + 32) fp32 -> relu -> fp16 pairs -> 16 packed registers
+__device__ __forceinline__ void relu_pack32(uint32_t taddr, uint32_t* u) {
+  float v[32];
+  tmem_ld16(taddr, v);
+  tmem_ld16(taddr + 16, v + 16);
+  tmem_ld_wait();
+  const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const __half2 h = __hmax2(pack2_sat(v[2 * j], v[2 * j + 1]), z);
+    u[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
 
 // ---- forward ---------------------------------------------------------------------------------------
+// One tile = 128 survivors; 256 threads: thread (row = 32*(warp%4)+lane, half = warp/4) owns one sample row and 64
+// of the 128 hidden columns.  The activations never touch shared memory: each layer's epilogue writes relu(D) as
+// packed fp16 straight back into tensor memory, where it is the A operand of the next layer's MMAs (TS form):
+//   layer 1 : D = X~ W1~^T           A = X~ tile in shared memory (K1 = 48: k0 | view PE | 1 carries b1)
+//   layer 2 : D = [H1 | 1] W2~^T     A = H1 in TMEM, K = 144 (the constant-1 column carries b2)
+//   layer 3 : D3 = H2 W3^T           A = H2 in TMEM, N = 16 (3 used): 10 cycles per MMA instead of 39 from smem and
+//                                     no SIMT dot products (round 1 spent ~5 instructions per hidden unit on them)
+// TMEM columns (256 per CTA, 2 CTAs per SM): [0,128) accumulator D, [128,200) H (64 packed columns + 8 for the
+// constant-1 K step), [224,240) layer-3 accumulator.
+constexpr uint32_t kFwdTH = 128, kFwdTD3 = 224;
+
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride, float* __restrict__ rgb,
-    long long* __restrict__ dbg) {
+    int32_t* __restrict__ counters, int64_t surv_cap, const uint8_t* __restrict__ wpack, int K1, int pe_stride,
+    float* __restrict__ rgb, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float sB3[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
-  const int d_in = C + P;
   int64_t count = counters[0];
   if (count > surv_cap) count = surv_cap;
   const int64_t n_tiles = (count + kTile - 1) / kTile;
   if (static_cast<int64_t>(blockIdx.x) >= n_tiles) return;  // uniform per CTA, before any allocation
+  if (dbg && blockIdx.x == 0 && (tid == 0 || tid == 255)) dbg[tid ? 64 : 0] = clock64();   // timeline: kernel entry
 
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW1 = base;
-  uint8_t* sW2 = sW1 + align1k(tile_bytes(kHid, K1));
-  uint8_t* sX = sW2 + align1k(tile_bytes(kHid, kHid));
-  uint8_t* sH1 = sX + align1k(tile_bytes(kTile, K1));
-  float* sW3 = reinterpret_cast<float*>(sH1 + align1k(tile_bytes(kTile, kHid)));
-  float* sB2 = sW3 + 3 * kHid;
-  float* sB3 = sB2 + kHid;
-  float* sPart = sB3 + 4;  // [128][3] partial layer-3 sums of the upper column half
-  float4* sL3 = reinterpret_cast<float4*>(sPart + 3 * kTile);  // [128] {W3[0][j], W3[1][j], W3[2][j], b2[j]}
+  uint8_t* sW1 = base;                                        // [128 out][K1]   K-major B of layer 1
+  uint8_t* sW2 = sW1 + align1k(tile_bytes(kHid, K1));         // [128 out][144]  K-major B of layer 2 (col 128 = b2)
+  uint8_t* sW3 = sW2 + align1k(tile_bytes(kHid, kHidA));      // [16 out][128]   K-major B of layer 3 (rows >= 3 zero)
+  uint8_t* sXb = sW3 + align1k(tile_bytes(16, kHid));         // 2 x [128 samples][K1] (double-buffered)
+  const uint32_t x_bytes = static_cast<uint32_t>(align1k(tile_bytes(kTile, K1)));
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
-  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init_fence(); }
-  load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3);
-  for (int j = tid; j < kHid; j += blockDim.x)
-    sL3[j] = make_float4(w.W3[j], w.W3[kHid + j], w.W3[2 * kHid + j], w.b2[j]);
+  if (tid == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_init_fence(); }
+  const WPack wl = wpack_layout(K1);
+  copy_to_smem(sW1, wpack, wl.offW3p);      // W1~ | W2~ | W3 tiles, same offsets in shared memory as in the pack
+  for (uint32_t i = tid; i < 2 * x_bytes / 16; i += blockDim.x)   // zero both X buffers once: padding columns stay 0
+    reinterpret_cast<uint4*>(sXb)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 3) sB3[tid] = reinterpret_cast<const float*>(wpack + wl.offB3)[tid];
+  fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tD1 = tmem, tD2 = tmem + 128;
-  MmaCtx ctx{smem_u32(&bar), 0u};
-
-  // software pipeline state (vector path only)
-  const bool vec = ((C | pe_stride) & 3) == 0 && K1 <= 48;
-  const int xr_r = tid & 127, xr_h = tid >> 7;
-  XRegs<3> xr;
-  int ray_next = 0;   // ray index of this thread's row in the tile after the prefetched one
-  auto row_ray = [&](int64_t t) -> int {
-    const int64_t sidx = t * kTile + xr_r;
-    return (t < n_tiles && sidx < count) ? __ldg(s_ray + sidx) : 0;
-  };
-  if (vec) {
-    const int64_t t0 = blockIdx.x;
-    const int ray0 = row_ray(t0);
-    x_load<3>(xr, xr_h, 2, K1, t0 * kTile + xr_r, t0 * kTile + xr_r < count, ray0, feat, C, pe, pe_stride);
-    ray_next = row_ray(t0 + gridDim.x);
+  const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+  const uint32_t tD = tmem, tH = tmem + kFwdTH, tD3 = tmem + kFwdTD3;
+  if (half == 0) {   // K = 128..143 of H: the constant 1 (fp16 0x3C00 in the low half of column 64), written once
+    const uint32_t one[8] = {0x3C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tmem_st8(tH + lane_sel + 64, one);
+    tmem_st_wait();
   }
-  int dbg_n = 0;
+  MmaCtx chain{smem_u32(&bars[0]), 0u};   // L1 / L2 completions (strictly alternating)
+  MmaCtx out3{smem_u32(&bars[1]), 0u};    // L3 completions
+  const uint32_t idesc128 = make_idesc_f16(128, kHid, 0, 0), idesc16 = make_idesc_f16(128, 16, 0, 0);
+
+  // software pipeline over tiles: raw fp32 inputs are loaded into registers two tiles ahead of their use and
+  // converted + stored into the other X buffer in the shadow of the layer-2 MMAs
+  const bool vec = ((C | pe_stride) & 3) == 0 && C <= 16 && pe_stride <= 32;
+  StageRegs sr;
+  const StageGeom sg = stage_geom(C, pe_stride);
+  auto tile_s0 = [&](int64_t t) -> int64_t { return t < n_tiles ? t * kTile : count; };   // past the end: all rows invalid
+  auto load_rays = [&](int64_t t) { if (vec) stage_rays(sr, tid, tile_s0(t), count, s_ray, sg); };
+  auto load_tile = [&](int64_t t) { if (vec) stage_loads(sr, tid, tile_s0(t), count, feat, pe, sg); };
+  auto store_tile = [&](int64_t t, uint8_t* sX) {
+    if (vec) stage_stores(sr, tid, C, K1, sX, sg);
+    else stage_x(sX, K1, t * kTile, count, feat, C, s_ray, pe, pe_stride, tid);
+  };
+  int dbg_n = 1;
   auto stamp = [&]() {  // optional in-kernel timeline (tools/mlp_timeline.py): CTA 0, threads 0 and 255
     if (dbg && blockIdx.x == 0 && (tid == 0 || tid == 255) && dbg_n < 64) dbg[(tid ? 64 : 0) + dbg_n++] = clock64();
   };
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t s0 = tile * kTile;
-    stamp();
-    if (vec) {
-      x_store<3>(xr, xr_h, 2, K1, xr_r, sX);
-      const int64_t tn = tile + gridDim.x;   // prefetch the next tile of this CTA; its loads land during this tile
-      x_load<3>(xr, xr_h, 2, K1, tn * kTile + xr_r, tn < n_tiles && tn * kTile + xr_r < count, ray_next, feat, C, pe,
-                pe_stride);
-      ray_next = row_ray(tn + gridDim.x);
-    } else {
-      stage_x(sX, K1, s0, count, feat, C, s_ray, pe, pe_stride);
-    }
-    stamp();
-    sync_for_mma();
-    stamp();
-    if (warp == 0) {
-      if (elect_one()) {
-        gemm_kk(tD1, smem_u32(sX), K1, smem_u32(sW1), K1, kHid, K1, false);
-        mma_commit(ctx.bar);
-      }
-      __syncwarp();
-    }
-    stamp();
-    mma_wait(ctx);
-    stamp();
-    epi_relu_to_smem(tD1, q, row, half * 64, nullptr, sH1, kHid);
-    stamp();
-    sync_for_mma();
-    stamp();
-    if (warp == 0) {
-      if (elect_one()) {
-        gemm_kk(tD2, smem_u32(sH1), kHid, smem_u32(sW2), kHid, kHid, kHid, false);
-        mma_commit(ctx.bar);
-      }
-      __syncwarp();
-    }
-    stamp();
-    mma_wait(ctx);
-    stamp();
-    // layer-2 epilogue fused with layer 3 (fp32 SIMT, H2 never leaves registers): a third MMA (N = 16) was
-    // measured at ~1700 cycles per tile (8 small MMAs issue at ~85 cycles each + sync + 16-column epilogue)
-    // against ~400 for these FMAs (tools/mlp_timeline.py)
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    {
-      float v[64];
-      tmem_ld64(tD2 + (static_cast<uint32_t>(q * 32) << 16) + half * 64, v);
+  // relu(D[row][64 half .. +64)) -> packed fp16 -> H columns [32 half, +32); then a CTA barrier (the MMA issuer
+  // may read H / overwrite D)
+  auto epilogue_to_h = [&]() {
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float4 t = sL3[half * 64 + j];  // one broadcast 16-byte load per hidden unit
-        const float hv = fmaxf(v[j] + t.w, 0.f);
-        a0 = fmaf(hv, t.x, a0);
-        a1 = fmaf(hv, t.y, a1);
-        a2 = fmaf(hv, t.z, a2);
-      }
+    for (int c = 0; c < 2; ++c) {
+      uint32_t u[16];
+      relu_pack32(tD + lane_sel + half * 64 + c * 32, u);
+      tmem_st16(tH + lane_sel + half * 32 + c * 16, u);
     }
-    stamp();
-    if (half == 1) { sPart[row * 3] = a0; sPart[row * 3 + 1] = a1; sPart[row * 3 + 2] = a2; }
+    tmem_st_wait();
     fence_before_sync();
     __syncthreads();
+    fence_after_sync();
+  };
+  auto issue_l1 = [&](uint32_t buf) {
+    if (warp == 0) {
+      if (elect_one()) {
+        gemm_kk(tD, smem_u32(sXb) + buf * x_bytes, K1, smem_u32(sW1), K1, kHid, K1, false);
+        mma_commit(chain.bar);
+      }
+      __syncwarp();
+    }
+  };
+
+  const int64_t step = gridDim.x;
+  int64_t tile = blockIdx.x;
+  // prologue: tile 0 staged synchronously, tile 1 prefetched into registers, ray indices one tile further ahead
+  load_rays(tile);
+  load_tile(tile);
+  store_tile(tile, sXb);
+  load_rays(tile + step);
+  load_tile(tile + step);
+  sync_for_mma();
+  issue_l1(0u);
+  uint32_t buf = 0u;
+  for (; tile < n_tiles; tile += step, buf ^= 1u) {
+    const int64_t s0 = tile * kTile;
+    const bool has_next = tile + step < n_tiles;
     stamp();
-    if (half == 0 && s0 + row < count) {
-      const float z0 = a0 + sPart[row * 3] + sB3[0];
-      const float z1 = a1 + sPart[row * 3 + 1] + sB3[1];
-      const float z2 = a2 + sPart[row * 3 + 2] + sB3[2];
-      float* __restrict__ o = rgb + (s0 + row) * 3;
-      o[0] = 1.f / (1.f + expf(-z0));
-      o[1] = 1.f / (1.f + expf(-z1));
-      o[2] = 1.f / (1.f + expf(-z2));
-      if (!(fabsf(z0) + fabsf(z1) + fabsf(z2) < 3.0e38f)) counters[1] = counters[1] | 2;  // NaN / inf logit (benign race: every writer sets bit 1)
+    // Ray indices of the tile after next, issued while NO other load of this thread is in flight: the hardware has
+    // six scoreboards per warp, the compiler shares them between loads, and overwriting these registers right after
+    // the tile loads below were issued made the warp wait for ALL of them (15 % of the kernel's stall samples in ncu).
+    if (has_next) load_rays(tile + 2 * step);
+    mma_wait(chain);                                       // L1(tile)
+    stamp();
+    epilogue_to_h();                                       // H1
+    stamp();
+    if (warp == 0) {
+      if (elect_one()) {
+        gemm_ts(tD, tH, desc_kmajor(smem_u32(sW2), kHidA), 256u, idesc128, kHidA / kMmaK, false);
+        mma_commit(chain.bar);
+      }
+      __syncwarp();
+    }
+    // shadow of the layer-2 MMAs: the next tile's X goes into the other buffer (its last reader, L1 of the previous
+    // tile, completed long ago), then the loads of the tile after that are issued
+    if (has_next) {
+      store_tile(tile + step, sXb + (buf ^ 1u) * x_bytes);
+      fence_async_smem();      // BEFORE the loads below are issued: the proxy fence waits for every load in flight
+      load_tile(tile + 2 * step);
     }
     stamp();
-    // sPart is rewritten by the next tile only after two more CTA-wide barriers
+    mma_wait(chain);                                       // L2(tile)
+    stamp();
+    epilogue_to_h();                                       // H2 (b2 came through the constant-1 K step)
+    stamp();
+    if (warp == 0) {
+      if (elect_one()) {
+        gemm_ts(tD3, tH, desc_kmajor(smem_u32(sW3), kHid), 256u, idesc16, kHid / kMmaK, false);
+        mma_commit(out3.bar);
+      }
+      __syncwarp();
+    }
+    if (has_next) issue_l1(buf ^ 1u);                      // L1 of the next tile queues behind L3: D is free, H is not touched
+    mma_wait(out3);                                        // L3(tile)
+    stamp();
+    if (half == 0) {                                       // warp-uniform: tcgen05.ld is warp-collective
+      float z[16];
+      tmem_ld16(tD3 + lane_sel, z);
+      tmem_ld_wait();
+      if (s0 + row < count) {
+        const float z0 = z[0] + sB3[0], z1 = z[1] + sB3[1], z2 = z[2] + sB3[2];
+        float* __restrict__ o = rgb + (s0 + row) * 3;
+        o[0] = __frcp_rn(1.f + expf(-z0));   // correctly rounded reciprocal == 1.f / x without the division's range fix-ups
+        o[1] = __frcp_rn(1.f + expf(-z1));
+        o[2] = __frcp_rn(1.f + expf(-z2));
+        if (!(fabsf(z0) + fabsf(z1) + fabsf(z2) < 3.0e38f)) counters[1] = counters[1] | 2;  // NaN / inf logit
+      }
+    }
+    stamp();
+    // L3 of the next tile is issued two CTA barriers from here, so these D3 reads are ordered before it
   }
   fence_before_sync();
   __syncthreads();
@@ -431,7 +637,7 @@ struct TileCtx {
 
 __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    int32_t* __restrict__ counters, int64_t surv_cap, MlpW w, int K1, int pe_stride,
+    int32_t* __restrict__ counters, int64_t surv_cap, const uint8_t* __restrict__ wpack, int K1, int pe_stride,
     const float* __restrict__ rgb, const float* __restrict__ d_rgb, float grad_scale, float* __restrict__ d_feat,
     MlpG g, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
@@ -454,9 +660,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   uint8_t* ctx_base = sW3t + align1k(tile_bytes(kHid, 16));
   const size_t ctx_bytes = align1k(tile_bytes(kTile, K1)) + align1k(tile_bytes(kTile, kHidA)) +
                            align1k(tile_bytes(kTile, kHid)) + align1k(tile_bytes(kTile, 16));
-  float* sW3 = reinterpret_cast<float*>(ctx_base + 2 * ctx_bytes);
-  float* sB2 = sW3 + 3 * kHid;
-  float* sB3 = sB2 + kHid;
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
   if (tid == 0) {
@@ -466,10 +669,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     mbar_init(smem_u32(&bars[3]), kBwdEpiThreads);
     mbar_init_fence();
   }
-  load_weights(w, d_in, K1, sW1, sW2, sW3, sB2, sB3, kHidA);
+  const WPack wl = wpack_layout(K1);
+  copy_to_smem(sW1, wpack, wl.offW3);                         // W1~ | W2~ tiles (fp16, packed once per step)
+  copy_to_smem(sW3t, wpack + wl.offW3t, tile_bytes(kHid, 16));
   for (int i = tid; i < kTile * 16; i += blockDim.x) {
     const int j = i / 16, c = i % 16;
-    *reinterpret_cast<__half*>(sW3t + tile_off(j, c, 16)) = half_sat(c < 3 ? w.W3[c * kHid + j] : 0.f);
     // columns 128..143 of both H1 tiles: the constant 1 (b2 rides the layer-2 GEMM, db2 the dW2 GEMM), then 0;
     // the epilogues only ever write columns < 128
     for (int cx_i = 0; cx_i < 2; ++cx_i) {
@@ -477,6 +681,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       *reinterpret_cast<__half*>(h1 + tile_off(j, kHid + c, kHidA)) = __float2half_rn(c == 0 ? 1.f : 0.f);
     }
   }
+  fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -513,14 +718,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   auto stage_load = [&](TileCtx& c, Staged& st, int ray) {
     const int64_t sidx = c.s0 + row;
     c.valid = sidx < count;
-    if (vecx) {
-      x_load<2>(st.x, part, 4, K1, sidx, c.valid, ray, feat, C, pe, pe_stride);
-    }
+    // (1) define every destination, (2) fence, (3) all loads back to back -- see ldg_nc_f4_if
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st.x.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { st.o[k] = 0.f; st.d[k] = 0.f; }
-    if (part == 0 && c.valid) {
+    reg_fence(st.x.v[0], st.x.v[1], st.x.v[2], st.x.v[3]);
+    reg_fence(st.o[0], st.o[1], st.o[2], st.d[0], st.d[1], st.d[2]);
+    if (vecx) {
+      const float* __restrict__ f = feat + sidx * C;
+      const float* __restrict__ e = pe + static_cast<int64_t>(ray) * pe_stride;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { st.o[k] = __ldg(rgb + sidx * 3 + k); st.d[k] = __ldg(d_rgb + sidx * 3 + k); }
+      for (int k = 0; k < 2; ++k) {
+        const int ch = part + 4 * k;
+#pragma unroll
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const int cc = ch * 8 + g2 * 4;
+          const bool in = c.valid && ch * 8 < K1 && cc < C + pe_stride;
+          const float* src = cc < C ? f + cc : e + (cc - C);
+          ldg_nc_f4_if(st.x.v[2 * k + g2], reinterpret_cast<const float4*>(in ? src : feat), in);
+        }
+      }
+    }
+    const bool want = part == 0 && c.valid;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ldg_nc_f32_if(st.o[k], want ? rgb + sidx * 3 + k : rgb, want);
+      ldg_nc_f32_if(st.d[k], want ? d_rgb + sidx * 3 + k : d_rgb, want);
     }
   };
   auto stage_store = [&](TileCtx& c, const Staged& st, int ray) {
@@ -680,14 +904,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     stage_load(A, stA, rayA);
     stage_load(B, stB, rayB);
     int rA = rayA, rB = rayB;
-    rayA = ray_of(A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
-    rayB = ray_of(B.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       stamp();
       stage_store(A, stA, rA); publish(A);
       stage_store(B, stB, rB); publish(B);
       const bool validA = A.valid, validB = B.valid;
       const int64_t s0A = A.s0, s0B = B.s0;
+      // ray indices of the NEXT pair, loaded here where no other load of this thread is in flight (the staged values
+      // have just been consumed): issued right after the tile loads further down, the overwrite of these registers
+      // waited for all of them -- the six per-warp scoreboards are shared -- ~4500 cycles per pair in the timeline
+      rayA = ray_of(A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
+      rayB = ray_of(B.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
+      {   // next pair -> L2: thread (row, part) touches tile A (part 0,1) or B (part 2,3): features / rgb + d_rgb rows
+        const int64_t s2 = A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile + (part >> 1) * kTile + row;
+        if (s2 < count) {
+          if ((part & 1) == 0) prefetch_l2(feat + s2 * C);
+          else { prefetch_l2(rgb + s2 * 3); prefetch_l2(d_rgb + s2 * 3); }
+        }
+      }
       stamp();
       mma_wait(A.bar); stamp(); epi_relu(A, nullptr, A.sH1, kHidA); publish(A); stamp();
       mma_wait(B.bar); stamp(); epi_relu(B, nullptr, B.sH1, kHidA); publish(B); stamp();
@@ -695,22 +929,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       mma_wait(B.bar); stamp(); epi_relu(B, nullptr, B.sH2, kHid); publish(B); stamp();
       mma_wait(A.bar); stamp(); epi_mask(A, A.sH2, kHid); publish(A); stamp();
       mma_wait(B.bar); stamp(); epi_mask(B, B.sH2, kHid); publish(B); stamp();
-      // prefetch the next pair (registers only; the tiles are still in use)
+      mma_wait(A.bar); stamp(); epi_mask(A, A.sH1, kHidA); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_mask(B, B.sH1, kHidA); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_dx(A);   // the last batch of the pair has completed: tiles may be re-staged
+      mma_wait(B.bar); stamp(); epi_dx(B); stamp();
+      // The next pair's inputs were pulled into L2 at the top of this iteration (prefetch.global.L2: no register, no
+      // scoreboard); load them now, when nothing else of this thread is in flight.  Holding them in registers across
+      // the epilogues instead (round 1) cost ~3000-4000 cycles per pair: a warp has six scoreboards, ptxas shares them
+      // between global loads, tcgen05.ld and ld.shared, and every tcgen05.wait::ld / fence.proxy.async issued while
+      // the prefetch was in flight waited for it (tools/mlp_timeline.py: the stall followed the prefetch wherever it
+      // was moved).
       A.s0 = (2 * (pair + gridDim.x)) * kTile;
       B.s0 = A.s0 + kTile;
       stage_load(A, stA, rayA);
       stage_load(B, stB, rayB);
       rA = rayA; rB = rayB;
-      rayA = ray_of(A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
-      rayB = ray_of(B.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
-      const bool nvA = A.valid, nvB = B.valid;
-      const int64_t nsA = A.s0, nsB = B.s0;
-      A.valid = validA; A.s0 = s0A; B.valid = validB; B.s0 = s0B;   // the current pair's identity for epi_dx
-      mma_wait(A.bar); stamp(); epi_mask(A, A.sH1, kHidA); publish(A); stamp();
-      mma_wait(B.bar); stamp(); epi_mask(B, B.sH1, kHidA); publish(B); stamp();
-      mma_wait(A.bar); stamp(); epi_dx(A);   // the last batch of the pair has completed: tiles may be re-staged
-      mma_wait(B.bar); stamp(); epi_dx(B); stamp();
-      A.valid = nvA; A.s0 = nsA; B.valid = nvB; B.s0 = nsB;
     }
   }
   fence_before_sync();
@@ -763,8 +996,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
 }
 
 static inline size_t mlp_fwd_smem(int K1) {
-  return 1024 + ((tile_bytes(kHid, K1) + 1023) & ~1023u) + tile_bytes(kHid, kHid) + ((tile_bytes(kTile, K1) + 1023) & ~1023u) +
-         tile_bytes(kTile, kHid) + (3 * kHid + kHid + 4 + 3 * kTile + 4 * kHid) * sizeof(float) + 64;
+  auto a1k = [](size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); };
+  return 1024 + a1k(tile_bytes(kHid, K1)) + a1k(tile_bytes(kHid, kHidA)) + a1k(tile_bytes(16, kHid)) + 2 * a1k(tile_bytes(kTile, K1)) + 64;
 }
 static inline size_t mlp_bwd_smem(int K1) {
   auto a1k = [](size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); };
@@ -1020,9 +1253,169 @@ __global__ void __launch_bounds__(128) tc_ts_probe_kernel(const float* __restric
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// TMEM -> register read-rate probe: `nwarps` warps each issue `reps` x (4 x tcgen05.ld 32x32b.x16 = 8 KB) from their own
+// lane quarter; out[0] = clock64 cycles of the slowest warp, out[1] = bytes read by the CTA.  mode 1: 2 x .x32, mode 2:
+// 1 x .x64 (same bytes per iteration).
+__global__ void __launch_bounds__(1024) tc_ldtm_rate_kernel(int reps, int mode, long long* __restrict__ out) {
+  __shared__ uint32_t tmem_base_s;
+  __shared__ long long t_max;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (threadIdx.x == 0) t_max = 0;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t t = tmem_base_s + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) & 7) * 64;
+  float acc = 0.f;
+  const long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    if (mode == 0) {
+      float v[64];
+      tmem_ld16(t, v); tmem_ld16(t + 16, v + 16); tmem_ld16(t + 32, v + 32); tmem_ld16(t + 48, v + 48);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 64; j += 16) acc += v[j];
+    } else if (mode == 1) {
+      uint32_t u[64];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(u[32 * h + 0]), "=r"(u[32 * h + 1]), "=r"(u[32 * h + 2]), "=r"(u[32 * h + 3]), "=r"(u[32 * h + 4]),
+              "=r"(u[32 * h + 5]), "=r"(u[32 * h + 6]), "=r"(u[32 * h + 7]), "=r"(u[32 * h + 8]), "=r"(u[32 * h + 9]),
+              "=r"(u[32 * h + 10]), "=r"(u[32 * h + 11]), "=r"(u[32 * h + 12]), "=r"(u[32 * h + 13]), "=r"(u[32 * h + 14]),
+              "=r"(u[32 * h + 15]), "=r"(u[32 * h + 16]), "=r"(u[32 * h + 17]), "=r"(u[32 * h + 18]), "=r"(u[32 * h + 19]),
+              "=r"(u[32 * h + 20]), "=r"(u[32 * h + 21]), "=r"(u[32 * h + 22]), "=r"(u[32 * h + 23]), "=r"(u[32 * h + 24]),
+              "=r"(u[32 * h + 25]), "=r"(u[32 * h + 26]), "=r"(u[32 * h + 27]), "=r"(u[32 * h + 28]), "=r"(u[32 * h + 29]),
+              "=r"(u[32 * h + 30]), "=r"(u[32 * h + 31])
+            : "r"(t + 32 * h));
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 64; j += 16) acc += __uint_as_float(u[j]);
+    } else {   // 16x256b.x4: 16 lanes x 256 bits per repeat -> this warp's 32 lanes need two (lane halves)
+      uint32_t u[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(u[16 * h + 0]), "=r"(u[16 * h + 1]), "=r"(u[16 * h + 2]), "=r"(u[16 * h + 3]), "=r"(u[16 * h + 4]),
+              "=r"(u[16 * h + 5]), "=r"(u[16 * h + 6]), "=r"(u[16 * h + 7]), "=r"(u[16 * h + 8]), "=r"(u[16 * h + 9]),
+              "=r"(u[16 * h + 10]), "=r"(u[16 * h + 11]), "=r"(u[16 * h + 12]), "=r"(u[16 * h + 13]), "=r"(u[16 * h + 14]),
+              "=r"(u[16 * h + 15])
+            : "r"(t + (static_cast<uint32_t>(16 * h) << 16)));
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) acc += __uint_as_float(u[j]);
+    }
+  }
+  const long long dt = clock64() - t0;
+  atomicMax(reinterpret_cast<unsigned long long*>(&t_max), static_cast<unsigned long long>(dt));
+  if (acc == 123.456f) out[2] = 1;   // keep the loads alive
+  fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[0] = t_max;
+    out[1] = static_cast<long long>(blockDim.x / 32) * reps * (mode == 2 ? 4096 : 8192);
+  }
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
+// What does a running tensor pipe take away from the other warps?  Warp 0 issues `n_mma` MMAs back to back (mma_mode 0:
+// none, 1: SS N=128, 2: TS N=128, 3: SS N=16, 4: TS N=16) while warps 1..8 each run `reps` iterations of simt_mode
+// 0: dependent FFMAs, 1: 4 x st.shared.v4, 2: 4 x ld.shared.v4, 3: 4 x ld.global.v4 (L2-resident), 4: 4 x tcgen05.ld x16.
+// out[0] = cycles of the slowest SIMT warp, out[1] = cycles of the MMA batch (issue to completion).
+__global__ void __launch_bounds__(288) tc_contention_kernel(int mma_mode, int n_mma, int simt_mode, int reps,
+                                                            const float4* __restrict__ gbuf, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ long long t_simt, t_mma;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sA = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  uint8_t* sB = sA + 32 * 1024;
+  uint8_t* sS = sB + 32 * 1024;   // 32 KB scratch for the SIMT warps
+  for (int i = tid; i < 24 * 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(sA)[i] = 0u;
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init_fence(); t_simt = 0; t_mma = 0; }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0) {
+    if (mma_mode && elect_one()) {
+      const int N = mma_mode <= 2 ? 128 : 16;
+      const uint32_t idesc = make_idesc_f16(128, N, 0, 0);
+      const uint64_t a0 = desc_kmajor(smem_u32(sA), 128), b0 = desc_kmajor(smem_u32(sB), 128);
+      const long long t0 = clock64();
+      for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (mma_mode & 1) mma_f16(tmem, a0 + k * 16, b0 + k * 16, idesc, 1u);
+          else mma_f16_ts(tmem, tmem + 256 + 8 * k, b0 + k * 16, idesc, 1u);
+        }
+      }
+      mma_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), 0);
+      t_mma = clock64() - t0;
+    }
+    __syncwarp();
+  } else {
+    float acc = 0.f;
+    uint4* sp = reinterpret_cast<uint4*>(sS) + (warp - 1) * 128 + lane;   // 2 KB per warp, conflict-free
+    const uint32_t t = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 384 + ((warp - 1) >> 2) * 64;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (simt_mode == 0) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc = fmaf(acc, 1.0001f, 0.5f);
+      } else if (simt_mode == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sp[32 * k] = make_uint4(r, k, lane, warp);
+      } else if (simt_mode == 2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const uint4 v = sp[32 * k]; acc += __uint_as_float(v.x ^ v.w); }
+      } else if (simt_mode == 3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float4 v = __ldg(gbuf + ((r * 4 + k) & 255) * 256 + (warp - 1) * 32 + lane); acc += v.x + v.w; }
+      } else {
+        float v[64];
+        tmem_ld16(t, v); tmem_ld16(t + 16, v + 16); tmem_ld16(t + 32, v + 32); tmem_ld16(t + 48, v + 48);
+        tmem_ld_wait();
+        acc += v[0] + v[17] + v[34] + v[51];
+      }
+    }
+    const long long dt = clock64() - t0;
+    atomicMax(reinterpret_cast<unsigned long long*>(&t_simt), static_cast<unsigned long long>(dt));
+    if (acc == 123.456f) out[3] = 1;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid == 0) { out[0] = t_simt; out[1] = t_mma; }
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace dvgo
 
 using namespace dvgo;
+
+DVGO_API int dvgo_tc_contention(int mma_mode, int n_mma, int simt_mode, int reps, const void* gbuf, long long* out,
+                                dvgo_stream_t stream) {
+  if (mma_mode < 0 || mma_mode > 4 || simt_mode < 0 || simt_mode > 4 || n_mma < 0 || reps < 1 || !gbuf || !out) return DVGO_EINVAL;
+  const size_t bytes = 97 * 1024 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tc_contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  tc_contention_kernel<<<1, 288, bytes, as_stream(stream)>>>(mma_mode, n_mma, simt_mode, reps,
+                                                             static_cast<const float4*>(gbuf), out);
+  return launch_status();
+}
+
+DVGO_API int dvgo_tc_ldtm_rate(int nwarps, int reps, int mode, long long* out, dvgo_stream_t stream) {
+  if (nwarps < 1 || nwarps > 32 || reps < 1 || mode < 0 || mode > 2 || !out) return DVGO_EINVAL;
+  tc_ldtm_rate_kernel<<<1, nwarps * 32, 0, as_stream(stream)>>>(reps, mode, out);
+  return launch_status();
+}
 
 DVGO_API int dvgo_tc_ts_probe(const float* A, const float* B, float* D, int N, int K, int b_mn, int reps,
                               long long* cycles, dvgo_stream_t stream) {
@@ -1061,25 +1454,27 @@ DVGO_API int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, i
 
 static inline int mlp_k1(int C, int pe_stride) { return ((C + pe_stride + 15) / 16) * 16; }
 
-DVGO_API int dvgo_mlp_fwd_timed(const float*, int, const int32_t*, const float*, int, int, int32_t*, int64_t, const float*,
-                                const float*, const float*, const float*, const float*, const float*, int, float*, long long*,
-                                dvgo_stream_t);
+DVGO_API int64_t dvgo_mlp_wpack_bytes(int C, int pe_stride) {
+  if (C < 0 || pe_stride < 1 || C + pe_stride > 64) return DVGO_EINVAL;
+  return static_cast<int64_t>(wpack_layout(mlp_k1(C, pe_stride)).total);
+}
 
-DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                          int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
-                          const float* W2, const float* b2, const float* W3, const float* b3, int width, float* rgb,
-                          dvgo_stream_t stream) {
-  return dvgo_mlp_fwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, W1, b1, W2, b2, W3, b3, width, rgb,
-                            nullptr, stream);
+DVGO_API int dvgo_mlp_pack_weights(int C, int P, int pe_stride, const float* W1, const float* b1, const float* W2,
+                                   const float* b2, const float* W3, const float* b3, int width, void* wpack,
+                                   dvgo_stream_t stream) {
+  if (width != kHid || C < 0 || P < 0 || C + P < 1 || C + P > 63 || pe_stride < P + 1) return DVGO_EINVAL;
+  if (!W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !wpack) return DVGO_EINVAL;
+  const int K1 = mlp_k1(C, pe_stride);
+  MlpW w{W1, b1, W2, b2, W3, b3};
+  mlp_pack_weights_kernel<<<32, 256, 0, as_stream(stream)>>>(w, C + P, K1, static_cast<uint8_t*>(wpack));
+  return launch_status();
 }
 
 DVGO_API int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                                int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
-                                const float* W2, const float* b2, const float* W3, const float* b3, int width,
-                                float* rgb, long long* timeline, dvgo_stream_t stream) {
-  if (width != kHid || C < 0 || P < 0 || C + P < 1 || C + P > 63 || surv_cap < 0 || pe_stride < P + 1) return DVGO_EINVAL;
-  if (!feat || !s_ray || (P > 0 && !pe) || !counters || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !rgb)
-    return DVGO_EINVAL;
+                                int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb, long long* timeline,
+                                dvgo_stream_t stream) {
+  if (C < 0 || P < 0 || C + P < 1 || C + P > 63 || surv_cap < 0 || pe_stride < P + 1) return DVGO_EINVAL;
+  if (!feat || !s_ray || (P > 0 && !pe) || !counters || !wpack || !rgb) return DVGO_EINVAL;
   if (surv_cap == 0) return 0;
   const int K1 = mlp_k1(C, pe_stride);
   const size_t bytes = mlp_fwd_smem(K1);
@@ -1087,36 +1482,25 @@ DVGO_API int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, 
   if (e != cudaSuccess) return static_cast<int>(e);
   const int64_t tiles = (surv_cap + kTile - 1) / kTile;
   const int grid = static_cast<int>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
-  MlpW w{W1, b1, W2, b2, W3, b3};
-  mlp_fwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, pe_stride, rgb,
+  mlp_fwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap,
+                                                                 static_cast<const uint8_t*>(wpack), K1, pe_stride, rgb,
                                                                  timeline);
   return launch_status();
 }
 
-DVGO_API int dvgo_mlp_bwd_timed(const float*, int, const int32_t*, const float*, int, int, int32_t*, int64_t, const float*,
-                                const float*, const float*, const float*, const float*, const float*, int, const float*,
-                                const float*, float, float*, float*, float*, float*, float*, float*, float*, long long*,
-                                dvgo_stream_t);
-
-DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                          int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
-                          const float* W2, const float* b2, const float* W3, const float* b3, int width,
-                          const float* rgb, const float* d_rgb, float grad_scale, float* d_feat, float* gW1,
-                          float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, dvgo_stream_t stream) {
-  return dvgo_mlp_bwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, W1, b1, W2, b2, W3, b3, width, rgb, d_rgb,
-                            grad_scale, d_feat, gW1, gb1, gW2, gb2, gW3, gb3, nullptr, stream);
+DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
+                          int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb, dvgo_stream_t stream) {
+  return dvgo_mlp_fwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, wpack, rgb, nullptr, stream);
 }
 
 DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                                int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
-                                const float* W2, const float* b2, const float* W3, const float* b3, int width,
-                                const float* rgb, const float* d_rgb, float grad_scale, float* d_feat, float* gW1,
-                                float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, long long* timeline,
-                                dvgo_stream_t stream) {
-  if (width != kHid || C < 1 || C > 16 || P < 0 || C + P > 63 || surv_cap < 0 || !(grad_scale > 0.f) || pe_stride < P + 1)
+                                int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb,
+                                const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
+                                float* gb2, float* gW3, float* gb3, long long* timeline, dvgo_stream_t stream) {
+  if (C < 1 || C > 16 || P < 0 || C + P > 63 || surv_cap < 0 || !(grad_scale > 0.f) || pe_stride < P + 1)
     return DVGO_EINVAL;
-  if (!feat || !s_ray || (P > 0 && !pe) || !counters || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !rgb || !d_rgb ||
-      !d_feat || !gW1 || !gb1 || !gW2 || !gb2 || !gW3 || !gb3)
+  if (!feat || !s_ray || (P > 0 && !pe) || !counters || !wpack || !rgb || !d_rgb || !d_feat || !gW1 || !gb1 || !gW2 ||
+      !gb2 || !gW3 || !gb3)
     return DVGO_EINVAL;
   if (surv_cap == 0) return 0;
   const int K1 = mlp_k1(C, pe_stride);
@@ -1126,11 +1510,19 @@ DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, 
   const int64_t tiles = (surv_cap + kTile - 1) / kTile;
   const int64_t pairs = (tiles + 1) / 2;
   const int grid = static_cast<int>(pairs < kNumSMs ? pairs : kNumSMs);
-  MlpW w{W1, b1, W2, b2, W3, b3};
   MlpG g{gW1, gb1, gW2, gb2, gW3, gb3};
-  mlp_bwd_kernel<<<grid, kBwdThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap, w, K1, pe_stride,
-                                                                 rgb, d_rgb, grad_scale, d_feat, g, timeline);
+  mlp_bwd_kernel<<<grid, kBwdThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap,
+                                                                 static_cast<const uint8_t*>(wpack), K1, pe_stride, rgb,
+                                                                 d_rgb, grad_scale, d_feat, g, timeline);
   return launch_status();
+}
+
+DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
+                          int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
+                          float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
+                          float* gb3, dvgo_stream_t stream) {
+  return dvgo_mlp_bwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, wpack, rgb, d_rgb, grad_scale, d_feat,
+                            gW1, gb1, gW2, gb2, gW3, gb3, nullptr, stream);
 }
 
 DVGO_API int dvgo_tc_rate(int ctas, int N, int ksteps, int reps, int a_mn, int b_mn, int a_lbo, int a_sbo, int a_kstep,

@@ -49,6 +49,21 @@ std::vector<Tensor> tc_ts_probe(Tensor A, Tensor B, int N, int K, bool b_mn, int
   return {D, cyc};
 }
 
+Tensor tc_contention(int mma_mode, int n_mma, int simt_mode, int reps) {
+  auto out = torch::zeros({4}, torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA));
+  auto gbuf = torch::ones({1 << 18}, torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA));
+  rc_check(dvgo_tc_contention(mma_mode, n_mma, simt_mode, reps, gbuf.data_ptr(),
+                              reinterpret_cast<long long*>(out.data_ptr<int64_t>()), cur_stream()), "tc_contention");
+  return out;
+}
+
+Tensor tc_ldtm_rate(int nwarps, int reps, int mode) {
+  auto out = torch::zeros({3}, torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA));
+  rc_check(dvgo_tc_ldtm_rate(nwarps, reps, mode, reinterpret_cast<long long*>(out.data_ptr<int64_t>()), cur_stream()),
+           "tc_ldtm_rate");
+  return out;
+}
+
 Tensor tc_rate(int ctas, int N, int ksteps, int reps, bool a_mn, bool b_mn, int a_lbo, int a_sbo, int a_kstep, int b_lbo,
                int b_sbo, int b_kstep, int layout, int n_accum) {
   auto out = torch::zeros({ctas}, torch::TensorOptions().dtype(torch::kInt64).device(torch::kCUDA));
@@ -82,36 +97,55 @@ inline Offsets offsets(int d_in, int width) {
   return o;
 }
 
-void mlp_fwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb) {
+// params (fp32 masters) -> wpack (fp16 operand tiles, uint8 tensor of mlp_wpack_bytes(C, pe_stride) bytes)
+int64_t mlp_wpack_bytes(int C, int pe_stride) { return dvgo_mlp_wpack_bytes(C, pe_stride); }
+
+void mlp_pack(Tensor params, int C, int P, int pe_stride, int width, Tensor wpack) {
+  chkf(params, "params");
+  const Offsets o = offsets(C + P, width);
+  TORCH_CHECK(params.numel() == o.total, "params has the wrong size");
+  TORCH_CHECK(wpack.is_cuda() && wpack.is_contiguous() && wpack.scalar_type() == torch::kUInt8 &&
+              wpack.numel() >= dvgo_mlp_wpack_bytes(C, pe_stride), "wpack: uint8 CUDA tensor of mlp_wpack_bytes bytes");
+  const c10::cuda::CUDAGuard guard(params.device());
+  const float* p = params.data_ptr<float>();
+  rc_check(dvgo_mlp_pack_weights(C, P, pe_stride, p + o.W1, p + o.b1, p + o.W2, p + o.b2, p + o.W3, p + o.b3, width,
+                                 wpack.data_ptr(), cur_stream()), "mlp_pack_weights");
+}
+
+// wpack = None: pack into a temporary (tests / one-off calls); the trainer keeps a persistent pack per step
+Tensor ensure_pack(c10::optional<Tensor> wpack, const Tensor& params, int C, int P, int pe_stride, int width) {
+  if (wpack.has_value()) return *wpack;
+  auto t = torch::empty({dvgo_mlp_wpack_bytes(C, pe_stride)}, params.options().dtype(torch::kUInt8));
+  mlp_pack(params, C, P, pe_stride, width, t);
+  return t;
+}
+
+void mlp_fwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb,
+             c10::optional<Tensor> wpack) {
   chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
   chkf(rgb, "rgb");
   const int C = feat.size(1), pe_stride = pe.size(1);
-  const Offsets o = offsets(C + P, width);
-  TORCH_CHECK(params.numel() == o.total, "params has the wrong size");
   const int64_t cap = s_ray.numel();
   TORCH_CHECK(feat.size(0) >= cap && rgb.numel() >= cap * 3, "stream buffers too small");
   const c10::cuda::CUDAGuard guard(feat.device());
-  const float* p = params.data_ptr<float>();
+  Tensor wp = ensure_pack(wpack, params, C, P, pe_stride, width);
   rc_check(dvgo_mlp_fwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
-                        counters.data_ptr<int32_t>(), cap, p + o.W1, p + o.b1, p + o.W2, p + o.b2, p + o.W3, p + o.b3,
-                        width, rgb.data_ptr<float>(), cur_stream()), "mlp_fwd");
+                        counters.data_ptr<int32_t>(), cap, wp.data_ptr(), rgb.data_ptr<float>(), cur_stream()), "mlp_fwd");
 }
 
 Tensor mlp_fwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb) {
   const int C = feat.size(1), pe_stride = pe.size(1);
-  const Offsets o = offsets(C + P, width);
   const c10::cuda::CUDAGuard guard(feat.device());
   auto tl = torch::zeros({128}, feat.options().dtype(torch::kInt64));
-  const float* p = params.data_ptr<float>();
+  Tensor wp = ensure_pack(c10::nullopt, params, C, P, pe_stride, width);
   rc_check(dvgo_mlp_fwd_timed(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
-                              counters.data_ptr<int32_t>(), s_ray.numel(), p + o.W1, p + o.b1, p + o.W2, p + o.b2,
-                              p + o.W3, p + o.b3, width, rgb.data_ptr<float>(),
+                              counters.data_ptr<int32_t>(), s_ray.numel(), wp.data_ptr(), rgb.data_ptr<float>(),
                               reinterpret_cast<long long*>(tl.data_ptr<int64_t>()), cur_stream()), "mlp_fwd_timed");
   return tl;
 }
 
 void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb, Tensor d_rgb,
-             double grad_scale, Tensor d_feat, Tensor grads) {
+             double grad_scale, Tensor d_feat, Tensor grads, c10::optional<Tensor> wpack) {
   chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
   chkf(rgb, "rgb"); chkf(d_rgb, "d_rgb"); chkf(d_feat, "d_feat"); chkf(grads, "grads");
   const int C = feat.size(1), pe_stride = pe.size(1);
@@ -119,13 +153,12 @@ void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tenso
   TORCH_CHECK(params.numel() == o.total && grads.numel() == o.total, "params/grads have the wrong size");
   const int64_t cap = s_ray.numel();
   const c10::cuda::CUDAGuard guard(feat.device());
-  const float* p = params.data_ptr<float>();
+  Tensor wp = ensure_pack(wpack, params, C, P, pe_stride, width);
   float* g = grads.data_ptr<float>();
   rc_check(dvgo_mlp_bwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
-                        counters.data_ptr<int32_t>(), cap, p + o.W1, p + o.b1, p + o.W2, p + o.b2, p + o.W3, p + o.b3,
-                        width, rgb.data_ptr<float>(), d_rgb.data_ptr<float>(), static_cast<float>(grad_scale),
-                        d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3,
-                        cur_stream()), "mlp_bwd");
+                        counters.data_ptr<int32_t>(), cap, wp.data_ptr(), rgb.data_ptr<float>(), d_rgb.data_ptr<float>(),
+                        static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2, g + o.b2,
+                        g + o.W3, g + o.b3, cur_stream()), "mlp_bwd");
 }
 
 Tensor mlp_bwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb,
@@ -134,14 +167,13 @@ Tensor mlp_bwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor coun
   const Offsets o = offsets(C + P, width);
   const c10::cuda::CUDAGuard guard(feat.device());
   auto tl = torch::zeros({128}, feat.options().dtype(torch::kInt64));
-  const float* p = params.data_ptr<float>();
+  Tensor wp = ensure_pack(c10::nullopt, params, C, P, pe_stride, width);
   float* g = grads.data_ptr<float>();
   rc_check(dvgo_mlp_bwd_timed(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
-                              counters.data_ptr<int32_t>(), s_ray.numel(), p + o.W1, p + o.b1, p + o.W2, p + o.b2,
-                              p + o.W3, p + o.b3, width, rgb.data_ptr<float>(), d_rgb.data_ptr<float>(),
-                              static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2,
-                              g + o.b2, g + o.W3, g + o.b3, reinterpret_cast<long long*>(tl.data_ptr<int64_t>()),
-                              cur_stream()), "mlp_bwd_timed");
+                              counters.data_ptr<int32_t>(), s_ray.numel(), wp.data_ptr(), rgb.data_ptr<float>(),
+                              d_rgb.data_ptr<float>(), static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1,
+                              g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3,
+                              reinterpret_cast<long long*>(tl.data_ptr<int64_t>()), cur_stream()), "mlp_bwd_timed");
   return tl;
 }
 }  // namespace
@@ -151,9 +183,18 @@ void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("tc_probe", &tc_probe);
   m.def("tc_rate", &tc_rate);
   m.def("tc_ts_probe", &tc_ts_probe);
+  m.def("tc_ldtm_rate", &tc_ldtm_rate);
+  m.def("tc_contention", &tc_contention);
   m.def("view_embedding", &view_embedding);
-  m.def("mlp_fwd", &mlp_fwd);
+  m.def("mlp_wpack_bytes", &mlp_wpack_bytes);
+  m.def("mlp_pack", &mlp_pack);
+  m.def("mlp_fwd", &mlp_fwd, pybind11::arg("feat"), pybind11::arg("s_ray"), pybind11::arg("pe"), pybind11::arg("P"),
+        pybind11::arg("counters"), pybind11::arg("params"), pybind11::arg("width"), pybind11::arg("rgb"),
+        pybind11::arg("wpack") = pybind11::none());
   m.def("mlp_fwd_timeline", &mlp_fwd_timeline);
-  m.def("mlp_bwd", &mlp_bwd);
+  m.def("mlp_bwd", &mlp_bwd, pybind11::arg("feat"), pybind11::arg("s_ray"), pybind11::arg("pe"), pybind11::arg("P"),
+        pybind11::arg("counters"), pybind11::arg("params"), pybind11::arg("width"), pybind11::arg("rgb"),
+        pybind11::arg("d_rgb"), pybind11::arg("grad_scale"), pybind11::arg("d_feat"), pybind11::arg("grads"),
+        pybind11::arg("wpack") = pybind11::none());
   m.def("mlp_bwd_timeline", &mlp_bwd_timeline);
 }

@@ -171,6 +171,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar_saddr, uint32_t parity) {
   }
 }
 
+// Non-blocking test of an mbarrier phase (the polling MMA issuer serves whichever tile context is ready first).
+__device__ __forceinline__ bool mbar_test(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar_saddr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 // TMEM allocation (one full warp executes these).
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_saddr, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_saddr), "r"(ncols)

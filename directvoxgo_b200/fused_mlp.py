@@ -64,16 +64,29 @@ class TensorCoreMLP:
         self._P = P
         return ext.view_embedding(viewdirs.contiguous(), viewfreq, (P + 1 + 3) // 4 * 4)
 
+    def pack(self, C, pe_stride):
+        """fp32 master weights -> the fp16 operand tiles the kernels bulk-copy (one tiny kernel; called by forward(),
+        reused by backward() of the same step: the masters only change in adam_step)."""
+        key = (C, pe_stride)
+        if getattr(self, "_wpack_key", None) != key:
+            self._wpack = torch.empty(ext.mlp_wpack_bytes(C, pe_stride), dtype=torch.uint8, device=self.params.device)
+            self._wpack_key = key
+        ext.mlp_pack(self.params, C, self.d_in - C, pe_stride, self.WIDTH, self._wpack)
+        return self._wpack
+
     def forward(self, feat, s_ray, pe_pad, counters, rgb):
-        ext.mlp_fwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb)
+        wp = self.pack(feat.shape[1], pe_pad.shape[1])
+        ext.mlp_fwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb, wp)
 
     def backward(self, feat, s_ray, pe_pad, counters, rgb, d_rgb, d_feat, n_global):
         """Accumulates weight gradients into self.grad_flat (zeroed here) and writes d_feat."""
         ext.zero_(self.grad_flat)
         # d_rgb <= ~2/(3 n_global): scale so that the largest FP16 backward operand is O(100)
         scale = 2.0 ** math.floor(math.log2(256.0 * n_global))
+        wp = self._wpack if getattr(self, "_wpack_key", None) == (feat.shape[1], pe_pad.shape[1]) else \
+            self.pack(feat.shape[1], pe_pad.shape[1])
         ext.mlp_bwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb, d_rgb,
-                    scale, d_feat, self.grad_flat)
+                    scale, d_feat, self.grad_flat, wp)
 
     def adam_step(self, step, beta1, beta2, lr, eps):
         adam_upd_cuda.adam_upd(self.params, self.grad_flat, self.exp_avg, self.exp_avg_sq, step, beta1, beta2, lr, eps)

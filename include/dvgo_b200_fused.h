@@ -181,38 +181,40 @@ int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G, dvgo_s
 /* rgbnet on the tensor cores (fused_mlp.cu): x = [feat (C) | pe[s_ray] (P)] -> Linear(C+P, 128) -> ReLU
  * -> Linear(128,128) -> ReLU -> Linear(128,3) -> sigmoid   (lib/dvgo.py:123-131, :524-539 with
  * rgbnet_direct=True, rgbnet_depth=3, rgbnet_width=128 -- the configs' default).
- * feat [surv_cap,C], s_ray [surv_cap] int32, counters[0] = M4.  pe [n_rays, pe_stride] is the per-ray view
- * embedding table padded so that column P holds the constant 1 (it carries b1 through the first GEMM) and the
- * remaining columns are 0; pe_stride >= P+1, a multiple of 4 enables 16-byte loads.
- * Weights are fp32 in torch nn.Linear layout ([out][in]); GEMM operands are rounded to FP16, accumulation
- * is fp32.  rgb [surv_cap,3].  width must be 128 (DVGO_EINVAL otherwise: the caller falls back). */
+ * feat [surv_cap,C], s_ray [surv_cap] int32, counters[0] = M4, counters[1] |= 2 on a non-finite value.
+ * pe [n_rays, pe_stride] is the per-ray view embedding table padded so that column P holds the constant 1 (it
+ * carries b1 through the first GEMM) and the remaining columns are 0; pe_stride >= P+1, a multiple of 4 (with C a
+ * multiple of 4) enables the coalesced staging path.
+ * Weights: fp32 masters in torch nn.Linear layout ([out][in]) are converted ONCE per step by dvgo_mlp_pack_weights
+ * into `wpack` (dvgo_mlp_wpack_bytes bytes of device memory: the fp16 operand tiles in the tensor core's canonical
+ * shared-memory layout, saturating conversion), which every CTA of the forward / backward kernels bulk-copies.
+ * GEMM operands are FP16, accumulation is fp32.  rgb [surv_cap,3].  width must be 128. */
+int64_t dvgo_mlp_wpack_bytes(int C, int pe_stride);
+int dvgo_mlp_pack_weights(int C, int P, int pe_stride, const float* W1, const float* b1, const float* W2,
+                          const float* b2, const float* W3, const float* b3, int width, void* wpack,
+                          dvgo_stream_t stream);
 int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                 int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
-                 const float* b2, const float* W3, const float* b3, int width, float* rgb,
-                 dvgo_stream_t stream);
+                 int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb, dvgo_stream_t stream);
 /* Same as dvgo_mlp_fwd; if `timeline` is non-NULL, CTA 0 records clock64() at every phase boundary of its
  * first tiles into timeline[0..63] (thread 0) and timeline[64..127] (thread 255) -- kernel-author tooling. */
 int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                       int32_t* counters, int64_t surv_cap, const float* W1, const float* b1,
-                       const float* W2, const float* b2, const float* W3, const float* b3, int width, float* rgb,
-                       long long* timeline, dvgo_stream_t stream);
+                       int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb, long long* timeline,
+                       dvgo_stream_t stream);
 /* Backward with forward recompute: d_feat [surv_cap,C] = dL/dfeat, and gW*, gb* += weight gradients
  * (accumulated in TMEM per CTA, flushed with atomics; the caller zeroes them).  d_rgb = dL/d(rgb) (after
  * the sigmoid).  grad_scale: power of two applied to the FP16 backward operands and removed exactly in
- * the fp32 epilogues. */
+ * the fp32 epilogues.  `wpack` must hold the same weights the forward used. */
 int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                 int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
-                 const float* b2, const float* W3, const float* b3, int width, const float* rgb,
-                 const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
-                 float* gb2, float* gW3, float* gb3, dvgo_stream_t stream);
+                 int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
+                 float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
+                 float* gb3, dvgo_stream_t stream);
 
-/* dvgo_mlp_bwd with an optional in-kernel timeline (CTA 0: epilogue thread 0 -> timeline[0..63], issuer ->
- * timeline[64..127], clock64 at every phase boundary of the first tile pair) -- kernel-author tooling. */
+/* dvgo_mlp_bwd with an optional in-kernel timeline (CTA 0: context-0 thread 0 -> timeline[0..63], issuer ->
+ * timeline[64..127], clock64 at every phase boundary of the first tiles) -- kernel-author tooling. */
 int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                       int32_t* counters, int64_t surv_cap, const float* W1, const float* b1, const float* W2,
-                       const float* b2, const float* W3, const float* b3, int width, const float* rgb,
-                       const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
-                       float* gb2, float* gW3, float* gb3, long long* timeline, dvgo_stream_t stream);
+                       int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
+                       float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
+                       float* gb3, long long* timeline, dvgo_stream_t stream);
 
 /* Tensor-core self test (one CTA): D[128,N] = A * B^T with tcgen05.mma kind::f16 (fp16 operands), for each operand
  * orientation the rgbnet kernels use.  a_mn=0: A is [128][K]; a_mn=1: A is [K][128]; b_mn=0: B is
@@ -239,6 +241,14 @@ int dvgo_tc_probe(const float* A, const float* Braw, float* D, int N, int K, int
  * cycles of `reps` x K/16 MMAs in the TMEM-A form and in the shared-memory-A form. */
 int dvgo_tc_ts_probe(const float* A, const float* B, float* D, int N, int K, int b_mn, int reps, long long* cycles,
                      dvgo_stream_t stream);
+
+/* Tensor pipe vs SIMT memory-path contention probe (tools/contention.py): out[0] = SIMT cycles, out[1] = MMA cycles;
+ * gbuf: >= 1 MiB of device memory. */
+int dvgo_tc_contention(int mma_mode, int n_mma, int simt_mode, int reps, const void* gbuf, long long* out,
+                       dvgo_stream_t stream);
+
+/* TMEM -> register read-rate probe (tools/ldtm_rate.py): out[0] = cycles, out[1] = bytes for nwarps x reps reads. */
+int dvgo_tc_ldtm_rate(int nwarps, int reps, int mode, long long* out, dvgo_stream_t stream);
 
 /* Zero `n` 4-byte words (counters, accumulators) on the stream. */
 int dvgo_fused_zero(void* ptr, int64_t n_words, dvgo_stream_t stream);

@@ -1,4 +1,5 @@
-"""Kernel-author tooling: in-kernel timeline of mlp_fwd_kernel (CTA 0): cycles between phase boundaries."""
+"""Kernel-author tooling: in-kernel clock64 timelines of mlp_fwd_kernel / mlp_bwd_kernel (CTA 0): cycles between the
+phase boundaries of a few steady-state tiles.   PYTHONPATH=. python tools/mlp_timeline.py"""
 import torch
 from directvoxgo_b200 import ext
 from directvoxgo_b200.fused_mlp import TensorCoreMLP
@@ -10,23 +11,29 @@ feat, pe, s_ray, counters, cap = _stream(M, 8192, 12, 27, 1, cap_extra=0)
 tc = TensorCoreMLP(net, "cuda")
 pe_pad = tc.pad_embedding(pe)
 rgb = torch.zeros(cap, 3, device="cuda")
+
+
+def show(who, t, names, first_tile=2, n_show=3):
+    t = [x for x in t if x]
+    n = len(names)
+    print(who, "(%d stamps)" % len(t))
+    for tile in range(first_tile, first_tile + n_show):
+        seg = t[tile * n:(tile + 1) * n + 1]
+        if len(seg) < n + 1:
+            break
+        d = [b - a for a, b in zip(seg[:-1], seg[1:])]
+        print("  tile %d: total %5d cyc | " % (tile, seg[-1] - seg[0]) + ", ".join("%s %d" % (a, b) for a, b in zip(names, d)))
+
+
 for _ in range(2):
     tl = ext.mlp_fwd_timeline(feat, s_ray, pe_pad, 27, counters, tc.params, 128, rgb)
 torch.cuda.synchronize()
-names = ["stage_x", "sync1", "issue L1", "wait L1", "epi1", "sync2", "issue L2", "wait L2", "epi2+L3", "exchange sync",
-         "sigmoid+store"]
-for who, off in (("thread 0", 0), ("thread 255", 64)):
-    t = tl[off:off + 64].cpu().tolist()
-    t = [x for x in t if x]
-    per_tile = len(names) + 1
-    print(who)
-    for tile in range(1, min(4, len(t) // per_tile)):
-        seg = t[tile * per_tile:(tile + 1) * per_tile + 1]
-        d = [b - a for a, b in zip(seg[:-1], seg[1:])]
-        print("  tile %d: total %d cyc | " % (tile, seg[-1] - seg[0] if len(seg) > per_tile else sum(d)) +
-              ", ".join("%s %d" % (n, x) for n, x in zip(names, d)))
+fwd = ["rays + wait L1", "e1->TMEM+sync", "issue L2 + stage next", "wait L2", "e2->TMEM+sync", "issue L3, L1(next) + wait L3", "e3 sigmoid+store", "loop"]
+t0 = tl[0:64].cpu().tolist()
+print("forward prologue (entry -> first loop top): %d cycles" % (t0[1] - t0[0]))
+show("forward, thread 0", t0[1:], fwd)
+show("forward, thread 255", tl[65:128].cpu().tolist(), fwd)
 
-# ---- backward ----
 d_rgb = (torch.randn(cap, 3, device="cuda") / (3 * 8192)).contiguous()
 tcb = TensorCoreMLP(net, "cuda", train=True)
 d_feat = torch.zeros(cap, 12, device="cuda")
@@ -35,13 +42,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 epi = ["stage A+B"] + [x for ph in ("relu1", "relu2", "mask2", "mask1") for x in
                        ("wait A", ph + " A", "wait B", ph + " B")] + ["wait A", "dx A + wait B", "dx B"]
-iss = [x for ph in ("L1", "L2", "dW3+dH2", "dW2+db2+dH1", "dW1+dX") for x in
-       ("acq A", ph + " A", "acq B", ph + " B")]
-for who, off, names in (("epilogue thread 0", 0, epi), ("issuer", 64, iss)):
-    t = [x for x in tl[off:off + 64].cpu().tolist() if x]
-    n = len(names) + 1
-    print(who, "(2nd pair)")
-    seg = t[n:2 * n]
-    if len(seg) == n:
-        d = [b - a for a, b in zip(seg[:-1], seg[1:])]
-        print("  pair total %d cyc | " % (seg[-1] - seg[0]) + ", ".join("%s %d" % (a, b) for a, b in zip(names, d)))
+t0 = tl[0:64].cpu().tolist()
+show("backward, epilogue thread 0", t0, epi, first_tile=1)
+t1 = [x for x in tl[64:128].cpu().tolist() if x]
+print("backward, issuer: cycles between consecutive batch issues (both contexts):", [b - a for a, b in zip(t1[10:-1], t1[11:])][:30])
