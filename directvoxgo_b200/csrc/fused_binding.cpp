@@ -150,12 +150,14 @@ void ray_finish(Tensor rgb_acc, Tensor alphainv_last, c10::optional<Tensor> targ
 }
 
 void sample_grad(Tensor rgb, Tensor s_weight, Tensor s_ray, Tensor G, Tensor target, Tensor counters, int n_global,
-                 double weight_rgbper, Tensor d_rgb, Tensor d_w, Tensor loss_acc) {
+                 double weight_rgbper, Tensor d_rgb, Tensor d_w, Tensor loss_acc, c10::optional<Tensor> dz3) {
   F32(rgb); F32(s_weight); I32(s_ray); F32(G); F32(target); I32(counters); F32(d_rgb); F32(d_w); F32(loss_acc);
+  if (dz3.has_value()) { F32((*dz3)); TORCH_CHECK(dz3->numel() >= rgb.numel() / 3 * 4, "dz3 must be [surv_cap,4]"); }
   const c10::cuda::CUDAGuard guard(rgb.device());
   rc_check(dvgo_fused_sample_grad(fp(rgb), fp(s_weight), ipm(s_ray), fp(G), fp(target), ipm(counters),
                                   rgb.numel() / 3, n_global, static_cast<float>(weight_rgbper), fpm(d_rgb), fpm(d_w),
-                                  fpm(loss_acc), cur_stream()), "sample_grad");
+                                  fpm(loss_acc), dz3.has_value() ? dz3->data_ptr<float>() : nullptr, cur_stream()),
+           "sample_grad");
 }
 
 void march_bwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor t_min, Tensor n_steps, Tensor ray_off,
@@ -218,6 +220,28 @@ void sweep_peer(Tensor param_in, std::vector<int64_t> param_out_ptrs, std::vecto
                                  static_cast<float>(wy), static_cast<float>(wz), masked, step,
                                  static_cast<float>(beta1), static_cast<float>(beta2), static_cast<float>(lr),
                                  static_cast<float>(eps), cur_stream()), "sweep_peer");
+}
+
+void peer_barrier(std::vector<int64_t> flag_ptrs, int self_rank, int epoch) {
+  const int np = static_cast<int>(flag_ptrs.size());
+  TORCH_CHECK(np >= 1 && np <= 8 && self_rank >= 0 && self_rank < np, "peer_barrier: 1..8 peers");
+  int32_t* flags[8];
+  for (int r = 0; r < np; ++r) flags[r] = reinterpret_cast<int32_t*>(flag_ptrs[r]);
+  rc_check(dvgo_peer_barrier(flags, np, self_rank, epoch, cur_stream()), "peer_barrier");
+}
+
+void adam_upd_peer(Tensor param, std::vector<int64_t> grad_ptrs, int64_t grad_mc, Tensor exp_avg, Tensor exp_avg_sq,
+                   int step, double beta1, double beta2, double lr, double eps) {
+  F32(param); F32(exp_avg); F32(exp_avg_sq);
+  const int np = static_cast<int>(grad_ptrs.size());
+  TORCH_CHECK(np >= 1 && np <= 8, "adam_upd_peer: 1..8 peers");
+  TORCH_CHECK(exp_avg.numel() == param.numel() && exp_avg_sq.numel() == param.numel(), "adam_upd_peer: shape mismatch");
+  const float* grads[8];
+  for (int r = 0; r < np; ++r) grads[r] = reinterpret_cast<const float*>(grad_ptrs[r]);
+  const c10::cuda::CUDAGuard guard(param.device());
+  rc_check(dvgo_adam_upd_peer(fpm(param), grads, reinterpret_cast<const float*>(grad_mc), np, fpm(exp_avg), fpm(exp_avg_sq),
+                              param.numel(), step, static_cast<float>(beta1), static_cast<float>(beta2),
+                              static_cast<float>(lr), static_cast<float>(eps), cur_stream()), "adam_upd_peer");
 }
 
 Tensor ncdhw_to_cl(Tensor src) {  // [1,C,X,Y,Z] -> [X,Y,Z,C]
@@ -384,7 +408,10 @@ void dvgo_bind_fused(pybind11::module_& m) {
   m.def("rgb_direct_bwd", &rgb_direct_bwd);
   m.def("composite", &composite);
   m.def("ray_finish", &ray_finish);
-  m.def("sample_grad", &sample_grad);
+  m.def("sample_grad", &sample_grad, pybind11::arg("rgb"), pybind11::arg("s_weight"), pybind11::arg("s_ray"),
+        pybind11::arg("G"), pybind11::arg("target"), pybind11::arg("counters"), pybind11::arg("n_global"),
+        pybind11::arg("weight_rgbper"), pybind11::arg("d_rgb"), pybind11::arg("d_w"), pybind11::arg("loss_acc"),
+        pybind11::arg("dz3") = pybind11::none());
   m.def("march_bwd", &march_bwd);
   m.def("sweep", &sweep, pybind11::arg("param_in"), pybind11::arg("param_out"), pybind11::arg("grad"),
         pybind11::arg("exp_avg"), pybind11::arg("exp_avg_sq"), pybind11::arg("perlr"), pybind11::arg("X"),
@@ -393,6 +420,8 @@ void dvgo_bind_fused(pybind11::module_& m) {
         pybind11::arg("beta1"), pybind11::arg("beta2"), pybind11::arg("lr"), pybind11::arg("eps"),
         pybind11::arg("x_begin") = 0, pybind11::arg("x_end") = -1);
   m.def("sweep_peer", &sweep_peer);
+  m.def("peer_barrier", &peer_barrier);
+  m.def("adam_upd_peer", &adam_upd_peer);
   m.def("ncdhw_to_cl", &ncdhw_to_cl);
   m.def("cl_to_ncdhw", &cl_to_ncdhw);
   m.def("zero_", &zero_);

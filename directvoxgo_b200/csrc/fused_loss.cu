@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) sample_grad_kernel(
     const float* __restrict__ rgb, const float* __restrict__ s_weight,
     const int32_t* __restrict__ s_ray, const float* __restrict__ G, const float* __restrict__ target,
     const int32_t* __restrict__ counters, int64_t cap, int n_global, float w_per,
-    float* __restrict__ d_rgb, float* __restrict__ d_w, float* __restrict__ loss_acc) {
+    float* __restrict__ d_rgb, float* __restrict__ d_w, float* __restrict__ loss_acc, float4* __restrict__ dz3) {
   const int64_t n = survivor_count(counters, cap);
   const float inv_n = 1.f / static_cast<float>(n_global);
   float loss = 0.f;
@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(256) sample_grad_kernel(
     const int r = s_ray[p];
     const float w = s_weight[p];
     float dw = 0.f;
+    float z[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float x = rgb[3 * p + c];
@@ -165,9 +166,11 @@ __global__ void __launch_bounds__(256) sample_grad_kernel(
         loss += w_per * w * d * d * inv_n;
       }
       d_rgb[3 * p + c] = dr;
+      z[c] = dr * x * (1.f - x);                  // through the sigmoid: what the rgbnet backward starts from
       dw += g * x;
     }
     d_w[p] = dw;
+    if (dz3) dz3[p] = make_float4(z[0], z[1], z[2], 0.f);
   }
   if (loss_acc && w_per > 0.f) {
     const float s = block_sum(loss);
@@ -285,13 +288,13 @@ DVGO_API int dvgo_fused_ray_finish(float* rgb_acc, const float* alphainv_last, c
 DVGO_API int dvgo_fused_sample_grad(const float* rgb, const float* s_weight, const int32_t* s_ray,
                                     const float* G, const float* target, const int32_t* counters,
                                     int64_t surv_cap, int n_global, float weight_rgbper, float* d_rgb,
-                                    float* d_w, float* loss_acc, dvgo_stream_t stream) {
+                                    float* d_w, float* loss_acc, float* dz3, dvgo_stream_t stream) {
   if (surv_cap < 0 || n_global <= 0 || !rgb || !s_weight || !s_ray || !G || !counters || !d_rgb ||
       !d_w || (weight_rgbper > 0.f && !target))
     return DVGO_EINVAL;
   sample_grad_kernel<<<stream_grid(surv_cap, 256), 256, 0, as_stream(stream)>>>(
       rgb, s_weight, s_ray, G, target, counters, surv_cap, n_global, weight_rgbper, d_rgb, d_w,
-      loss_acc);
+      loss_acc, reinterpret_cast<float4*>(dz3));
   return launch_status();
 }
 

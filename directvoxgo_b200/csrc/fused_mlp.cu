@@ -638,8 +638,8 @@ struct TileCtx {
 __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
     int32_t* __restrict__ counters, int64_t surv_cap, const uint8_t* __restrict__ wpack, int K1, int pe_stride,
-    const float* __restrict__ rgb, const float* __restrict__ d_rgb, float grad_scale, float* __restrict__ d_feat,
-    MlpG g, long long* __restrict__ dbg) {
+    const float* __restrict__ rgb, const float* __restrict__ d_rgb, const float* __restrict__ dz3, float grad_scale,
+    float* __restrict__ d_feat, MlpG g, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4];  // full[0], full[1], ready[0], ready[1]
   __shared__ uint32_t tmem_base_s;
@@ -672,6 +672,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   const WPack wl = wpack_layout(K1);
   copy_to_smem(sW1, wpack, wl.offW3);                         // W1~ | W2~ tiles (fp16, packed once per step)
   copy_to_smem(sW3t, wpack + wl.offW3t, tile_bytes(kHid, 16));
+  for (int cx_i = 0; cx_i < 2; ++cx_i)      // X~ tiles: the padding columns [C + pe_stride, K1) are written once, here
+    for (uint32_t i = tid; i < tile_bytes(kTile, K1) / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(ctx_base + cx_i * ctx_bytes)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < kTile * 16; i += blockDim.x) {
     const int j = i / 16, c = i % 16;
     // columns 128..143 of both H1 tiles: the constant 1 (b2 rides the layer-2 GEMM, db2 the dW2 GEMM), then 0;
@@ -709,8 +712,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   // then conversion + shared-memory stores.  The loads of BOTH contexts are issued before either is
   // consumed, and the ray indices (the head of the dependent chain s_ray -> embedding row) are fetched one
   // pair ahead, so a pair pays one global-memory latency instead of four (tools/mlp_timeline.py).
-  const bool vecx = ((C | pe_stride) & 3) == 0 && K1 <= 64;
-  struct Staged { XRegs<2> x; float o[3], d[3]; };
+  // Vector path (C and pe_stride multiples of 4, pe_stride <= 32): the 128 feature rows of a tile are one contiguous
+  // block, read FLAT (thread t takes float4 t: 4 cache lines per warp load instead of 12 with one row per lane), the
+  // embedding row of a sample by its (row, part) owner (float4 part, part + 4), and dZ3 as ONE float4 per row when the
+  // loss kernel wrote d_rgb * rgb (1 - rgb) (`dz3`; otherwise 6 scalar loads of rgb / d_rgb).  The LSU, not the memory
+  // system, bounds this staging: ~72 -> ~28 line requests per 32 rows.
+  const bool vecx = ((C | pe_stride) & 3) == 0 && C <= 16 && pe_stride <= 32;
+  const StageGeom sg = stage_geom(C, pe_stride);
+  struct Staged { float4 f; float4 p[2]; float o[3], d[3]; };
   auto ray_of = [&](int64_t s0) -> int {
     const int64_t sidx = s0 + row;
     return sidx < count ? __ldg(s_ray + sidx) : 0;
@@ -719,32 +728,35 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     const int64_t sidx = c.s0 + row;
     c.valid = sidx < count;
     // (1) define every destination, (2) fence, (3) all loads back to back -- see ldg_nc_f4_if
-#pragma unroll
-    for (int k = 0; k < 4; ++k) st.x.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    st.f = make_float4(0.f, 0.f, 0.f, 0.f);
+    st.p[0] = st.f;
+    st.p[1] = st.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { st.o[k] = 0.f; st.d[k] = 0.f; }
-    reg_fence(st.x.v[0], st.x.v[1], st.x.v[2], st.x.v[3]);
+    float4 pad = st.f;
+    reg_fence(st.f, st.p[0], st.p[1], pad);
     reg_fence(st.o[0], st.o[1], st.o[2], st.d[0], st.d[1], st.d[2]);
     if (vecx) {
-      const float* __restrict__ f = feat + sidx * C;
-      const float* __restrict__ e = pe + static_cast<int64_t>(ray) * pe_stride;
+      const bool fin = tid < 128 * sg.nf4 && c.s0 + fast_div(tid, sg.inv_f) < count;
+      ldg_nc_f4_if(st.f, reinterpret_cast<const float4*>(feat) + (fin ? c.s0 * sg.nf4 + tid : 0), fin);
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int ch = part + 4 * k;
-#pragma unroll
-        for (int g2 = 0; g2 < 2; ++g2) {
-          const int cc = ch * 8 + g2 * 4;
-          const bool in = c.valid && ch * 8 < K1 && cc < C + pe_stride;
-          const float* src = cc < C ? f + cc : e + (cc - C);
-          ldg_nc_f4_if(st.x.v[2 * k + g2], reinterpret_cast<const float4*>(in ? src : feat), in);
-        }
+        const int c4 = part + 4 * k;
+        const bool pin = c.valid && c4 < sg.np4;
+        ldg_nc_f4_if(st.p[k], reinterpret_cast<const float4*>(pe) + (pin ? static_cast<int64_t>(ray) * sg.np4 + c4 : 0), pin);
       }
     }
     const bool want = part == 0 && c.valid;
+    if (dz3) {   // d_rgb * rgb * (1 - rgb), written by the loss kernel: one 16-byte load per row
+      float4 z = make_float4(st.d[0], st.d[1], st.d[2], 0.f);
+      ldg_nc_f4_if(z, reinterpret_cast<const float4*>(dz3) + (want ? sidx : 0), want);
+      st.d[0] = z.x; st.d[1] = z.y; st.d[2] = z.z;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      ldg_nc_f32_if(st.o[k], want ? rgb + sidx * 3 + k : rgb, want);
-      ldg_nc_f32_if(st.d[k], want ? d_rgb + sidx * 3 + k : d_rgb, want);
+      for (int k = 0; k < 3; ++k) {
+        ldg_nc_f32_if(st.o[k], want ? rgb + sidx * 3 + k : rgb, want);
+        ldg_nc_f32_if(st.d[k], want ? d_rgb + sidx * 3 + k : d_rgb, want);
+      }
     }
   };
   auto stage_store = [&](TileCtx& c, const Staged& st, int ray) {
@@ -754,14 +766,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       for (int j = 0; j < 16; ++j) v[j] = 0.f;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        v[k] = st.d[k] * st.o[k] * (1.f - st.o[k]) * grad_scale;   // dZ3 (scaled)
+        v[k] = (dz3 ? st.d[k] : st.d[k] * st.o[k] * (1.f - st.o[k])) * grad_scale;   // dZ3 (scaled)
         db3[k] += v[k];
       }
       *reinterpret_cast<uint4*>(c.sdZ3 + tile_off(row, 0, 16)) = pack8(v);
       *reinterpret_cast<uint4*>(c.sdZ3 + tile_off(row, 8, 16)) = pack8(v + 8);
     }
     if (vecx) {
-      x_store<2>(st.x, part, 4, K1, row, c.sX);
+      if (tid < 128 * sg.nf4) {
+        const int r = fast_div(tid, sg.inv_f), c4 = tid - r * sg.nf4;
+        *reinterpret_cast<uint2*>(c.sX + tile_off(r, 4 * c4, K1)) = pack4(st.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int c4 = part + 4 * k;
+        if (c4 < sg.np4) *reinterpret_cast<uint2*>(c.sX + tile_off(row, C + 4 * c4, K1)) = pack4(st.p[k]);
+      }
     } else {  // generic (scalar) path: C or the embedding stride not a multiple of 4
       const int64_t sidx = c.s0 + row;
       const float* __restrict__ f = feat + sidx * C;
@@ -919,6 +939,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
         const int64_t s2 = A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile + (part >> 1) * kTile + row;
         if (s2 < count) {
           if ((part & 1) == 0) prefetch_l2(feat + s2 * C);
+          else if (dz3) prefetch_l2(dz3 + s2 * 4);
           else { prefetch_l2(rgb + s2 * 3); prefetch_l2(d_rgb + s2 * 3); }
         }
       }
@@ -1495,12 +1516,13 @@ DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const 
 
 DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                                 int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb,
-                                const float* d_rgb, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
-                                float* gb2, float* gW3, float* gb3, long long* timeline, dvgo_stream_t stream) {
+                                const float* d_rgb, const float* dz3, float grad_scale, float* d_feat, float* gW1,
+                                float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, long long* timeline,
+                                dvgo_stream_t stream) {
   if (C < 1 || C > 16 || P < 0 || C + P > 63 || surv_cap < 0 || !(grad_scale > 0.f) || pe_stride < P + 1)
     return DVGO_EINVAL;
-  if (!feat || !s_ray || (P > 0 && !pe) || !counters || !wpack || !rgb || !d_rgb || !d_feat || !gW1 || !gb1 || !gW2 ||
-      !gb2 || !gW3 || !gb3)
+  if (!feat || !s_ray || (P > 0 && !pe) || !counters || !wpack || (!dz3 && (!rgb || !d_rgb)) || !d_feat || !gW1 || !gb1 ||
+      !gW2 || !gb2 || !gW3 || !gb3)
     return DVGO_EINVAL;
   if (surv_cap == 0) return 0;
   const int K1 = mlp_k1(C, pe_stride);
@@ -1513,16 +1535,16 @@ DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, 
   MlpG g{gW1, gb1, gW2, gb2, gW3, gb3};
   mlp_bwd_kernel<<<grid, kBwdThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap,
                                                                  static_cast<const uint8_t*>(wpack), K1, pe_stride, rgb,
-                                                                 d_rgb, grad_scale, d_feat, g, timeline);
+                                                                 d_rgb, dz3, grad_scale, d_feat, g, timeline);
   return launch_status();
 }
 
 DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                           int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
-                          float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
-                          float* gb3, dvgo_stream_t stream) {
-  return dvgo_mlp_bwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, wpack, rgb, d_rgb, grad_scale, d_feat,
-                            gW1, gb1, gW2, gb2, gW3, gb3, nullptr, stream);
+                          const float* dz3, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
+                          float* gb2, float* gW3, float* gb3, dvgo_stream_t stream) {
+  return dvgo_mlp_bwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, wpack, rgb, d_rgb, dz3, grad_scale,
+                            d_feat, gW1, gb1, gW2, gb2, gW3, gb3, nullptr, stream);
 }
 
 DVGO_API int dvgo_tc_rate(int ctas, int N, int ksteps, int reps, int a_mn, int b_mn, int a_lbo, int a_sbo, int a_kstep,

@@ -250,6 +250,60 @@ __global__ void __launch_bounds__(256, kPeer ? DVGO_PEER_MINB : 1) sweep_kernel(
   if constexpr (kPeer) __threadfence_system();   // peer / multicast stores performed before the kernel retires
 }
 
+// ---- cross-GPU ordering and the small (rgbnet) gradient over peer memory --------------------------------------------
+// Round 1 ordered the ranks around the peer sweep with two tiny NCCL all-reduces (~55 + ~70 us at 8 ranks, 6 % of the
+// step).  Here each rank owns an array of n int32 flags in symmetric memory: a barrier is one 32-thread kernel in which
+// lane r stores the new epoch into slot `self` of rank r's array (st.release.sys over NVLink) and then spins on slot r of
+// its own array (ld.acquire.sys, local memory) until it shows the epoch.  Stream order makes every earlier kernel of
+// this GPU complete (its writes performed) before the release stores; the acquire loads order the later kernels' peer
+// reads after the other ranks' writes.  The spin is bounded: a missing rank traps instead of hanging the GPU.
+struct PeerFlags {
+  int32_t* flags[8];
+  int n, self;
+};
+__global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, int epoch) {
+  const int r = threadIdx.x;
+  if (r >= pf.n) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(pf.flags[r] + pf.self), "r"(epoch) : "memory");
+  const int32_t* mine = pf.flags[pf.self] + r;
+  const long long t0 = clock64();
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (v - epoch >= 0) break;
+    __nanosleep(100);
+    if (clock64() - t0 > 8000000000LL) __trap();   // ~4 s at 1.9 GHz: a rank is missing
+  } while (true);
+  __threadfence_system();
+}
+
+// Adam on a small replicated tensor whose gradient is the SUM over ranks, read straight from the peers' buffers (or,
+// with NVLS, already summed by the switch): every rank computes the identical update, no collective call.
+struct SmallPeers {
+  const float* grad[8];
+  const float* grad_mc;
+  int n;
+};
+__global__ void __launch_bounds__(256) adam_peer_kernel(float* __restrict__ param, SmallPeers sp, float* __restrict__ m_,
+                                                        float* __restrict__ v_, int64_t N, float step_size, float beta1,
+                                                        float beta2, float eps) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < N;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float g = 0.f;
+    if (sp.grad_mc) {
+      g = multimem_ld_reduce_add1(sp.grad_mc + i);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < sp.n) g = fadd(g, sp.grad[r][i]);      // rank order: every rank gets bit-identical sums
+    }
+    float p = param[i], m = m_[i], v = v_[i];
+    adam_elem_nolr(p, g, m, v, step_size, beta1, beta2, eps);
+    param[i] = p; m_[i] = m; v_[i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) ncdhw_to_cl_kernel(const float* __restrict__ src,
                                                           float* __restrict__ dst, int C, int64_t G) {
   const int64_t n = G * C;
@@ -375,6 +429,40 @@ DVGO_API int dvgo_fused_sweep_peer(const float* param_in, float* const* param_ou
   return sweep_launch(param_in, peers.pout[self_rank], const_cast<float*>(peers.grad[self_rank]), exp_avg, exp_avg_sq,
                       perlr, X, Y, Z, C, x_begin, x_end, tv, tv_dense, wx, wy, wz, masked, step, beta1, beta2, lr, eps,
                       peers, stream);
+}
+
+DVGO_API int dvgo_peer_barrier(int32_t* const* flags_peers_host, int n_peers, int self_rank, int epoch,
+                               dvgo_stream_t stream) {
+  if (!flags_peers_host || n_peers < 1 || n_peers > 8 || self_rank < 0 || self_rank >= n_peers) return DVGO_EINVAL;
+  PeerFlags pf;
+  pf.n = n_peers;
+  pf.self = self_rank;
+  for (int r = 0; r < 8; ++r) {
+    pf.flags[r] = r < n_peers ? flags_peers_host[r] : nullptr;
+    if (r < n_peers && !pf.flags[r]) return DVGO_EINVAL;
+  }
+  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pf, epoch);
+  return launch_status();
+}
+
+DVGO_API int dvgo_adam_upd_peer(float* param, const float* const* grad_peers_host, const float* grad_multicast,
+                                int n_peers, float* exp_avg, float* exp_avg_sq, int64_t N, int step, float beta1,
+                                float beta2, float lr, float eps, dvgo_stream_t stream) {
+  if (!param || !grad_peers_host || !exp_avg || !exp_avg_sq || n_peers < 1 || n_peers > 8 || N < 0 || step <= 0)
+    return DVGO_EINVAL;
+  if (N == 0) return 0;
+  SmallPeers sp;
+  sp.n = n_peers;
+  sp.grad_mc = grad_multicast;
+  for (int r = 0; r < 8; ++r) {
+    sp.grad[r] = r < n_peers ? grad_peers_host[r] : nullptr;
+    if (r < n_peers && !sp.grad[r]) return DVGO_EINVAL;
+  }
+  const float step_size = lr * sqrtf(1.f - powf(beta2, static_cast<float>(step))) /
+                          (1.f - powf(beta1, static_cast<float>(step)));  // adam_upd_kernel.cu:72
+  const int blocks = static_cast<int>((N + 255) / 256 < kNumSMs ? (N + 255) / 256 : kNumSMs);
+  adam_peer_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, sp, exp_avg, exp_avg_sq, N, step_size, beta1, beta2, eps);
+  return launch_status();
 }
 
 DVGO_API int dvgo_grid_ncdhw_to_cl(const float* src, float* dst, int C, int64_t G,

@@ -145,7 +145,7 @@ Tensor mlp_fwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor coun
 }
 
 void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb, Tensor d_rgb,
-             double grad_scale, Tensor d_feat, Tensor grads, c10::optional<Tensor> wpack) {
+             double grad_scale, Tensor d_feat, Tensor grads, c10::optional<Tensor> wpack, c10::optional<Tensor> dz3) {
   chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
   chkf(rgb, "rgb"); chkf(d_rgb, "d_rgb"); chkf(d_feat, "d_feat"); chkf(grads, "grads");
   const int C = feat.size(1), pe_stride = pe.size(1);
@@ -155,10 +155,12 @@ void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tenso
   const c10::cuda::CUDAGuard guard(feat.device());
   Tensor wp = ensure_pack(wpack, params, C, P, pe_stride, width);
   float* g = grads.data_ptr<float>();
+  if (dz3.has_value()) { chkf(*dz3, "dz3"); TORCH_CHECK(dz3->numel() >= cap * 4, "dz3 must be [surv_cap,4]"); }
   rc_check(dvgo_mlp_bwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
                         counters.data_ptr<int32_t>(), cap, wp.data_ptr(), rgb.data_ptr<float>(), d_rgb.data_ptr<float>(),
-                        static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2, g + o.b2,
-                        g + o.W3, g + o.b3, cur_stream()), "mlp_bwd");
+                        dz3.has_value() ? dz3->data_ptr<float>() : nullptr, static_cast<float>(grad_scale),
+                        d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3, cur_stream()),
+           "mlp_bwd");
 }
 
 Tensor mlp_bwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb,
@@ -171,7 +173,7 @@ Tensor mlp_bwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor coun
   float* g = grads.data_ptr<float>();
   rc_check(dvgo_mlp_bwd_timed(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
                               counters.data_ptr<int32_t>(), s_ray.numel(), wp.data_ptr(), rgb.data_ptr<float>(),
-                              d_rgb.data_ptr<float>(), static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1,
+                              d_rgb.data_ptr<float>(), nullptr, static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1,
                               g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3,
                               reinterpret_cast<long long*>(tl.data_ptr<int64_t>()), cur_stream()), "mlp_bwd_timed");
   return tl;
@@ -195,6 +197,6 @@ void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("mlp_bwd", &mlp_bwd, pybind11::arg("feat"), pybind11::arg("s_ray"), pybind11::arg("pe"), pybind11::arg("P"),
         pybind11::arg("counters"), pybind11::arg("params"), pybind11::arg("width"), pybind11::arg("rgb"),
         pybind11::arg("d_rgb"), pybind11::arg("grad_scale"), pybind11::arg("d_feat"), pybind11::arg("grads"),
-        pybind11::arg("wpack") = pybind11::none());
+        pybind11::arg("wpack") = pybind11::none(), pybind11::arg("dz3") = pybind11::none());
   m.def("mlp_bwd_timeline", &mlp_bwd_timeline);
 }

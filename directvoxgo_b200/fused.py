@@ -72,6 +72,7 @@ class _Workspace:
             self.d_rgb = torch.empty(cap, 3, **f32)
             self.d_w = torch.empty(cap, **f32)
             self.d_feat = torch.empty(cap, C, **f32)
+            self.dz3 = torch.empty(cap, 4, **f32)     # d_rgb * rgb (1 - rgb): loss kernel -> rgbnet backward
 
 
 def view_embedding(viewdirs, viewfreq):
@@ -321,15 +322,18 @@ class FusedTrainer(_FusedBase):
         #           (torch symmetric memory gives every rank the device addresses of every rank's buffers);
         #   "nccl": reduce_scatter -> slab sweep -> all_gather (or plain all-reduce when shard_sweep=False).
         self._pp = None
+        self._flags = None
+        self._side, self._zero_pending = None, False
+        self._side2, self.overlap_density_bwd = None, True
         self.exchange = "none"
         if world_size > 1:
             self.exchange = "nccl"
             if exchange in ("auto", "peer", "peer_p2p") and shard_sweep and world_size <= 8:
-                # "peer_p2p" / "auto": per-peer loads and stores; "peer": NVLS multicast (multimem.ld_reduce / st) when
-                # the system has it.  Measured on B200 (profiles/r01_peer_exchange.txt): multicast moves fewer bytes per
-                # link from 4 ranks up, but the multimem accesses run at about half the link rate, so the plain peer
-                # accesses (latency hidden by 4 resident CTAs per SM) are the default at every rank count.
-                use_mc = exchange == "peer"
+                # "peer_p2p": per-peer loads and stores; "peer": NVLS multicast (multimem.ld_reduce / multimem.st through
+                # the switch); "auto": multicast from 4 ranks up.  Measured on B200 (round 2, profiles/r02_scaling.md):
+                # 2 ranks p2p is ahead (same bytes per link, plain accesses run faster); 4 ranks 1.90 vs 1.95 ms/step
+                # (320^3: 9.20 vs 9.41); 8 ranks 1.90 vs 2.03 ms/step (320^3: 6.62 vs 7.66) in favour of multicast.
+                use_mc = exchange == "peer" or (exchange == "auto" and world_size >= 4)
                 self._setup_peer(required=(exchange != "auto"), multicast=use_mc)
 
     def _setup_peer(self, required=False, multicast=True):
@@ -370,6 +374,38 @@ class FusedTrainer(_FusedBase):
         self.multicast = bool(mc["k0"])
         self._bar = torch.zeros(1, device=self.device)
         self.exchange = "peer"
+        # Ordering without a collective library: per-rank flag arrays in symmetric memory (ext.peer_barrier), and --
+        # with the tensor-core rgbnet, whose gradient is one flat buffer -- that buffer too, so that its sum over ranks
+        # is read inside the Adam kernel (ext.adam_upd_peer).  Round 1 used two NCCL all-reduces per step for this
+        # (~55 + ~70 us at 8 ranks).  mlp='torch' keeps its autograd gradients and the NCCL all-reduce.
+        self._flags = None
+        if self.model.rgbnet is None or self.mlp_mode == "tc":
+            ok2 = True
+            try:
+                flags = symm.empty((8,), dtype=torch.int32, device=self.device)
+                flags.zero_()
+                fh = symm.rendezvous(flags, group)
+                fptrs = [int(p) for p in fh.buffer_ptrs]
+                gptrs, gmc, gflat = None, 0, None
+                if self.model.rgbnet is not None:
+                    gflat = symm.empty(tuple(self._tc.grad_flat.shape), dtype=torch.float32, device=self.device)
+                    gflat.zero_()
+                    gh = symm.rendezvous(gflat, group)
+                    gptrs = [int(p) for p in gh.buffer_ptrs]
+                    gmc = int(gh.multicast_ptr or 0) if self.multicast else 0
+                    keep.append(gh)
+                keep.append(fh)
+            except Exception:
+                ok2 = False
+            f2 = torch.tensor([1.0 if ok2 else 0.0], device=self.device)
+            dist.all_reduce(f2, op=dist.ReduceOp.MIN, group=self.dist_group)
+            if float(f2.item()) >= 1.0:
+                torch.cuda.synchronize()
+                dist.barrier(group=self.dist_group)          # every rank's flags are zeroed before anyone signals
+                self._flags, self._flag_ptrs, self._epoch = flags, fptrs, 0
+                if gflat is not None:
+                    self._tc.grad_flat = gflat
+                    self._gflat_ptrs, self._gflat_mc = gptrs, gmc
 
     def set_pervoxel_lr(self, count):
         """View-count learning-rate table for the density grid (lib/masked_adam.py:35-37)."""
@@ -390,6 +426,11 @@ class FusedTrainer(_FusedBase):
             out[b] = sum(ts) / max(len(ts), 1)
         return out
 
+    def _join_side(self):
+        if self._zero_pending:
+            torch.cuda.current_stream().wait_event(self._zero_done)
+            self._zero_pending = False
+
     # -- state snapshot / restore (bench.py: the clock ramp and warm-up must not train the model that is timed) -----
     @torch.no_grad()
     def snapshot(self):
@@ -404,6 +445,7 @@ class FusedTrainer(_FusedBase):
     @torch.no_grad()
     def restore(self, snap):
         """In place (the buffers may live in symmetric memory that peers hold addresses of)."""
+        self._join_side()
         for n, t in snap["t"].items():
             getattr(self, n).copy_(t)
         for g in (self.g_density, self.g_k0):
@@ -429,17 +471,41 @@ class FusedTrainer(_FusedBase):
         self._march(ws, rays_o, rays_d)
         self._mark("march_fwd")
 
+        dens_async = False
         w_main = float(cfg.get("weight_main", 1.0))
         w_ent = float(cfg.get("weight_entropy_last", 0.0))
         w_per = float(cfg.get("weight_rgbper", 0.0))
         bg = float(self.rk["bg"])
+
+        use_dz3 = model.rgbnet is not None and self.mlp_mode == "tc"
+
+        def density_backward_async():
+            """alpha2weight / raw2alpha backward + density scatter (march_bwd) depend on d_w from the loss kernels only,
+            not on the rgbnet backward: launch them on a side stream so they run under it (the rgbnet kernel holds one
+            CTA per SM for its shared memory but leaves registers and issue slots; march_bwd uses no shared memory)."""
+            if not self.split_k0 or not self.overlap_density_bwd or self.stage_events is not None:
+                return False    # (per-stage event timing wants the stages one after the other)
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=self.device)
+                self._dens_done = torch.cuda.Event()
+            ev = torch.cuda.Event()
+            ev.record()
+            self._side2.wait_event(ev)
+            if self._zero_pending:
+                self._side2.wait_event(self._zero_done)
+            with torch.cuda.stream(self._side2):
+                ext.march_bwd(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T,
+                              ws.slot_expd, ws.slot_code, ws.d_feat, ws.d_w, ws.alphainv_last, ws.g_last, self.g_density,
+                              None)
+                self._dens_done.record()
+            return True
 
         def after_rgb():
             ext.composite(ws.rgb, ws.s_weight, ws.s_ray, ws.s_slot, ws.ray_off, ws.counters, ws.rgb_acc, None)
             ext.ray_finish(ws.rgb_acc, ws.alphainv_last, target, bg, n, n_global, w_main, w_ent, ws.G, ws.g_last,
                            ws.loss_acc)
             ext.sample_grad(ws.rgb, ws.s_weight, ws.s_ray, ws.G, target, ws.counters, n_global, w_per, ws.d_rgb,
-                            ws.d_w, ws.loss_acc)
+                            ws.d_w, ws.loss_acc, ws.dz3 if use_dz3 else None)
 
         if model.rgbnet is None:
             ext.rgb_direct(ws.feat, ws.counters, ws.rgb)
@@ -452,7 +518,8 @@ class FusedTrainer(_FusedBase):
             self._mark("mlp_fwd")
             after_rgb()
             self._mark("loss")
-            self._tc.backward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb, ws.d_rgb, ws.d_feat, n_global)
+            dens_async = density_backward_async()
+            self._tc.backward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb, ws.d_rgb, ws.d_feat, n_global, ws.dz3)
         else:
             m4 = int(ws.counters[0].item())  # parity mode: one host read of the survivor count
             for p in model.rgbnet.parameters():
@@ -466,12 +533,16 @@ class FusedTrainer(_FusedBase):
                 ws.d_feat[:m4].copy_(feat.grad)
 
         self._mark("mlp_bwd")
-        ext.march_bwd(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T,
-                      ws.slot_expd, ws.slot_code, ws.d_feat, ws.d_w, ws.alphainv_last, ws.g_last, self.g_density,
-                      None if self.split_k0 else self.g_k0)
+        self._join_side()     # the side-stream re-zeroing of the gradient slabs must have finished before the scatter
+        if not dens_async:
+            ext.march_bwd(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T,
+                          ws.slot_expd, ws.slot_code, ws.d_feat, ws.d_w, ws.alphainv_last, ws.g_last, self.g_density,
+                          None if self.split_k0 else self.g_k0)
         if self.split_k0:
             ext.k0_scatter(self.scene, rays_o, rays_d, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot, ws.counters,
                            ws.d_feat, self.g_k0)
+        if dens_async:
+            torch.cuda.current_stream().wait_event(self._dens_done)
         self._mark("march_bwd")
         self._optimise(n_global)
         self._mark("sweep")
@@ -544,7 +615,13 @@ class FusedTrainer(_FusedBase):
         cfg = self.cfg
         peer = self.exchange == "peer"
         slab = None if peer else self._slab()
-        if peer:
+        flags = peer and self._flags is not None
+        if flags:
+            self._epoch += 1
+            ext.peer_barrier(self._flag_ptrs, self.rank, self._epoch)     # every rank's backward has finished
+            self._mark("grad_exchange")
+            x0, x1 = (self.X * self.rank) // self.world_size, (self.X * (self.rank + 1)) // self.world_size
+        elif peer:
             self._peer_barrier(with_small_grads=True)      # every rank's backward has finished
             self._mark("grad_exchange")
             x0, x1 = (self.X * self.rank) // self.world_size, (self.X * (self.rank + 1)) // self.world_size
@@ -592,20 +669,42 @@ class FusedTrainer(_FusedBase):
                     for tab in (self._pp, self._mc):
                         tab[name], tab[name + "_next"] = tab[name + "_next"], tab[name]
             updated.append(name)
+        rgbnet_done = False
+        if flags and self.model.rgbnet is not None and self.lr["rgbnet"] > 0:
+            # rgbnet Adam on the gradient summed over ranks, read from the peers' flat buffers inside the kernel
+            ext.adam_upd_peer(self._tc.params, self._gflat_ptrs, self._gflat_mc, self._tc.exp_avg, self._tc.exp_avg_sq,
+                              self.opt_step, b1, b2, self.lr["rgbnet"], self.eps)
+            rgbnet_done = True
         if peer:
             self._mark("sweep_grids")
-            self._peer_barrier()          # every rank has read my gradients and written my parameters
-            for g in (self.g_density, self.g_k0):   # the slabs other ranks own still hold my partial sums
-                if x0 > 0:
-                    ext.zero_(g[:x0])
-                if x1 < self.X:
-                    ext.zero_(g[x1:])
+            if flags:
+                self._epoch += 1
+                ext.peer_barrier(self._flag_ptrs, self.rank, self._epoch)   # every rank has read my gradients and written
+            else:                                                           # my parameters
+                self._peer_barrier()
+            # The slabs other ranks own still hold my partial sums: (n-1)/n of both gradient accumulators to re-zero
+            # (187 MB at 8 ranks).  Nothing reads them before the next backward's scatter, so the zeroing runs on a side
+            # stream under the next forward pass instead of on the critical path.
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+                self._zero_done = torch.cuda.Event()
+            ev = torch.cuda.Event()
+            ev.record()
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                for g in (self.g_density, self.g_k0):
+                    if x0 > 0:
+                        ext.zero_(g[:x0])
+                    if x1 < self.X:
+                        ext.zero_(g[x1:])
+                self._zero_done.record()
+            self._zero_pending = True
             self._mark("param_gather")
         elif slab is not None:
             self._mark("sweep_grids")     # slab-sharded grid sweeps end here; "sweep" then only holds the rgbnet Adam
             self._gather_params(slab, updated)
             self._mark("param_gather")
-        if self.model.rgbnet is not None and self.lr["rgbnet"] > 0:
+        if self.model.rgbnet is not None and self.lr["rgbnet"] > 0 and not rgbnet_done:
             if self.mlp_mode == "tc":
                 self._tc.adam_step(self.opt_step, b1, b2, self.lr["rgbnet"], self.eps)
             else:

@@ -78,15 +78,16 @@ class TensorCoreMLP:
         wp = self.pack(feat.shape[1], pe_pad.shape[1])
         ext.mlp_fwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb, wp)
 
-    def backward(self, feat, s_ray, pe_pad, counters, rgb, d_rgb, d_feat, n_global):
-        """Accumulates weight gradients into self.grad_flat (zeroed here) and writes d_feat."""
+    def backward(self, feat, s_ray, pe_pad, counters, rgb, d_rgb, d_feat, n_global, dz3=None):
+        """Accumulates weight gradients into self.grad_flat (zeroed here) and writes d_feat.  dz3: the [cap,4] buffer
+        ext.sample_grad filled with d_rgb * rgb * (1 - rgb) (optional; computed in the kernel otherwise)."""
         ext.zero_(self.grad_flat)
         # d_rgb <= ~2/(3 n_global): scale so that the largest FP16 backward operand is O(100)
         scale = 2.0 ** math.floor(math.log2(256.0 * n_global))
         wp = self._wpack if getattr(self, "_wpack_key", None) == (feat.shape[1], pe_pad.shape[1]) else \
             self.pack(feat.shape[1], pe_pad.shape[1])
         ext.mlp_bwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb, d_rgb,
-                    scale, d_feat, self.grad_flat, wp)
+                    scale, d_feat, self.grad_flat, wp, dz3)
 
     def adam_step(self, step, beta1, beta2, lr, eps):
         adam_upd_cuda.adam_upd(self.params, self.grad_flat, self.exp_avg, self.exp_avg_sq, step, beta1, beta2, lr, eps)

@@ -128,11 +128,13 @@ int dvgo_fused_ray_finish(float* rgb_acc, const float* alphainv_last, const floa
 /* sample_grad: per survivor i of ray r (run.py:383-386 and SURVEY.md appendix C):
  *   d_rgb[i] = w_i*G[r] + weight_rgbper * 2 w_i (rgb_i - target[r]) / n_global
  *   d_w[i]   = sum_c G[r,c]*rgb_i,c                       (weights are detached in the rgbper term)
- *   loss_acc[0] += weight_rgbper * w_i * |rgb_i - target[r]|^2 / n_global */
+ *   loss_acc[0] += weight_rgbper * w_i * |rgb_i - target[r]|^2 / n_global
+ * dz3 (optional, [surv_cap,4], 16-byte aligned): d_rgb[i] * rgb_i * (1 - rgb_i) (the gradient through the sigmoid of
+ * lib/dvgo.py:539) and a zero, one float4 per survivor -- the input of dvgo_mlp_bwd. */
 int dvgo_fused_sample_grad(const float* rgb, const float* s_weight, const int32_t* s_ray,
                            const float* G, const float* target, const int32_t* counters,
                            int64_t surv_cap, int n_global, float weight_rgbper, float* d_rgb,
-                           float* d_w, float* loss_acc, dvgo_stream_t stream);
+                           float* d_w, float* loss_acc, float* dz3, dvgo_stream_t stream);
 
 /* march_bwd: accumulates into grad_density [X,Y,Z] and grad_k0_cl [X,Y,Z,C] (fp32 atomics).
  * d_feat [M4,C] = dL/d(k0 features), d_w [M4] = dL/d(weights), g_last [N] = dL/d(alphainv_last). */
@@ -203,18 +205,32 @@ int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const flo
 /* Backward with forward recompute: d_feat [surv_cap,C] = dL/dfeat, and gW*, gb* += weight gradients
  * (accumulated in TMEM per CTA, flushed with atomics; the caller zeroes them).  d_rgb = dL/d(rgb) (after
  * the sigmoid).  grad_scale: power of two applied to the FP16 backward operands and removed exactly in
- * the fp32 epilogues.  `wpack` must hold the same weights the forward used. */
+ * the fp32 epilogues.  `wpack` must hold the same weights the forward used.  `dz3` (optional, [surv_cap,4]): the
+ * pre-activation gradient d_rgb * rgb * (1 - rgb) as dvgo_fused_sample_grad writes it (one 16-byte load per sample
+ * instead of six scalar ones); when NULL it is computed from rgb and d_rgb. */
 int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                  int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
-                 float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
-                 float* gb3, dvgo_stream_t stream);
+                 const float* dz3, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2,
+                 float* gW3, float* gb3, dvgo_stream_t stream);
 
 /* dvgo_mlp_bwd with an optional in-kernel timeline (CTA 0: context-0 thread 0 -> timeline[0..63], issuer ->
  * timeline[64..127], clock64 at every phase boundary of the first tiles) -- kernel-author tooling. */
 int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
                        int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
-                       float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
-                       float* gb3, long long* timeline, dvgo_stream_t stream);
+                       const float* dz3, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2,
+                       float* gW3, float* gb3, long long* timeline, dvgo_stream_t stream);
+
+/* Cross-GPU barrier on the stream without a collective library: flags_peers_host[r] = rank r's array of n_peers int32
+ * flags (symmetric memory, zero-initialised, peer-mapped); the kernel stores `epoch` into slot self_rank of every rank's
+ * array (release.sys) and waits until every slot of the local array has reached it (acquire.sys).  epoch must grow by
+ * one per call on every rank.  A rank that never arrives makes the others trap after ~4 s instead of hanging. */
+int dvgo_peer_barrier(int32_t* const* flags_peers_host, int n_peers, int self_rank, int epoch, dvgo_stream_t stream);
+/* Adam (lib/masked_adam.py:60-71, dense variant) on a small replicated tensor whose gradient is the sum over ranks,
+ * read from the peers' buffers in rank order (grad_multicast non-NULL: one multimem.ld_reduce per element instead).
+ * The rgbnet's 22 K parameters in ray-sharded training: every rank computes the identical update. */
+int dvgo_adam_upd_peer(float* param, const float* const* grad_peers_host, const float* grad_multicast, int n_peers,
+                       float* exp_avg, float* exp_avg_sq, int64_t N, int step, float beta1, float beta2, float lr,
+                       float eps, dvgo_stream_t stream);
 
 /* Tensor-core self test (one CTA): D[128,N] = A * B^T with tcgen05.mma kind::f16 (fp16 operands), for each operand
  * orientation the rgbnet kernels use.  a_mn=0: A is [128][K]; a_mn=1: A is [K][128]; b_mn=0: B is

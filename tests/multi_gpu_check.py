@@ -38,27 +38,35 @@ def main():
     base = base.to(dev)
     cfg, rk = dict(syn.FINE_TRAIN), dict(syn.RENDER_KWARGS)
     ok = True
-    for exchange, shard in (("auto", True), ("peer_p2p", True), ("nccl", True), ("nccl", False)):
+    # mlp='torch': exact fp32 rgbnet, NCCL for its gradient; mlp='tc': tensor-core rgbnet, flag barriers + peer Adam
+    for exchange, shard, mlp, ltol in (("auto", True, "torch", 2e-5), ("peer_p2p", True, "torch", 2e-5),
+                                       ("nccl", True, "torch", 2e-5), ("nccl", False, "torch", 2e-5),
+                                       ("auto", True, "tc", 1e-3), ("peer_p2p", True, "tc", 1e-3), ("peer", True, "tc", 1e-3)):
         m_dp, m_one = copy.deepcopy(base), copy.deepcopy(base)
-        t_dp = FusedTrainer(m_dp, cfg, rk, world_size=world, mlp="torch", shard_sweep=shard, exchange=exchange)
+        try:
+            t_dp = FusedTrainer(m_dp, cfg, rk, world_size=world, mlp=mlp, shard_sweep=shard, exchange=exchange)
+        except RuntimeError as e:      # "peer" (multicast required) on a system without NVLS
+            if rank == 0:
+                print("exchange=%s mlp=%s unavailable: %s" % (exchange, mlp, str(e)[:80]))
+            continue
         if rank == 0:
-            print("requested exchange=%s shard_sweep=%s -> running %s (multicast %s)" % (
-                exchange, shard, t_dp.exchange, getattr(t_dp, "multicast", False)))
-        t_one = FusedTrainer(m_one, cfg, rk, world_size=1, mlp="torch")
+            print("requested exchange=%s shard_sweep=%s mlp=%s -> running %s (multicast %s, flag barriers %s)" % (
+                exchange, shard, mlp, t_dp.exchange, getattr(t_dp, "multicast", False), t_dp._flags is not None))
+        t_one = FusedTrainer(m_one, cfg, rk, world_size=1, mlp=mlp)
         for it in range(3):
             batch = syn.random_training_rays(4096, n_views=20, seed=90 + it, device=dev)
             mine = tuple(t.contiguous() for t in shard_rays(batch, rank, world))
             l_dp = t_dp.step(*mine)
             dist.all_reduce(l_dp)
             l_one = t_one.step(*batch)
-            if abs(float(l_dp) - float(l_one)) > 2e-5 * max(1.0, abs(float(l_one))):
+            if abs(float(l_dp) - float(l_one)) > ltol * max(1.0, abs(float(l_one))):
                 ok = False
                 print("rank", rank, t_dp.exchange, "shard", shard, "it", it, "loss mismatch", float(l_dp), float(l_one))
         t_dp.sync_to_model(); t_one.sync_to_model()
         for name in ("density", "k0"):
             d = (getattr(m_dp, name) - getattr(m_one, name)).abs()
             med, q = float(d.median()), float(torch.quantile(d.flatten()[:4_000_000], 0.999))
-            if not (med < 1e-4 and q < 5e-3):
+            if not (med < (1e-4 if mlp == "torch" else 2e-3) and q < (5e-3 if mlp == "torch" else 0.25)):
                 ok = False
             if rank == 0:
                 print("%s shard_sweep=%s %s: median |d| %.2e, 99.9%% %.2e" % (t_dp.exchange, shard, name, med, q))
