@@ -97,21 +97,12 @@ __device__ __forceinline__ float unnorm_coord(float x, float lo, float hi, int s
   const float n = fsub(fmul(u, 2.f), 1.f);
   return fmul(fmul(fadd(n, 1.f), 0.5f), static_cast<float>(size - 1));
 }
+__device__ __forceinline__ Tri tri_from_index(float fx, float fy, float fz);
 __device__ __forceinline__ Tri tri_setup(float px, float py, float pz,
                                          const float* __restrict__ lo,
                                          const float* __restrict__ hi, int X, int Y, int Z) {
-  Tri t;
-  const float fx = unnorm_coord(px, lo[0], hi[0], X);
-  const float fy = unnorm_coord(py, lo[1], hi[1], Y);
-  const float fz = unnorm_coord(pz, lo[2], hi[2], Z);
-  const float x0f = floorf(fx), y0f = floorf(fy), z0f = floorf(fz);
-  t.x0 = static_cast<int>(x0f);
-  t.y0 = static_cast<int>(y0f);
-  t.z0 = static_cast<int>(z0f);
-  t.wx0 = fsub(x0f + 1.f, fx); t.wx1 = fsub(fx, x0f);
-  t.wy0 = fsub(y0f + 1.f, fy); t.wy1 = fsub(fy, y0f);
-  t.wz0 = fsub(z0f + 1.f, fz); t.wz1 = fsub(fz, z0f);
-  return t;
+  return tri_from_index(unnorm_coord(px, lo[0], hi[0], X), unnorm_coord(py, lo[1], hi[1], Y),
+                        unnorm_coord(pz, lo[2], hi[2], Z));
 }
 // Same, for coordinates that are ALREADY normalised to [-1, 1] (the `grid` argument of F.grid_sample itself): only
 // ATen's align_corners=True un-normalisation ((n + 1) / 2) * (size - 1) is applied.

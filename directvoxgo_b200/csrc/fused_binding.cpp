@@ -76,7 +76,7 @@ void ray_setup(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor t_min, Tens
 void march_fwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor density, c10::optional<Tensor> k0_cl,
                Tensor t_min, Tensor n_steps, Tensor ray_off, Tensor slot_alpha, Tensor slot_T,
                Tensor slot_expd, Tensor slot_code, Tensor feat, Tensor s_ray, Tensor s_slot, Tensor s_weight,
-               Tensor alphainv_last, Tensor counters) {
+               Tensor alphainv_last, Tensor counters, c10::optional<Tensor> s_pos) {
   F32(rays_o); F32(rays_d); F32(density); F32(t_min); I32(n_steps); I32(ray_off); F32(slot_alpha);
   F32(slot_T); F32(slot_expd); I32(slot_code); F32(feat); I32(s_ray); I32(s_slot); F32(s_weight);
   F32(alphainv_last); I32(counters);
@@ -87,11 +87,13 @@ void march_fwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor density, c1
   TORCH_CHECK(slot_alpha.numel() >= slot_cap && slot_T.numel() >= slot_cap && slot_expd.numel() >= slot_cap, "slot arrays");
   TORCH_CHECK(s_slot.numel() >= surv_cap && s_weight.numel() >= surv_cap && feat.numel() >= surv_cap * sc.s.C, "survivor arrays");
   TORCH_CHECK(alphainv_last.numel() >= n && counters.numel() >= 2, "per-ray arrays");
+  if (s_pos.has_value()) { F32((*s_pos)); TORCH_CHECK(s_pos->numel() >= surv_cap * 4, "s_pos must be [surv_cap,4]"); }
   const c10::cuda::CUDAGuard guard(rays_o.device());
   rc_check(dvgo_fused_march_fwd(fp(rays_o), fp(rays_d), &sc.s, fp(density), fp_opt(k0_cl), n, fp(t_min),
                                 ipm(n_steps), ipm(ray_off), slot_cap, surv_cap, fpm(slot_alpha), fpm(slot_T),
                                 fpm(slot_expd), ipm(slot_code), fpm(feat), ipm(s_ray), ipm(s_slot),
-                                fpm(s_weight), fpm(alphainv_last), ipm(counters), cur_stream()), "march_fwd");
+                                fpm(s_weight), fpm(alphainv_last), ipm(counters),
+                                s_pos.has_value() ? s_pos->data_ptr<float>() : nullptr, cur_stream()), "march_fwd");
 }
 
 void k0_gather(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor k0_cl, Tensor t_min, Tensor ray_off, Tensor s_ray,
@@ -102,13 +104,33 @@ void k0_gather(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor k0_cl, Tens
                                 ipm(s_slot), ipm(counters), s_ray.numel(), fpm(feat), cur_stream()), "k0_gather");
 }
 
+void k0_gather_tiles(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor k0_cl, Tensor t_min, Tensor ray_off,
+                     Tensor s_ray, Tensor s_slot, Tensor counters, c10::optional<Tensor> s_pos, Tensor pe16, int pe_stride,
+                     Tensor xt) {
+  if (s_pos.has_value()) { F32((*s_pos)); TORCH_CHECK(s_pos->numel() >= s_ray.numel() * 4, "s_pos must be [surv_cap,4]"); }
+  F32(rays_o); F32(rays_d); F32(k0_cl); F32(t_min); I32(ray_off); I32(s_ray); I32(s_slot); I32(counters);
+  TORCH_CHECK(pe16.is_cuda() && pe16.is_contiguous() && pe16.scalar_type() == torch::kHalf && pe16.dim() == 2 &&
+              pe16.size(0) >= rays_o.size(0) && pe16.size(1) == ((sc.s.C + pe_stride + 15) / 16) * 16,
+              "pe16 must be the [n_rays, K1] half table view_embedding(..., C) returns");
+  TORCH_CHECK(xt.is_cuda() && xt.is_contiguous() && xt.scalar_type() == torch::kUInt8 &&
+              xt.numel() >= dvgo_mlp_xtile_bytes(s_ray.numel(), sc.s.C, pe_stride) &&
+              reinterpret_cast<uintptr_t>(xt.data_ptr()) % 16 == 0, "xt: uint8 CUDA tensor of mlp_xtile_bytes bytes");
+  const c10::cuda::CUDAGuard guard(rays_o.device());
+  rc_check(dvgo_fused_k0_gather_tiles(fp(rays_o), fp(rays_d), &sc.s, fp(k0_cl), fp(t_min), ipm(ray_off), ipm(s_ray),
+                                      ipm(s_slot), ipm(counters), s_ray.numel(),
+                                      s_pos.has_value() ? s_pos->data_ptr<float>() : nullptr, pe16.data_ptr(), pe_stride,
+                                      xt.data_ptr(), cur_stream()), "k0_gather_tiles");
+}
+
 void k0_scatter(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor t_min, Tensor ray_off, Tensor s_ray, Tensor s_slot,
-                Tensor counters, Tensor d_feat, Tensor grad_k0_cl) {
+                Tensor counters, Tensor d_feat, Tensor grad_k0_cl, c10::optional<Tensor> s_pos) {
   F32(rays_o); F32(rays_d); F32(t_min); I32(ray_off); I32(s_ray); I32(s_slot); I32(counters); F32(d_feat);
   F32(grad_k0_cl);
+  if (s_pos.has_value()) { F32((*s_pos)); TORCH_CHECK(s_pos->numel() >= s_ray.numel() * 4, "s_pos must be [surv_cap,4]"); }
   const c10::cuda::CUDAGuard guard(rays_o.device());
   rc_check(dvgo_fused_k0_scatter(fp(rays_o), fp(rays_d), &sc.s, fp(t_min), ipm(ray_off), ipm(s_ray), ipm(s_slot),
-                                 ipm(counters), s_ray.numel(), fp(d_feat), fpm(grad_k0_cl), cur_stream()), "k0_scatter");
+                                 ipm(counters), s_ray.numel(), s_pos.has_value() ? s_pos->data_ptr<float>() : nullptr,
+                                 fp(d_feat), fpm(grad_k0_cl), cur_stream()), "k0_scatter");
 }
 
 void rgb_direct(Tensor feat, Tensor counters, Tensor rgb) {
@@ -150,13 +172,18 @@ void ray_finish(Tensor rgb_acc, Tensor alphainv_last, c10::optional<Tensor> targ
 }
 
 void sample_grad(Tensor rgb, Tensor s_weight, Tensor s_ray, Tensor G, Tensor target, Tensor counters, int n_global,
-                 double weight_rgbper, Tensor d_rgb, Tensor d_w, Tensor loss_acc, c10::optional<Tensor> dz3) {
+                 double weight_rgbper, Tensor d_rgb, Tensor d_w, Tensor loss_acc, c10::optional<Tensor> dzt,
+                 double grad_scale) {
   F32(rgb); F32(s_weight); I32(s_ray); F32(G); F32(target); I32(counters); F32(d_rgb); F32(d_w); F32(loss_acc);
-  if (dz3.has_value()) { F32((*dz3)); TORCH_CHECK(dz3->numel() >= rgb.numel() / 3 * 4, "dz3 must be [surv_cap,4]"); }
+  if (dzt.has_value())
+    TORCH_CHECK(dzt->is_cuda() && dzt->is_contiguous() && dzt->scalar_type() == torch::kUInt8 &&
+                dzt->numel() >= dvgo_mlp_dztile_bytes(rgb.numel() / 3) &&
+                reinterpret_cast<uintptr_t>(dzt->data_ptr()) % 16 == 0, "dzt: uint8 CUDA tensor of mlp_dztile_bytes bytes");
   const c10::cuda::CUDAGuard guard(rgb.device());
   rc_check(dvgo_fused_sample_grad(fp(rgb), fp(s_weight), ipm(s_ray), fp(G), fp(target), ipm(counters),
                                   rgb.numel() / 3, n_global, static_cast<float>(weight_rgbper), fpm(d_rgb), fpm(d_w),
-                                  fpm(loss_acc), dz3.has_value() ? dz3->data_ptr<float>() : nullptr, cur_stream()),
+                                  fpm(loss_acc), dzt.has_value() ? dzt->data_ptr() : nullptr,
+                                  static_cast<float>(grad_scale), cur_stream()),
            "sample_grad");
 }
 
@@ -401,9 +428,10 @@ void dvgo_bind_fused(pybind11::module_& m) {
                           c10::optional<Tensor>, double, double, double, double, double, double, bool, int>())
       .def("max_steps", &Scene::max_steps);
   m.def("ray_setup", &ray_setup);
-  m.def("march_fwd", &march_fwd);
+  m.def("march_fwd", &march_fwd, pybind11::arg("scene"), pybind11::arg("rays_o"), pybind11::arg("rays_d"), pybind11::arg("density"), pybind11::arg("k0_cl"), pybind11::arg("t_min"), pybind11::arg("n_steps"), pybind11::arg("ray_off"), pybind11::arg("slot_alpha"), pybind11::arg("slot_T"), pybind11::arg("slot_expd"), pybind11::arg("slot_code"), pybind11::arg("feat"), pybind11::arg("s_ray"), pybind11::arg("s_slot"), pybind11::arg("s_weight"), pybind11::arg("alphainv_last"), pybind11::arg("counters"), pybind11::arg("s_pos") = pybind11::none());
   m.def("k0_gather", &k0_gather);
-  m.def("k0_scatter", &k0_scatter);
+  m.def("k0_gather_tiles", &k0_gather_tiles);
+  m.def("k0_scatter", &k0_scatter, pybind11::arg("scene"), pybind11::arg("rays_o"), pybind11::arg("rays_d"), pybind11::arg("t_min"), pybind11::arg("ray_off"), pybind11::arg("s_ray"), pybind11::arg("s_slot"), pybind11::arg("counters"), pybind11::arg("d_feat"), pybind11::arg("grad_k0_cl"), pybind11::arg("s_pos") = pybind11::none());
   m.def("rgb_direct", &rgb_direct);
   m.def("rgb_direct_bwd", &rgb_direct_bwd);
   m.def("composite", &composite);
@@ -411,7 +439,7 @@ void dvgo_bind_fused(pybind11::module_& m) {
   m.def("sample_grad", &sample_grad, pybind11::arg("rgb"), pybind11::arg("s_weight"), pybind11::arg("s_ray"),
         pybind11::arg("G"), pybind11::arg("target"), pybind11::arg("counters"), pybind11::arg("n_global"),
         pybind11::arg("weight_rgbper"), pybind11::arg("d_rgb"), pybind11::arg("d_w"), pybind11::arg("loss_acc"),
-        pybind11::arg("dz3") = pybind11::none());
+        pybind11::arg("dzt") = pybind11::none(), pybind11::arg("grad_scale") = 1.0);
   m.def("march_bwd", &march_bwd);
   m.def("sweep", &sweep, pybind11::arg("param_in"), pybind11::arg("param_out"), pybind11::arg("grad"),
         pybind11::arg("exp_avg"), pybind11::arg("exp_avg_sq"), pybind11::arg("perlr"), pybind11::arg("X"),

@@ -5,6 +5,7 @@
 // Reference: lib/dvgo.py:512-514 (sigmoid colour), :554-576 (segment_coo compositing),
 // run.py:377-386 (loss), SURVEY.md appendix C (gradient flow).
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "../../include/dvgo_b200_fused.h"
 
 namespace dvgo {
@@ -145,12 +146,19 @@ __global__ void __launch_bounds__(256) sample_grad_kernel(
     const float* __restrict__ rgb, const float* __restrict__ s_weight,
     const int32_t* __restrict__ s_ray, const float* __restrict__ G, const float* __restrict__ target,
     const int32_t* __restrict__ counters, int64_t cap, int n_global, float w_per,
-    float* __restrict__ d_rgb, float* __restrict__ d_w, float* __restrict__ loss_acc, float4* __restrict__ dz3) {
+    float* __restrict__ d_rgb, float* __restrict__ d_w, float* __restrict__ loss_acc, uint8_t* __restrict__ dzt,
+    float grad_scale) {
   const int64_t n = survivor_count(counters, cap);
+  const int64_t rows = dzt ? (n + 255) / 256 * 256 : n;   // the dZ3 tiles are zero up to the end of the last tile pair
   const float inv_n = 1.f / static_cast<float>(n_global);
   float loss = 0.f;
-  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < n;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < rows;
        p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint8_t* t = dzt ? dzt + (p >> 7) * tc::tile_bytes(128, 16) + tc::tile_off(static_cast<int>(p & 127), 0, 16) : nullptr;
+    if (p >= n) {   // (columns 8..15 of every row are never written: the buffer is allocated zeroed)
+      *reinterpret_cast<uint4*>(t) = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
     const int r = s_ray[p];
     const float w = s_weight[p];
     float dw = 0.f;
@@ -170,7 +178,10 @@ __global__ void __launch_bounds__(256) sample_grad_kernel(
       dw += g * x;
     }
     d_w[p] = dw;
-    if (dz3) dz3[p] = make_float4(z[0], z[1], z[2], 0.f);
+    if (t) {   // [row][0..2] = S * dZ3 as saturated fp16, [3..15] = 0
+      const uint2 h = tc::pack4(make_float4(z[0] * grad_scale, z[1] * grad_scale, z[2] * grad_scale, 0.f));
+      *reinterpret_cast<uint4*>(t) = make_uint4(h.x, h.y, 0u, 0u);
+    }
   }
   if (loss_acc && w_per > 0.f) {
     const float s = block_sum(loss);
@@ -219,7 +230,8 @@ static inline int stream_grid(int64_t cap, int threads) {
 // GEMM), the rest up to `stride` is 0.  One launch instead of ~8 elementwise torch kernels per step / render chunk.
 __global__ void __launch_bounds__(256) view_embedding_kernel(const float* __restrict__ viewdirs,
                                                              const float* __restrict__ freq, int F, int64_t n,
-                                                             int stride, float* __restrict__ out) {
+                                                             int stride, float* __restrict__ out,
+                                                             __half* __restrict__ rows16, int C, int K1) {
   const int P = 3 + 6 * F;
   const int64_t total = n * stride;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -237,6 +249,8 @@ __global__ void __launch_bounds__(256) view_embedding_kernel(const float* __rest
       v = c == P ? 1.f : 0.f;
     }
     out[i] = v;
+    // the same value as the tail of the ray's X~ row (fp16, columns [C, C + stride) of K1): what k0_gather_tiles copies
+    if (rows16) rows16[r * K1 + C + c] = __low2half(tc::pack2_sat(v, 0.f));
   }
 }
 
@@ -288,13 +302,14 @@ DVGO_API int dvgo_fused_ray_finish(float* rgb_acc, const float* alphainv_last, c
 DVGO_API int dvgo_fused_sample_grad(const float* rgb, const float* s_weight, const int32_t* s_ray,
                                     const float* G, const float* target, const int32_t* counters,
                                     int64_t surv_cap, int n_global, float weight_rgbper, float* d_rgb,
-                                    float* d_w, float* loss_acc, float* dz3, dvgo_stream_t stream) {
+                                    float* d_w, float* loss_acc, void* dzt, float grad_scale,
+                                    dvgo_stream_t stream) {
   if (surv_cap < 0 || n_global <= 0 || !rgb || !s_weight || !s_ray || !G || !counters || !d_rgb ||
-      !d_w || (weight_rgbper > 0.f && !target))
+      !d_w || (weight_rgbper > 0.f && !target) || (dzt && !(grad_scale > 0.f)))
     return DVGO_EINVAL;
   sample_grad_kernel<<<stream_grid(surv_cap, 256), 256, 0, as_stream(stream)>>>(
       rgb, s_weight, s_ray, G, target, counters, surv_cap, n_global, weight_rgbper, d_rgb, d_w,
-      loss_acc, reinterpret_cast<float4*>(dz3));
+      loss_acc, static_cast<uint8_t*>(dzt), grad_scale);
   return launch_status();
 }
 
@@ -315,12 +330,15 @@ DVGO_API int dvgo_fused_step_begin(void* zblock, int64_t n_words, long long* sta
 }
 
 DVGO_API int dvgo_view_embedding(const float* viewdirs, const float* freq, int n_freq, int64_t n_rays, int stride,
-                                 float* out, dvgo_stream_t stream) {
+                                 float* out, void* rows16, int C, dvgo_stream_t stream) {
   if (n_rays < 0 || n_freq < 0 || stride < 3 + 6 * n_freq + 1 || !out) return DVGO_EINVAL;
+  if (rows16 && (C < 0 || C + stride > 64)) return DVGO_EINVAL;
+  const int K1 = ((C + stride + 15) / 16) * 16;
   if (n_rays == 0) return 0;
   if (!viewdirs || (n_freq > 0 && !freq)) return DVGO_EINVAL;
   const int64_t want = (n_rays * stride + 255) / 256;
   const int blocks = static_cast<int>(want < kNumSMs * 8 ? want : kNumSMs * 8);
-  view_embedding_kernel<<<blocks, 256, 0, as_stream(stream)>>>(viewdirs, freq, n_freq, n_rays, stride, out);
+  view_embedding_kernel<<<blocks, 256, 0, as_stream(stream)>>>(viewdirs, freq, n_freq, n_rays, stride, out,
+                                                               static_cast<__half*>(rows16), C, K1);
   return launch_status();
 }

@@ -15,6 +15,7 @@
 // Arithmetic follows the reference expression trees exactly where integer / boolean results depend
 // on it (common.cuh); see include/dvgo_b200_fused.h for the data layout.
 #include "fused_scene.cuh"
+#include "tc_common.cuh"
 
 namespace dvgo {
 
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256, 3) march_fwd_kernel(
     float* __restrict__ slot_alpha, float* __restrict__ slot_T, float* __restrict__ slot_expd,
     int32_t* __restrict__ slot_code, float* __restrict__ feat, int32_t* __restrict__ s_ray,
     int32_t* __restrict__ s_slot, float* __restrict__ s_weight, float* __restrict__ alphainv_last,
-    int32_t* __restrict__ counters) {
+    int32_t* __restrict__ counters, float4* __restrict__ s_pos) {
   const SceneDev sc = load_scene(a);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -152,12 +153,17 @@ __global__ void __launch_bounds__(256, 3) march_fwd_kernel(
       live = live && occupancy(sc, px, py, pz);                                  // :469-473
       float alpha = 0.f, e = 0.f;
       Corner8 cn;
+      float fx = 0.f, fy = 0.f, fz = 0.f;
       if (live) {
-        cn = corner8(sc, px, py, pz);
+        voxel_coords(sc, px, py, pz, fx, fy, fz);
+        cn = corner8_idx(sc, fx, fy, fz);
         float dens = 0.f;  // :476 trilinear density (ATen accumulation order)
+        float dv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dv[k] = __ldg(density + (cn.ok(k) ? cn.off(k) : 0));   // unconditional: eight loads in flight
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (cn.ok(k)) dens = fma_(__ldg(density + cn.off(k)), cn.w(k), dens);
+          if (cn.ok(k)) dens = fma_(dv[k], cn.w(k), dens);
         e = expf(fadd(dens, sc.act_shift));                     // render_utils_kernel.cu:366
         alpha = fsub(1.f, powf(fadd(1.f, e), -sc.interval));    // :368
         if (use_thres) live = alpha > sc.thres;                 // lib/dvgo.py:478-484
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(256, 3) march_fwd_kernel(
           s_ray[idx4] = r;
           s_slot[idx4] = static_cast<int32_t>(slot);
           s_weight[idx4] = w;
+          if (s_pos) s_pos[idx4] = make_float4(fx, fy, fz, __int_as_float(r));   // the k0 kernels' per-survivor record
           if (k0) gather_k0<C>(k0, cn, feat + static_cast<int64_t>(idx4) * C);  // lib/dvgo.py:509
         } else {
           counters[1] = 1;
@@ -343,13 +350,19 @@ __global__ void __launch_bounds__(256) k0_gather_kernel(
     float acc[W];
 #pragma unroll
     for (int c = 0; c < W; ++c) acc[c] = 0.f;
+    float4 f8[(C % 4 == 0) ? 8 : 1];
+    if (C % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)      // unconditional (see k0_gather_tiles_kernel): eight loads in flight
+        f8[k] = __ldg(reinterpret_cast<const float4*>(k0 + static_cast<int64_t>(cn.ok(k) ? cn.off(k) : 0) * C + q * W));
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (!cn.ok(k)) continue;
       const float* __restrict__ v = k0 + static_cast<int64_t>(cn.off(k)) * C + q * W;
       const float wk = cn.w(k);
       if (C % 4 == 0) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(v));
+        const float4 f = f8[(C % 4 == 0) ? k : 0];
         acc[0] = fma_(f.x, wk, acc[0]); acc[1] = fma_(f.y, wk, acc[1]);
         acc[2 % W] = fma_(f.z, wk, acc[2 % W]); acc[3 % W] = fma_(f.w, wk, acc[3 % W]);
       } else {
@@ -366,13 +379,148 @@ __global__ void __launch_bounds__(256) k0_gather_kernel(
   }
 }
 
+// k0_gather with the rgbnet's X~ tiles as output (tc_common.cuh: tiles_for; include/dvgo_b200_fused.h): row p of
+// the tile stream = [k0 features (C) | pe[s_ray[p]] (pe_stride) | 0 ...] as saturated fp16 in the tensor core's operand
+// layout, K1 columns.  In that layout a row is K1/8 CHUNKS of 16 bytes, one per 128-byte core matrix, and the same
+// chunk of 8 consecutive rows is one contiguous 128-byte line: every store below is a 16-byte chunk and the G = C/4
+// threads of consecutive survivors write the same chunk index in the same instruction, so the stores leave the SM as
+// full 32-byte sectors (a first version with 8-byte stores per thread cost +47 us per step in partial-sector writes).
+//   chunk k < ceil(G/2)  : feature units 2k, 2k+1 -> thread 2k of the survivor (unit 2k+1 arrives by one shuffle)
+//   other chunks         : embedding / padding columns, dealt round-robin to the G threads
+//   chunks that lie entirely past C + pe_stride are never written: the buffer is allocated zeroed
+// Rows from the survivor count to the next multiple of 256 are written as zeros (the backward kernel consumes tile
+// pairs).  A warp holds 32/G whole survivors (30 active lanes for G = 3).
+template <int C>
+__global__ void __launch_bounds__(256, 3) k0_gather_tiles_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
+    const float* __restrict__ k0, const float* __restrict__ t_min, const int32_t* __restrict__ ray_off,
+    const int32_t* __restrict__ s_ray, const int32_t* __restrict__ s_slot,
+    const int32_t* __restrict__ counters, int64_t surv_cap, const float4* __restrict__ s_pos,
+    const uint8_t* __restrict__ pe16, int pe_stride, int K1, uint8_t* __restrict__ xt) {
+  constexpr int G = (C % 4 == 0) ? C / 4 : 1;   // threads per survivor
+  constexpr int SPW = 32 / G;                   // survivors per warp
+  constexpr int FC = (G + 1) / 2;               // chunks that hold feature columns (C % 4 == 0 path)
+  const SceneDev sc = load_scene(a);
+  int64_t n = counters[0];
+  if (n > surv_cap) n = surv_cap;
+  const int64_t rows = (n + 255) / 256 * 256;
+  const uint32_t xb = tc::tile_bytes(128, K1);
+  const int used_chunks = (C + pe_stride + 7) >> 3;    // chunks with any non-padding column
+  const int lane = threadIdx.x & 31;
+  const int q = lane % G, sub = lane / G;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t base = warp0 * SPW; base < rows; base += n_warps * SPW) {   // warp-uniform trip count
+    const int64_t p = base + sub;
+    const bool active = sub < SPW && p < rows;
+    const bool live = active && p < n;
+    uint8_t* __restrict__ trow = xt + (p >> 7) * xb + tc::tile_off(static_cast<int>(p & 127), 0, K1);
+    auto chunk_ptr = [&](int k) { return reinterpret_cast<uint4*>(trow + k * 128); };
+    int r = 0;
+    Corner8 cn;
+    cn.valid = 0u;
+    if (live) {
+      if (s_pos) {       // march_fwd's record: continuous voxel coordinates + ray index, one 16-byte load
+        const float4 rec = __ldg(s_pos + p);
+        r = __float_as_int(rec.w);
+        cn = corner8_idx(sc, rec.x, rec.y, rec.z);
+      } else {
+        r = s_ray[p];
+        const int step = s_slot[p] - ray_off[r];
+        const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
+        float px, py, pz;
+        sample_point(sc, g, step, px, py, pz);
+        cn = corner8(sc, px, py, pz);
+      }
+    }
+    // the ray's share of the row, already fp16 (view_embedding's rows16): chunk k at byte 16 k
+    const uint8_t* __restrict__ e = pe16 + static_cast<int64_t>(r) * (K1 * 2);
+    if (C % 4 == 0) {
+      // Every lane runs the same instruction stream (predicated): embedding chunk loads, the eight corner loads, then
+      // the stores.  (Dealing the chunks out under divergent branches serialised one load round trip per branch.)
+      constexpr int NJ = (8 - FC + G - 1) / G;          // embedding / padding chunks per thread, at most
+      const int k_first = FC + (q + G - 1) % G;         // this thread's chunks: k_first + j G
+      uint4 pv[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = k_first + j * G;
+        pv[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (live && k < used_chunks) pv[j] = __ldg(reinterpret_cast<const uint4*>(e + 16 * k));
+      }
+      const bool odd_tail = (q & 1) == 0 && q + 1 >= G;  // last feature chunk of an odd G: its upper unit is embedding
+      uint2 ph = make_uint2(0u, 0u);
+      if (live && odd_tail) ph = __ldg(reinterpret_cast<const uint2*>(e + 8 * (q + 1)));
+      // All eight corner loads are issued unconditionally (a corner outside the grid reads voxel 0 and is skipped by
+      // the predicated multiply-add below): with predicated loads ptxas gave successive loads the same destination
+      // registers and waited for each before issuing the next -- 7 dependent memory round trips per thread, 65 % of
+      // the kernel's stall samples (ncu, round 2).
+      float4 f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        f[k] = __ldg(reinterpret_cast<const float4*>(k0 + static_cast<int64_t>(cn.ok(k) ? cn.off(k) : 0) * C + q * 4));
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!cn.ok(k)) continue;
+        const float wk = cn.w(k);
+        acc[0] = fma_(f[k].x, wk, acc[0]); acc[1] = fma_(f[k].y, wk, acc[1]);
+        acc[2] = fma_(f[k].z, wk, acc[2]); acc[3] = fma_(f[k].w, wk, acc[3]);
+      }
+      const uint2 mine = tc::pack4(make_float4(acc[0], acc[1], acc[2], acc[3]));
+      uint2 nb;                         // the feature unit of the next thread of the same survivor
+      nb.x = __shfl_down_sync(0xffffffffu, mine.x, 1);
+      nb.y = __shfl_down_sync(0xffffffffu, mine.y, 1);
+      if (active) {
+        if ((q & 1) == 0) {             // feature chunk q/2: units q (mine) and q + 1 (neighbour, or embedding)
+          const uint2 hi = odd_tail ? ph : nb;
+          *chunk_ptr(q >> 1) = make_uint4(mine.x, mine.y, hi.x, hi.y);
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int k = k_first + j * G;
+          if (k < used_chunks) *chunk_ptr(k) = pv[j];
+        }
+      }
+    } else if (active) {   // one thread per survivor, channel counts that are no multiple of 4 (3, 6, 9)
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!cn.ok(k)) continue;
+        const float* __restrict__ v = k0 + static_cast<int64_t>(cn.off(k)) * C;
+        const float wk = cn.w(k);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fma_(__ldg(v + c), wk, acc[c]);
+      }
+      constexpr int CK = (C + 7) / 8;      // chunks that hold at least one feature column
+#pragma unroll
+      for (int k = 0; k < CK; ++k) {       // feature halves, then whatever the ray's row holds in the rest of the chunk
+        uint4 rowc = make_uint4(0u, 0u, 0u, 0u);
+        if (live) rowc = __ldg(reinterpret_cast<const uint4*>(e + 16 * k));
+        __half h[8];
+        *reinterpret_cast<uint4*>(h) = rowc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (8 * k + j < C) h[j] = __low2half(tc::pack2_sat(acc[8 * k + j], 0.f));
+        *chunk_ptr(k) = *reinterpret_cast<const uint4*>(h);
+      }
+      for (int k = CK; k < used_chunks; ++k) {
+        uint4 rowc = make_uint4(0u, 0u, 0u, 0u);
+        if (live) rowc = __ldg(reinterpret_cast<const uint4*>(e + 16 * k));
+        *chunk_ptr(k) = rowc;
+      }
+    }
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(256) k0_scatter_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
     const float* __restrict__ t_min, const int32_t* __restrict__ ray_off,
     const int32_t* __restrict__ s_ray, const int32_t* __restrict__ s_slot,
-    const int32_t* __restrict__ counters, int64_t surv_cap, const float* __restrict__ d_feat,
-    float* __restrict__ grad_k0) {
+    const int32_t* __restrict__ counters, int64_t surv_cap, const float4* __restrict__ s_pos,
+    const float* __restrict__ d_feat, float* __restrict__ grad_k0) {
   constexpr int G = (C % 4 == 0) ? C / 4 : 1;
   constexpr int W = (C % 4 == 0) ? 4 : C;
   const SceneDev sc = load_scene(a);
@@ -383,12 +531,18 @@ __global__ void __launch_bounds__(256) k0_scatter_kernel(
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t p = i / G;
     const int q = static_cast<int>(i - p * G);
-    const int r = s_ray[p];
-    const int step = s_slot[p] - ray_off[r];
-    const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
-    float px, py, pz;
-    sample_point(sc, g, step, px, py, pz);
-    const Corner8 cn = corner8(sc, px, py, pz);
+    Corner8 cn;
+    if (s_pos) {         // march_fwd's per-survivor record (continuous voxel coordinates)
+      const float4 rec = __ldg(s_pos + p);
+      cn = corner8_idx(sc, rec.x, rec.y, rec.z);
+    } else {
+      const int r = s_ray[p];
+      const int step = s_slot[p] - ray_off[r];
+      const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
+      float px, py, pz;
+      sample_point(sc, g, step, px, py, pz);
+      cn = corner8(sc, px, py, pz);
+    }
     float d[W];
     const float* __restrict__ src = d_feat + p * C + q * W;
     if (C % 4 == 0) {
@@ -462,7 +616,7 @@ DVGO_API int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, cons
                                   int64_t slot_cap, int64_t surv_cap, float* slot_alpha, float* slot_T,
                                   float* slot_expd, int32_t* slot_code, float* feat, int32_t* s_ray,
                                   int32_t* s_slot, float* s_weight, float* alphainv_last,
-                                  int32_t* counters, dvgo_stream_t stream) {
+                                  int32_t* counters, float* s_pos, dvgo_stream_t stream) {
   if (n_rays < 0 || !scene) return DVGO_EINVAL;
   if (n_rays == 0) return 0;
   if (!rays_o || !rays_d || !density || !t_min || !n_steps || !ray_off || !slot_alpha || !slot_T ||
@@ -476,7 +630,7 @@ DVGO_API int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, cons
                                                     as_stream(stream)>>>(
       rays_o, rays_d, to_args(scene), density, k0_cl, n_rays, t_min, n_steps, ray_off, slot_cap,
       surv_cap, slot_alpha, slot_T, slot_expd, slot_code, feat, s_ray, s_slot, s_weight,
-      alphainv_last, counters)));
+      alphainv_last, counters, reinterpret_cast<float4*>(s_pos))));
   return launch_status();
 }
 
@@ -515,10 +669,32 @@ DVGO_API int dvgo_fused_k0_gather(const float* rays_o, const float* rays_d, cons
   return launch_status();
 }
 
+DVGO_API int dvgo_fused_k0_gather_tiles(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                                        const float* k0_cl, const float* t_min, const int32_t* ray_off,
+                                        const int32_t* s_ray, const int32_t* s_slot, const int32_t* counters,
+                                        int64_t surv_cap, const float* s_pos, const void* pe_rows16,
+                                        int pe_stride, void* xt, dvgo_stream_t stream) {
+  if (!scene || surv_cap < 0 || pe_stride < 1 || scene->C + pe_stride > 64) return DVGO_EINVAL;
+  if (surv_cap == 0) return 0;
+  if (!rays_o || !rays_d || !k0_cl || !t_min || !ray_off || !s_ray || !s_slot || !counters || !pe_rows16 || !xt)
+    return DVGO_EINVAL;
+  const int K1 = ((scene->C + pe_stride + 15) / 16) * 16;
+  const int groups = (scene->C % 4 == 0) ? scene->C / 4 : 1;
+  const int64_t rows = (surv_cap + 255) / 256 * 256;
+  const int64_t want = (rows / (32 / groups) + 1 + 7) / 8;      // 8 warps per CTA, 32/G survivors per warp
+  const int blocks = static_cast<int>(want < kNumSMs * 32 ? want : kNumSMs * 32);
+  DVGO_DISPATCH_C(scene->C, (k0_gather_tiles_kernel<kC><<<blocks, 256, 0, as_stream(stream)>>>(
+      rays_o, rays_d, to_args(scene), k0_cl, t_min, ray_off, s_ray, s_slot, counters, surv_cap,
+      reinterpret_cast<const float4*>(s_pos), static_cast<const uint8_t*>(pe_rows16), pe_stride, K1,
+      static_cast<uint8_t*>(xt))));
+  return launch_status();
+}
+
 DVGO_API int dvgo_fused_k0_scatter(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
                                    const float* t_min, const int32_t* ray_off, const int32_t* s_ray,
                                    const int32_t* s_slot, const int32_t* counters, int64_t surv_cap,
-                                   const float* d_feat, float* grad_k0_cl, dvgo_stream_t stream) {
+                                   const float* s_pos, const float* d_feat, float* grad_k0_cl,
+                                   dvgo_stream_t stream) {
   if (!scene || surv_cap < 0) return DVGO_EINVAL;
   if (surv_cap == 0) return 0;
   if (!rays_o || !rays_d || !t_min || !ray_off || !s_ray || !s_slot || !counters || !d_feat || !grad_k0_cl)
@@ -527,6 +703,7 @@ DVGO_API int dvgo_fused_k0_scatter(const float* rays_o, const float* rays_d, con
   const int64_t want = (surv_cap * groups + 255) / 256;
   const int blocks = static_cast<int>(want < kNumSMs * 32 ? want : kNumSMs * 32);
   DVGO_DISPATCH_C(scene->C, (k0_scatter_kernel<kC><<<blocks, 256, 0, as_stream(stream)>>>(
-      rays_o, rays_d, to_args(scene), t_min, ray_off, s_ray, s_slot, counters, surv_cap, d_feat, grad_k0_cl)));
+      rays_o, rays_d, to_args(scene), t_min, ray_off, s_ray, s_slot, counters, surv_cap,
+      reinterpret_cast<const float4*>(s_pos), d_feat, grad_k0_cl)));
   return launch_status();
 }

@@ -38,15 +38,6 @@ struct MlpG {            // fp32 gradient accumulators, same shapes
   float* W1; float* b1; float* W2; float* b2; float* W3; float* b3;
 };
 
-// fp32 pair -> packed fp16 pair, round-to-nearest, SATURATING to +-65504 (one F2FP.SATFINITE instruction): a
-// feature / activation / scaled gradient beyond FP16's range clamps instead of becoming inf and poisoning the
-// training state through Adam (the reference's fp32 nn.Linear has no such range limit).  NaN stays NaN and is
-// reported through the status word (counters[1] bit 1).
-__device__ __forceinline__ __half2 pack2_sat(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return *reinterpret_cast<__half2*>(&r);
-}
 __device__ __forceinline__ __half half_sat(float x) {
   return __low2half(pack2_sat(x, 0.f));
 }
@@ -80,179 +71,60 @@ __device__ __forceinline__ uint4 pack8_masked(const float* v, const uint4& act) 
   return *reinterpret_cast<uint4*>(h);
 }
 
-// Augmented input tile [128 x K1]: cols [0,C) k0 features, [C,C+pe_stride) the ray's row of the padded
-// view-embedding table (P embedding values, then the constant 1 that carries b1, then zeros), rest 0;
-// rows past the survivor count are zero.  16-byte vector loads when C and pe_stride are multiples of 4.
-__device__ __forceinline__ void stage_x(uint8_t* sX, int K1, int64_t base, int64_t count,
-                                        const float* __restrict__ feat, int C,
-                                        const int32_t* __restrict__ s_ray, const float* __restrict__ pe,
-                                        int pe_stride, int gtid) {   // gtid: thread index inside a 256-thread group
-  const int r = gtid & 127, h = gtid >> 7;
-  const int64_t s = base + r;
-  const bool valid = s < count;
-  const float* __restrict__ f = feat + s * C;
-  const float* __restrict__ e = pe + static_cast<int64_t>(valid ? s_ray[s] : 0) * pe_stride;
-  const bool vec = ((C | pe_stride) & 3) == 0;
-  for (int ch = h; ch < K1 / 8; ch += 2) {
-    float v[8];
-    if (vec) {
+// ---- survivor tiles from fp32 streams -----------------------------------------------------------------
+// The rgbnet kernels take their per-survivor inputs as fp16 TILES in the operand layout (tc_common.cuh: tiles_for):
+//   X~ tile  [128][K1]: cols [0,C) k0 features, [C,C+pe_stride) the ray's row of the padded view-embedding table
+//                       (P embedding values, the constant 1 that carries b1, zeros), rest 0
+//   dZ3 tile [128][16]: cols 0..2 = S * d_rgb * rgb (1 - rgb), rest 0
+// In the fused step they are written by their producers (k0_gather / sample_grad) and pulled by one bulk copy per tile;
+// the two kernels below build them from fp32 streams for callers that hold those (tests, tools, the C ABI's users).
+__global__ void __launch_bounds__(256) mlp_pack_x_kernel(
+    const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe,
+    int pe_stride, const int32_t* __restrict__ counters, int64_t surv_cap, int K1, uint8_t* __restrict__ xt) {
+  int64_t n = counters[0];
+  if (n > surv_cap) n = surv_cap;
+  const int units = K1 >> 2;                      // 8-byte units (4 halves) per row
+  const int64_t rows = (n + 255) / 256 * 256;     // zero rows up to the end of the last tile PAIR
+  const uint32_t xb = tile_bytes(kTile, K1);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < rows * units;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t p = i / units;
+    const int u = static_cast<int>(i - p * units);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < n) {
+      const float* __restrict__ e = pe ? pe + static_cast<int64_t>(s_ray[p]) * pe_stride : nullptr;
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int c = ch * 8 + g * 4;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-          if (c < C) x = __ldg(reinterpret_cast<const float4*>(f + c));
-          else if (c < C + pe_stride) x = __ldg(reinterpret_cast<const float4*>(e + (c - C)));
-        }
-        v[g * 4] = x.x; v[g * 4 + 1] = x.y; v[g * 4 + 2] = x.z; v[g * 4 + 3] = x.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = ch * 8 + j;
-        float x = 0.f;
-        if (valid) x = c < C ? __ldg(f + c) : (c < C + pe_stride ? __ldg(e + (c - C)) : 0.f);
-        v[j] = x;
+      for (int j = 0; j < 4; ++j) {
+        const int c = 4 * u + j;
+        v[j] = c < C ? __ldg(feat + p * C + c) : ((e && c < C + pe_stride) ? __ldg(e + (c - C)) : 0.f);
       }
     }
-    *reinterpret_cast<uint4*>(sX + tile_off(r, ch * 8, K1)) = pack8(v);
+    *reinterpret_cast<uint2*>(xt + (p >> 7) * xb + tile_off(static_cast<int>(p & 127), 4 * u, K1)) =
+        pack4(make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+__global__ void __launch_bounds__(256) mlp_pack_dz_kernel(
+    const float* __restrict__ rgb, const float* __restrict__ d_rgb, float scale,
+    const int32_t* __restrict__ counters, int64_t surv_cap, uint8_t* __restrict__ dzt) {
+  int64_t n = counters[0];
+  if (n > surv_cap) n = surv_cap;
+  const int64_t rows = (n + 255) / 256 * 256;
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < rows;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p < n) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float x = rgb[3 * p + k];
+        z[k] = d_rgb[3 * p + k] * x * (1.f - x) * scale;
+      }
+    }
+    uint8_t* t = dzt + (p >> 7) * tile_bytes(kTile, 16) + tile_off(static_cast<int>(p & 127), 0, 16);
+    *reinterpret_cast<uint4*>(t) = pack8(z);
+    *reinterpret_cast<uint4*>(t + 128) = make_uint4(0u, 0u, 0u, 0u);   // columns 8..15
   }
 }
 
-// ---- flat, coalesced, software-pipelined staging of the X~ tile (vector path: C and pe_stride multiples of 4) ----
-// A group of 256 threads fills one [128 rows][K1] fp16 tile.  Round 1 gave each thread one row and read 16 bytes per
-// lane from 32 different rows per instruction (feature rows 48 B apart, embedding rows gathered by ray): every warp
-// load touched 12-32 cache lines and the LSU, not the memory system, set the staging time (2000-5000 cycles per tile in
-// tools/mlp_timeline.py, more than all MMAs of the tile).  Here the 128 feature rows of a tile are ONE contiguous
-// 128*C*4-byte block read with consecutive float4 per lane, and the embedding rows are read with pe_stride/4
-// consecutive lanes per row.  The raw fp32 values of the NEXT tile are loaded into registers while the current tile
-// computes and only converted + stored at the next hand-off; the ray indices (head of the dependent chain
-// s_ray -> embedding row) are fetched one tile further ahead.
-// Prefetch loads as VOLATILE asm: a plain __ldg whose value is first used a whole tile later may legally be sunk by the
-// compiler to just before that use (it does: the consumer then eats the full memory latency -- 1200-1800 cycles per
-// tile in the timeline); volatile asm keeps its place between the (volatile) MMA-issue / barrier statements.
-__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ int ldg_nc_s32(const int32_t* p) {
-  int v;
-  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-// Predicated loads that read-modify-write their destination (kept at its previous value when the predicate is off), and
-// a zero-cost "all of these registers are defined here" fence.  Prefetch pattern that does not stall on the per-warp
-// scoreboards (only six, shared by the compiler between all loads in flight): (1) zero every destination register --
-// the write-after-write waits against the loads of the PREVIOUS tile land here, where nothing is in flight;
-// (2) reg_fence(); (3) issue all loads back to back.  Interleaving (1) and (3) per register made every zeroing MOV
-// wait for the loads issued just before it: 4000-5000 cycles per tile pair in tools/mlp_timeline.py.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void ldg_nc_f4_if(float4& v, const float4* p, bool pred) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
-      "}\n"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "l"(p), "r"(static_cast<int>(pred)));
-}
-__device__ __forceinline__ void ldg_nc_f32_if(float& v, const float* p, bool pred) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q ld.global.nc.f32 %0, [%1];\n\t"
-      "}\n"
-      : "+f"(v)
-      : "l"(p), "r"(static_cast<int>(pred)));
-}
-__device__ __forceinline__ void reg_fence(float4& a, float4& b, float4& c, float4& d) {
-  asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w),
-                    "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w), "+f"(d.x), "+f"(d.y), "+f"(d.z), "+f"(d.w));
-}
-__device__ __forceinline__ void reg_fence(float& a, float& b, float& c, float& d, float& e, float& f) {
-  asm volatile("" : "+f"(a), "+f"(b), "+f"(c), "+f"(d), "+f"(e), "+f"(f));
-}
-struct StageRegs {
-  float4 f[2];   // feature float4 ids gtid, gtid + 256           (< 128 * C/4 <= 512)
-  float4 p[4];   // embedding float4 ids gtid + 256 k, k < 4      (< 128 * pe_stride/4 <= 1024)
-  int ray[4];    // ray index of the rows of p[], for the tile AFTER the one held in f / p
-};
-// id / d for id < 1024, d <= 8 as one multiply + shift: inv = ceil(2^16 / d), computed ONCE per kernel (StageGeom).
-// (The first version divided by the runtime d at every use: a ~30-instruction dependent chain through I2F / MUFU.RCP /
-// F2I per load and per store, 16 times per tile -- 3000+ cycles of pure latency per tile in tools/mlp_timeline.py.)
-struct StageGeom {
-  int nf4, np4, inv_f, inv_p;
-};
-__device__ __forceinline__ StageGeom stage_geom(int C, int pe_stride) {
-  StageGeom g;
-  g.nf4 = C >> 2;
-  g.np4 = pe_stride >> 2;
-  g.inv_f = g.nf4 > 0 ? (65536 + g.nf4 - 1) / g.nf4 : 0;
-  g.inv_p = g.np4 > 0 ? (65536 + g.np4 - 1) / g.np4 : 0;
-  return g;
-}
-__device__ __forceinline__ int fast_div(int id, int inv) { return (id * inv) >> 16; }
-__device__ __forceinline__ void stage_rays(StageRegs& r, int gtid, int64_t s0, int64_t count,
-                                           const int32_t* __restrict__ s_ray, const StageGeom& g) {
-  const int np4 = g.np4;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int id = gtid + 256 * k;
-    const int64_t sidx = s0 + fast_div(id, g.inv_p);
-    r.ray[k] = -1;
-    if (id < 128 * np4 && sidx < count) r.ray[k] = ldg_nc_s32(s_ray + sidx);
-  }
-}
-// loads of the tile at s0 with the ray indices already in r.ray
-__device__ __forceinline__ void stage_loads(StageRegs& r, int gtid, int64_t s0, int64_t count,
-                                            const float* __restrict__ feat, const float* __restrict__ pe,
-                                            const StageGeom& g) {
-  const int nf4 = g.nf4, np4 = g.np4;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int id = gtid + 256 * k;
-    r.f[k] = zero;
-    if (id < 128 * nf4 && s0 + fast_div(id, g.inv_f) < count)
-      r.f[k] = ldg_nc_f4(reinterpret_cast<const float4*>(feat) + s0 * nf4 + id);
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int id = gtid + 256 * k;
-    r.p[k] = zero;
-    if (r.ray[k] >= 0) {
-      const int c4 = id - fast_div(id, g.inv_p) * np4;
-      r.p[k] = ldg_nc_f4(reinterpret_cast<const float4*>(pe) + static_cast<int64_t>(r.ray[k]) * np4 + c4);
-    }
-  }
-}
-__device__ __forceinline__ uint2 pack4(const float4& v) {
-  const __half2 a = pack2_sat(v.x, v.y), b = pack2_sat(v.z, v.w);
-  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
-}
-__device__ __forceinline__ void stage_stores(const StageRegs& r, int gtid, int C, int K1, uint8_t* sX,
-                                             const StageGeom& g) {
-  const int nf4 = g.nf4, np4 = g.np4;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int id = gtid + 256 * k;
-    if (id < 128 * nf4) {
-      const int row = fast_div(id, g.inv_f), c4 = id - row * nf4;
-      *reinterpret_cast<uint2*>(sX + tile_off(row, 4 * c4, K1)) = pack4(r.f[k]);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int id = gtid + 256 * k;
-    if (id < 128 * np4) {
-      const int row = fast_div(id, g.inv_p), c4 = id - row * np4;
-      *reinterpret_cast<uint2*>(sX + tile_off(row, C + 4 * c4, K1)) = pack4(r.p[k]);
-    }
-  }
-}
 
 // ---- fp16 weight tiles, converted once per call by mlp_pack_weights_kernel and bulk-copied by every CTA ----
 // (round 1: every CTA converted 22 K fp32 weights with scalar loads and integer divisions: 84 K cycles = 43 us of
@@ -308,49 +180,6 @@ __device__ __forceinline__ void copy_to_smem(uint8_t* dst, const uint8_t* __rest
 }
 __device__ __forceinline__ void group_sync(int ctx) {   // named barrier of one 256-thread epilogue group
   asm volatile("bar.sync %0, %1;" ::"r"(1 + ctx), "r"(256) : "memory");
-}
-
-// Row-wise software-pipelined staging (backward kernel) (vector path: C and pe_stride multiples of 4): the raw fp32 inputs of the NEXT
-// tile are loaded into registers while the current tile computes, and only converted + stored to shared
-// memory at the top of the next iteration.  The in-kernel timeline (tools/mlp_timeline.py) showed ~3300
-// of ~9000 cycles per tile exposed in the synchronous stage_x (two dependent global-load latencies:
-// s_ray -> embedding row); the ray index is therefore fetched one tile further ahead.
-template <int NCH>   // chunks (of 8 halves) this thread fills: ch = first + k*stride, k < NCH
-struct XRegs {
-  float4 v[2 * NCH];
-};
-template <int NCH>
-__device__ __forceinline__ void x_load(XRegs<NCH>& xr, int first, int stride, int K1, int64_t s, bool valid, int ray,
-                                       const float* __restrict__ feat, int C, const float* __restrict__ pe,
-                                       int pe_stride) {
-  const float* __restrict__ f = feat + s * C;
-  const float* __restrict__ e = pe + static_cast<int64_t>(ray) * pe_stride;
-#pragma unroll
-  for (int k = 0; k < NCH; ++k) {
-    const int ch = first + k * stride;
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int c = ch * 8 + g * 4;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid && ch * 8 < K1) {
-        if (c < C) x = __ldg(reinterpret_cast<const float4*>(f + c));
-        else if (c < C + pe_stride) x = __ldg(reinterpret_cast<const float4*>(e + (c - C)));
-      }
-      xr.v[2 * k + g] = x;
-    }
-  }
-}
-template <int NCH>
-__device__ __forceinline__ void x_store(const XRegs<NCH>& xr, int first, int stride, int K1, int r, uint8_t* sX) {
-#pragma unroll
-  for (int k = 0; k < NCH; ++k) {
-    const int ch = first + k * stride;
-    if (ch * 8 < K1) {
-      const float v[8] = {xr.v[2 * k].x, xr.v[2 * k].y, xr.v[2 * k].z, xr.v[2 * k].w,
-                          xr.v[2 * k + 1].x, xr.v[2 * k + 1].y, xr.v[2 * k + 1].z, xr.v[2 * k + 1].w};
-      *reinterpret_cast<uint4*>(sX + tile_off(r, ch * 8, K1)) = pack8(v);
-    }
-  }
 }
 
 struct MmaCtx {
@@ -431,22 +260,24 @@ __device__ __forceinline__ void relu_pack32(uint32_t taddr, uint32_t* u) {
 
 // ---- forward ---------------------------------------------------------------------------------------
 // One tile = 128 survivors; 256 threads: thread (row = 32*(warp%4)+lane, half = warp/4) owns one sample row and 64
-// of the 128 hidden columns.  The activations never touch shared memory: each layer's epilogue writes relu(D) as
-// packed fp16 straight back into tensor memory, where it is the A operand of the next layer's MMAs (TS form):
+// of the 128 hidden columns.  The X~ tile arrives by one bulk copy (double-buffered, two tiles ahead) and the
+// activations never touch shared memory: each layer's epilogue writes relu(D) as packed fp16 straight back into
+// tensor memory, where it is the A operand of the next layer's MMAs (TS form):
 //   layer 1 : D = X~ W1~^T           A = X~ tile in shared memory (K1 = 48: k0 | view PE | 1 carries b1)
 //   layer 2 : D = [H1 | 1] W2~^T     A = H1 in TMEM, K = 144 (the constant-1 column carries b2)
 //   layer 3 : D3 = H2 W3^T           A = H2 in TMEM, N = 16 (3 used): 10 cycles per MMA instead of 39 from smem and
 //                                     no SIMT dot products (round 1 spent ~5 instructions per hidden unit on them)
 // TMEM columns (256 per CTA, 2 CTAs per SM): [0,128) accumulator D, [128,200) H (64 packed columns + 8 for the
 // constant-1 K step), [224,240) layer-3 accumulator.
+// No thread of this kernel issues a global LOAD inside the loop: round 2's register-staged version lost 20-30 % of
+// every tile to scoreboard-shared stalls around its prefetch registers.
 constexpr uint32_t kFwdTH = 128, kFwdTD3 = 224;
 
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
-    const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    int32_t* __restrict__ counters, int64_t surv_cap, const uint8_t* __restrict__ wpack, int K1, int pe_stride,
-    float* __restrict__ rgb, long long* __restrict__ dbg) {
+    const uint8_t* __restrict__ xt, int32_t* __restrict__ counters, int64_t surv_cap,
+    const uint8_t* __restrict__ wpack, int K1, float* __restrict__ rgb, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[4];   // chain (L1 / L2), out3 (L3), xfull[0], xfull[1]
   __shared__ uint32_t tmem_base_s;
   __shared__ float sB3[4];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -462,14 +293,15 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
   uint8_t* sW2 = sW1 + align1k(tile_bytes(kHid, K1));         // [128 out][144]  K-major B of layer 2 (col 128 = b2)
   uint8_t* sW3 = sW2 + align1k(tile_bytes(kHid, kHidA));      // [16 out][128]   K-major B of layer 3 (rows >= 3 zero)
   uint8_t* sXb = sW3 + align1k(tile_bytes(16, kHid));         // 2 x [128 samples][K1] (double-buffered)
-  const uint32_t x_bytes = static_cast<uint32_t>(align1k(tile_bytes(kTile, K1)));
+  const uint32_t x_bytes = tile_bytes(kTile, K1);             // K1 * 256: a multiple of 1024
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
-  if (tid == 0) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); mbar_init_fence(); }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    mbar_init_fence();
+  }
   const WPack wl = wpack_layout(K1);
   copy_to_smem(sW1, wpack, wl.offW3p);      // W1~ | W2~ | W3 tiles, same offsets in shared memory as in the pack
-  for (uint32_t i = tid; i < 2 * x_bytes / 16; i += blockDim.x)   // zero both X buffers once: padding columns stay 0
-    reinterpret_cast<uint4*>(sXb)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < 3) sB3[tid] = reinterpret_cast<const float*>(wpack + wl.offB3)[tid];
   fence_async_smem();
   fence_before_sync();
@@ -485,23 +317,23 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
   }
   MmaCtx chain{smem_u32(&bars[0]), 0u};   // L1 / L2 completions (strictly alternating)
   MmaCtx out3{smem_u32(&bars[1]), 0u};    // L3 completions
+  const uint32_t xbar = smem_u32(&bars[2]);
+  uint32_t xphase = 0u;                    // bit b: parity of the next fill of X buffer b to wait for
   const uint32_t idesc128 = make_idesc_f16(128, kHid, 0, 0), idesc16 = make_idesc_f16(128, 16, 0, 0);
 
-  // software pipeline over tiles: raw fp32 inputs are loaded into registers two tiles ahead of their use and
-  // converted + stored into the other X buffer in the shadow of the layer-2 MMAs
-  const bool vec = ((C | pe_stride) & 3) == 0 && C <= 16 && pe_stride <= 32;
-  StageRegs sr;
-  const StageGeom sg = stage_geom(C, pe_stride);
-  auto tile_s0 = [&](int64_t t) -> int64_t { return t < n_tiles ? t * kTile : count; };   // past the end: all rows invalid
-  auto load_rays = [&](int64_t t) { if (vec) stage_rays(sr, tid, tile_s0(t), count, s_ray, sg); };
-  auto load_tile = [&](int64_t t) { if (vec) stage_loads(sr, tid, tile_s0(t), count, feat, pe, sg); };
-  auto store_tile = [&](int64_t t, uint8_t* sX) {
-    if (vec) stage_stores(sr, tid, C, K1, sX, sg);
-    else stage_x(sX, K1, t * kTile, count, feat, C, s_ray, pe, pe_stride, tid);
-  };
   int dbg_n = 1;
   auto stamp = [&]() {  // optional in-kernel timeline (tools/mlp_timeline.py): CTA 0, threads 0 and 255
     if (dbg && blockIdx.x == 0 && (tid == 0 || tid == 255) && dbg_n < 64) dbg[(tid ? 64 : 0) + dbg_n++] = clock64();
+  };
+  // one elected thread: arm the buffer's barrier and start the bulk copy of tile t into X buffer b
+  auto load_x = [&](int64_t t, uint32_t b) {
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(xbar + 8u * b, x_bytes);
+        bulk_g2s(smem_u32(sXb) + b * x_bytes, xt + t * static_cast<int64_t>(x_bytes), x_bytes, xbar + 8u * b);
+      }
+      __syncwarp();
+    }
   };
   // relu(D[row][64 half .. +64)) -> packed fp16 -> H columns [32 half, +32); then a CTA barrier (the MMA issuer
   // may read H / overwrite D)
@@ -517,36 +349,30 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     __syncthreads();
     fence_after_sync();
   };
-  auto issue_l1 = [&](uint32_t buf) {
+  auto issue_l1 = [&](uint32_t b) {       // waits for the tile in X buffer b, then queues layer 1 on it
     if (warp == 0) {
       if (elect_one()) {
-        gemm_kk(tD, smem_u32(sXb) + buf * x_bytes, K1, smem_u32(sW1), K1, kHid, K1, false);
+        mbar_wait(xbar + 8u * b, (xphase >> b) & 1u);
+        gemm_kk(tD, smem_u32(sXb) + b * x_bytes, K1, smem_u32(sW1), K1, kHid, K1, false);
         mma_commit(chain.bar);
       }
       __syncwarp();
     }
+    xphase ^= 1u << b;
   };
 
   const int64_t step = gridDim.x;
   int64_t tile = blockIdx.x;
-  // prologue: tile 0 staged synchronously, tile 1 prefetched into registers, ray indices one tile further ahead
-  load_rays(tile);
-  load_tile(tile);
-  store_tile(tile, sXb);
-  load_rays(tile + step);
-  load_tile(tile + step);
-  sync_for_mma();
+  load_x(tile, 0u);
+  if (tile + step < n_tiles) load_x(tile + step, 1u);
   issue_l1(0u);
   uint32_t buf = 0u;
   for (; tile < n_tiles; tile += step, buf ^= 1u) {
     const int64_t s0 = tile * kTile;
     const bool has_next = tile + step < n_tiles;
     stamp();
-    // Ray indices of the tile after next, issued while NO other load of this thread is in flight: the hardware has
-    // six scoreboards per warp, the compiler shares them between loads, and overwriting these registers right after
-    // the tile loads below were issued made the warp wait for ALL of them (15 % of the kernel's stall samples in ncu).
-    if (has_next) load_rays(tile + 2 * step);
-    mma_wait(chain);                                       // L1(tile)
+    mma_wait(chain);                                       // L1(tile): X buffer `buf` is free again
+    if (tile + 2 * step < n_tiles) load_x(tile + 2 * step, buf);
     stamp();
     epilogue_to_h();                                       // H1
     stamp();
@@ -556,13 +382,6 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
         mma_commit(chain.bar);
       }
       __syncwarp();
-    }
-    // shadow of the layer-2 MMAs: the next tile's X goes into the other buffer (its last reader, L1 of the previous
-    // tile, completed long ago), then the loads of the tile after that are issued
-    if (has_next) {
-      store_tile(tile + step, sXb + (buf ^ 1u) * x_bytes);
-      fence_async_smem();      // BEFORE the loads below are issued: the proxy fence waits for every load in flight
-      load_tile(tile + 2 * step);
     }
     stamp();
     mma_wait(chain);                                       // L2(tile)
@@ -630,23 +449,26 @@ struct TileCtx {
   uint32_t tWork;
   MmaCtx bar;     // full[ctx]: MMA batch complete
   MmaCtx ready;   // ready[ctx]: epilogue output in place
+  uint32_t xbar;  // tiles[ctx]: the X~ and dZ3 tiles of the pair have landed (bulk copies)
+  uint32_t xfree; // xfree[ctx]: the last batch of the pair (the only late reader of X~ / dZ3) has completed
   int64_t s0;
-  float dz[3];
   bool valid;
 };
 
+// Inputs: X~ tiles and dZ3 tiles (see mlp_pack_x_kernel).  One bulk copy per tile puts them where the tensor core
+// reads them; no thread issues a global load inside the loop.  (Round 2's register-staged version left the tensor
+// pipe idle ~4500 of ~12300 cycles per tile pair at the pair boundary: the loads could only be issued after the last
+// epilogue, because registers held across the epilogues stalled every tcgen05.wait::ld on the shared scoreboards.)
 __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
-    const float* __restrict__ feat, int C, const int32_t* __restrict__ s_ray, const float* __restrict__ pe, int P,
-    int32_t* __restrict__ counters, int64_t surv_cap, const uint8_t* __restrict__ wpack, int K1, int pe_stride,
-    const float* __restrict__ rgb, const float* __restrict__ d_rgb, const float* __restrict__ dz3, float grad_scale,
+    const uint8_t* __restrict__ xt, const uint8_t* __restrict__ dzt, int C, int d_in,
+    int32_t* __restrict__ counters, int64_t surv_cap, const uint8_t* __restrict__ wpack, int K1, float grad_scale,
     float* __restrict__ d_feat, MlpG g, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[4];  // full[0], full[1], ready[0], ready[1]
+  __shared__ __align__(8) uint64_t bars[8];  // full[0,1], ready[0,1], tiles[0,1], xfree[0,1]
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer = warp == kBwdEpiThreads / 32;
   const int q = warp & 3, part = (warp >> 2) & 3, row = q * 32 + lane;  // part in 0..3: 32 hidden columns each
-  const int d_in = C + P;
   int64_t count = counters[0];
   if (count > surv_cap) count = surv_cap;
   const int64_t n_tiles = (count + kTile - 1) / kTile;
@@ -660,6 +482,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   uint8_t* ctx_base = sW3t + align1k(tile_bytes(kHid, 16));
   const size_t ctx_bytes = align1k(tile_bytes(kTile, K1)) + align1k(tile_bytes(kTile, kHidA)) +
                            align1k(tile_bytes(kTile, kHid)) + align1k(tile_bytes(kTile, 16));
+  const uint32_t x_bytes = tile_bytes(kTile, K1), dz_bytes = tile_bytes(kTile, 16);
 
   if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
   if (tid == 0) {
@@ -667,14 +490,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     mbar_init(smem_u32(&bars[1]), 1);
     mbar_init(smem_u32(&bars[2]), kBwdEpiThreads);
     mbar_init(smem_u32(&bars[3]), kBwdEpiThreads);
+    for (int i = 4; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
     mbar_init_fence();
   }
   const WPack wl = wpack_layout(K1);
   copy_to_smem(sW1, wpack, wl.offW3);                         // W1~ | W2~ tiles (fp16, packed once per step)
   copy_to_smem(sW3t, wpack + wl.offW3t, tile_bytes(kHid, 16));
-  for (int cx_i = 0; cx_i < 2; ++cx_i)      // X~ tiles: the padding columns [C + pe_stride, K1) are written once, here
-    for (uint32_t i = tid; i < tile_bytes(kTile, K1) / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(ctx_base + cx_i * ctx_bytes)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < kTile * 16; i += blockDim.x) {
     const int j = i / 16, c = i % 16;
     // columns 128..143 of both H1 tiles: the constant 1 (b2 rides the layer-2 GEMM, db2 the dW2 GEMM), then 0;
@@ -701,115 +522,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     cx[i].tWork = tmem + 128 * i;
     cx[i].bar = MmaCtx{smem_u32(&bars[i]), 0u};
     cx[i].ready = MmaCtx{smem_u32(&bars[2 + i]), 0u};
+    cx[i].xbar = smem_u32(&bars[4 + i]);
+    cx[i].xfree = smem_u32(&bars[6 + i]);
   }
   const float inv_scale = 1.f / grad_scale;
   const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
   float db3[3] = {0.f, 0.f, 0.f};
   bool first = true;
 
-  // ---- per-context stages (all 512 threads unless noted) ----
-  // Staging of a context = global loads (X~ chunks of this thread, and for part 0 the d_rgb / rgb of the row)
-  // then conversion + shared-memory stores.  The loads of BOTH contexts are issued before either is
-  // consumed, and the ray indices (the head of the dependent chain s_ray -> embedding row) are fetched one
-  // pair ahead, so a pair pays one global-memory latency instead of four (tools/mlp_timeline.py).
-  // Vector path (C and pe_stride multiples of 4, pe_stride <= 32): the 128 feature rows of a tile are one contiguous
-  // block, read FLAT (thread t takes float4 t: 4 cache lines per warp load instead of 12 with one row per lane), the
-  // embedding row of a sample by its (row, part) owner (float4 part, part + 4), and dZ3 as ONE float4 per row when the
-  // loss kernel wrote d_rgb * rgb (1 - rgb) (`dz3`; otherwise 6 scalar loads of rgb / d_rgb).  The LSU, not the memory
-  // system, bounds this staging: ~72 -> ~28 line requests per 32 rows.
-  const bool vecx = ((C | pe_stride) & 3) == 0 && C <= 16 && pe_stride <= 32;
-  const StageGeom sg = stage_geom(C, pe_stride);
-  struct Staged { float4 f; float4 p[2]; float o[3], d[3]; };
-  auto ray_of = [&](int64_t s0) -> int {
-    const int64_t sidx = s0 + row;
-    return sidx < count ? __ldg(s_ray + sidx) : 0;
-  };
-  auto stage_load = [&](TileCtx& c, Staged& st, int ray) {
-    const int64_t sidx = c.s0 + row;
-    c.valid = sidx < count;
-    // (1) define every destination, (2) fence, (3) all loads back to back -- see ldg_nc_f4_if
-    st.f = make_float4(0.f, 0.f, 0.f, 0.f);
-    st.p[0] = st.f;
-    st.p[1] = st.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { st.o[k] = 0.f; st.d[k] = 0.f; }
-    float4 pad = st.f;
-    reg_fence(st.f, st.p[0], st.p[1], pad);
-    reg_fence(st.o[0], st.o[1], st.o[2], st.d[0], st.d[1], st.d[2]);
-    if (vecx) {
-      const bool fin = tid < 128 * sg.nf4 && c.s0 + fast_div(tid, sg.inv_f) < count;
-      ldg_nc_f4_if(st.f, reinterpret_cast<const float4*>(feat) + (fin ? c.s0 * sg.nf4 + tid : 0), fin);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int c4 = part + 4 * k;
-        const bool pin = c.valid && c4 < sg.np4;
-        ldg_nc_f4_if(st.p[k], reinterpret_cast<const float4*>(pe) + (pin ? static_cast<int64_t>(ray) * sg.np4 + c4 : 0), pin);
-      }
-    }
-    const bool want = part == 0 && c.valid;
-    if (dz3) {   // d_rgb * rgb * (1 - rgb), written by the loss kernel: one 16-byte load per row
-      float4 z = make_float4(st.d[0], st.d[1], st.d[2], 0.f);
-      ldg_nc_f4_if(z, reinterpret_cast<const float4*>(dz3) + (want ? sidx : 0), want);
-      st.d[0] = z.x; st.d[1] = z.y; st.d[2] = z.z;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        ldg_nc_f32_if(st.o[k], want ? rgb + sidx * 3 + k : rgb, want);
-        ldg_nc_f32_if(st.d[k], want ? d_rgb + sidx * 3 + k : d_rgb, want);
-      }
-    }
-  };
-  auto stage_store = [&](TileCtx& c, const Staged& st, int ray) {
-    if (part == 0) {
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = 0.f;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        v[k] = (dz3 ? st.d[k] : st.d[k] * st.o[k] * (1.f - st.o[k])) * grad_scale;   // dZ3 (scaled)
-        db3[k] += v[k];
-      }
-      *reinterpret_cast<uint4*>(c.sdZ3 + tile_off(row, 0, 16)) = pack8(v);
-      *reinterpret_cast<uint4*>(c.sdZ3 + tile_off(row, 8, 16)) = pack8(v + 8);
-    }
-    if (vecx) {
-      if (tid < 128 * sg.nf4) {
-        const int r = fast_div(tid, sg.inv_f), c4 = tid - r * sg.nf4;
-        *reinterpret_cast<uint2*>(c.sX + tile_off(r, 4 * c4, K1)) = pack4(st.f);
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int c4 = part + 4 * k;
-        if (c4 < sg.np4) *reinterpret_cast<uint2*>(c.sX + tile_off(row, C + 4 * c4, K1)) = pack4(st.p[k]);
-      }
-    } else {  // generic (scalar) path: C or the embedding stride not a multiple of 4
-      const int64_t sidx = c.s0 + row;
-      const float* __restrict__ f = feat + sidx * C;
-      const float* __restrict__ e = pe + static_cast<int64_t>(ray) * pe_stride;
-      for (int ch = part; ch < K1 / 8; ch += 4) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int cc = ch * 8 + j;
-          v[j] = !c.valid ? 0.f : (cc < C ? __ldg(f + cc) : (cc < C + pe_stride ? __ldg(e + (cc - C)) : 0.f));
-        }
-        *reinterpret_cast<uint4*>(c.sX + tile_off(row, ch * 8, K1)) = pack8(v);
-      }
-    }
-  };
-  // TMEM work[row][32*part, +32) -> relu(v + bias) -> fp16 -> smem
-  auto epi_relu = [&](TileCtx& c, const float* sBias, uint8_t* sOut, int out_cols) {
+  // ---- per-context stages (all 512 epilogue threads unless noted) ----
+  // TMEM work[row][32*part, +32) -> relu(v) -> fp16 -> smem
+  auto epi_relu = [&](TileCtx& c, uint8_t* sOut, int out_cols) {
     float v[32];
     tmem_ld16(c.tWork + lane_sel + part * 32, v);
     tmem_ld16(c.tWork + lane_sel + part * 32 + 16, v + 16);
     tmem_ld_wait();
-    if (sBias) {
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 b = *reinterpret_cast<const float4*>(sBias + part * 32 + j4 * 4);
-        v[j4 * 4] += b.x; v[j4 * 4 + 1] += b.y; v[j4 * 4 + 2] += b.z; v[j4 * 4 + 3] += b.w;
-      }
-    }
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc)
       *reinterpret_cast<uint4*>(sOut + tile_off(row, part * 32 + cc * 8, out_cols)) = pack8_relu(v + cc * 8);
@@ -851,7 +578,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
       }
     }
   };
-  // MMA batches (thread 0 only)
+  // db3 += this row's (scaled, fp16) dZ3, read back from the tile the bulk copy delivered (part 0: one row per thread)
+  auto add_db3 = [&](TileCtx& c, uint32_t parity) {
+    if (part == 0) {
+      mbar_wait(c.xbar, parity);
+      const uint2 h = *reinterpret_cast<const uint2*>(c.sdZ3 + tile_off(row, 0, 16));
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+      db3[0] += a.x; db3[1] += a.y; db3[2] += b.x;
+    }
+  };
+  // MMA batches (one elected thread)
   auto issue_l1 = [&](TileCtx& c) {
     gemm_kk(c.tWork, smem_u32(c.sX), K1, smem_u32(sW1), K1, kHid, K1, false);
     mma_commit(c.bar.bar);
@@ -874,6 +611,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
     gemm_mm(tdW1, smem_u32(c.sH1), kHidA, smem_u32(c.sX), K1, K1, kTile, acc);        // dW1~ += dZ1^T X~
     gemm_km(c.tWork, smem_u32(c.sH1), kHidA, smem_u32(sW1), K1, 16, kHid, false);     // dX = dZ1 W1[:, :16]
     mma_commit(c.bar.bar);
+    mma_commit(c.xfree);          // second arrival of the same completion: the issuer's "tiles may be refilled"
+  };
+  // issuer: start the bulk copies of tile `t` (X~ and dZ3) into a context
+  auto load_tiles = [&](TileCtx& c, int64_t t) {
+    mbar_expect_tx(c.xbar, x_bytes + dz_bytes);
+    bulk_g2s(smem_u32(c.sX), xt + t * static_cast<int64_t>(x_bytes), x_bytes, c.xbar);
+    bulk_g2s(smem_u32(c.sdZ3), dzt + t * static_cast<int64_t>(dz_bytes), dz_bytes, c.xbar);
   };
   TileCtx& A = cx[0];
   TileCtx& B = cx[1];
@@ -897,10 +641,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
   };
   if (is_issuer) {
     if (elect_one()) {
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      uint32_t par = 0u;     // parity of this pair's tiles[] / xfree[] phases (one phase of each per pair)
+      load_tiles(A, 2 * static_cast<int64_t>(blockIdx.x));
+      load_tiles(B, 2 * static_cast<int64_t>(blockIdx.x) + 1);   // <= n_tiles: producers zero-fill up to the pair's end
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, par ^= 1u) {
+        const int64_t next = pair + gridDim.x;
+        const bool has_next = next < n_pairs;
+        if (has_next) {      // pull the next pair's tiles (contiguous in global memory) into L2 a whole pair ahead
+          bulk_prefetch_l2(xt + 2 * next * static_cast<int64_t>(x_bytes), 2u * x_bytes);
+          bulk_prefetch_l2(dzt + 2 * next * static_cast<int64_t>(dz_bytes), 2u * dz_bytes);
+        }
         stamp();
-        acquire(A); stamp(); issue_l1(A); stamp();
-        acquire(B); stamp(); issue_l1(B); stamp();
+        acquire(A); mbar_wait(A.xbar, par); stamp(); issue_l1(A); stamp();
+        acquire(B); mbar_wait(B.xbar, par); stamp(); issue_l1(B); stamp();
         acquire(A); stamp(); issue_l2(A); stamp();
         acquire(B); stamp(); issue_l2(B); stamp();
         acquire(A); stamp(); issue_dw3(A, !first); stamp();
@@ -910,61 +663,32 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(
         acquire(A); stamp(); issue_l1b(A, !first); stamp();
         acquire(B); stamp(); issue_l1b(B, true); stamp();
         first = false;
+        if (has_next) {      // the pair's last batch was the only remaining reader of its X~ / dZ3 tiles
+          mbar_wait(A.xfree, par); load_tiles(A, 2 * next);
+          mbar_wait(B.xfree, par); load_tiles(B, 2 * next + 1);
+        }
       }
     }
   } else {
-    // Software pipeline over pairs: the global loads of the NEXT pair are issued before the last two
-    // epilogue phases of the current one, so that at the pair boundary only the conversion + shared-memory
-    // stores remain (the timeline showed the tensor core idle ~7.5k of ~21k cycles per pair there).
-    Staged stA, stB;
-    int rayA = ray_of((2 * static_cast<int64_t>(blockIdx.x)) * kTile);
-    int rayB = ray_of((2 * static_cast<int64_t>(blockIdx.x) + 1) * kTile);
-    A.s0 = (2 * static_cast<int64_t>(blockIdx.x)) * kTile;
-    B.s0 = A.s0 + kTile;                // may lie past the count: then every row is invalid (all-zero tile)
-    stage_load(A, stA, rayA);
-    stage_load(B, stB, rayB);
-    int rA = rayA, rB = rayB;
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    publish(A);   // nothing of the first pair to wait for: the TMEM work columns are free
+    publish(B);
+    uint32_t par = 0u;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, par ^= 1u) {
+      A.s0 = 2 * pair * kTile;
+      B.s0 = A.s0 + kTile;              // may lie past the count: then every row is invalid (an all-zero tile)
+      A.valid = A.s0 + row < count;
+      B.valid = B.s0 + row < count;
       stamp();
-      stage_store(A, stA, rA); publish(A);
-      stage_store(B, stB, rB); publish(B);
-      const bool validA = A.valid, validB = B.valid;
-      const int64_t s0A = A.s0, s0B = B.s0;
-      // ray indices of the NEXT pair, loaded here where no other load of this thread is in flight (the staged values
-      // have just been consumed): issued right after the tile loads further down, the overwrite of these registers
-      // waited for all of them -- the six per-warp scoreboards are shared -- ~4500 cycles per pair in the timeline
-      rayA = ray_of(A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
-      rayB = ray_of(B.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile);
-      {   // next pair -> L2: thread (row, part) touches tile A (part 0,1) or B (part 2,3): features / rgb + d_rgb rows
-        const int64_t s2 = A.s0 + 2 * static_cast<int64_t>(gridDim.x) * kTile + (part >> 1) * kTile + row;
-        if (s2 < count) {
-          if ((part & 1) == 0) prefetch_l2(feat + s2 * C);
-          else if (dz3) prefetch_l2(dz3 + s2 * 4);
-          else { prefetch_l2(rgb + s2 * 3); prefetch_l2(d_rgb + s2 * 3); }
-        }
-      }
-      stamp();
-      mma_wait(A.bar); stamp(); epi_relu(A, nullptr, A.sH1, kHidA); publish(A); stamp();
-      mma_wait(B.bar); stamp(); epi_relu(B, nullptr, B.sH1, kHidA); publish(B); stamp();
-      mma_wait(A.bar); stamp(); epi_relu(A, nullptr, A.sH2, kHid); publish(A); stamp();
-      mma_wait(B.bar); stamp(); epi_relu(B, nullptr, B.sH2, kHid); publish(B); stamp();
+      mma_wait(A.bar); stamp(); epi_relu(A, A.sH1, kHidA); publish(A); add_db3(A, par); stamp();
+      mma_wait(B.bar); stamp(); epi_relu(B, B.sH1, kHidA); publish(B); add_db3(B, par); stamp();
+      mma_wait(A.bar); stamp(); epi_relu(A, A.sH2, kHid); publish(A); stamp();
+      mma_wait(B.bar); stamp(); epi_relu(B, B.sH2, kHid); publish(B); stamp();
       mma_wait(A.bar); stamp(); epi_mask(A, A.sH2, kHid); publish(A); stamp();
       mma_wait(B.bar); stamp(); epi_mask(B, B.sH2, kHid); publish(B); stamp();
       mma_wait(A.bar); stamp(); epi_mask(A, A.sH1, kHidA); publish(A); stamp();
       mma_wait(B.bar); stamp(); epi_mask(B, B.sH1, kHidA); publish(B); stamp();
-      mma_wait(A.bar); stamp(); epi_dx(A);   // the last batch of the pair has completed: tiles may be re-staged
-      mma_wait(B.bar); stamp(); epi_dx(B); stamp();
-      // The next pair's inputs were pulled into L2 at the top of this iteration (prefetch.global.L2: no register, no
-      // scoreboard); load them now, when nothing else of this thread is in flight.  Holding them in registers across
-      // the epilogues instead (round 1) cost ~3000-4000 cycles per pair: a warp has six scoreboards, ptxas shares them
-      // between global loads, tcgen05.ld and ld.shared, and every tcgen05.wait::ld / fence.proxy.async issued while
-      // the prefetch was in flight waited for it (tools/mlp_timeline.py: the stall followed the prefetch wherever it
-      // was moved).
-      A.s0 = (2 * (pair + gridDim.x)) * kTile;
-      B.s0 = A.s0 + kTile;
-      stage_load(A, stA, rayA);
-      stage_load(B, stB, rayB);
-      rA = rayA; rB = rayB;
+      mma_wait(A.bar); stamp(); epi_dx(A); publish(A);   // work columns read: layer 1 of the next pair may overwrite them
+      mma_wait(B.bar); stamp(); epi_dx(B); publish(B); stamp();
     }
   }
   fence_before_sync();
@@ -1024,8 +748,7 @@ static inline size_t mlp_bwd_smem(int K1) {
   auto a1k = [](size_t x) { return (x + 1023) & ~static_cast<size_t>(1023); };
   const size_t ctx = a1k(tile_bytes(kTile, K1)) + a1k(tile_bytes(kTile, kHidA)) + a1k(tile_bytes(kTile, kHid)) +
                      a1k(tile_bytes(kTile, 16));
-  return 1024 + a1k(tile_bytes(kHid, K1)) + a1k(tile_bytes(kHid, kHidA)) + a1k(tile_bytes(kHid, 16)) + 2 * ctx +
-         (3 * kHid + kHid + 4) * sizeof(float) + 64;
+  return 1024 + a1k(tile_bytes(kHid, K1)) + a1k(tile_bytes(kHid, kHidA)) + a1k(tile_bytes(kHid, 16)) + 2 * ctx + 64;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -1491,11 +1214,48 @@ DVGO_API int dvgo_mlp_pack_weights(int C, int P, int pe_stride, const float* W1,
   return launch_status();
 }
 
-DVGO_API int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                                int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb, long long* timeline,
-                                dvgo_stream_t stream) {
-  if (C < 0 || P < 0 || C + P < 1 || C + P > 63 || surv_cap < 0 || pe_stride < P + 1) return DVGO_EINVAL;
-  if (!feat || !s_ray || (P > 0 && !pe) || !counters || !wpack || !rgb) return DVGO_EINVAL;
+static inline bool mlp_shape_ok(int C, int P, int pe_stride) {
+  return C >= 0 && P >= 0 && C + P >= 1 && C + P <= 63 && pe_stride >= P + 1 && C + pe_stride <= 64;
+}
+static inline int pack_grid(int64_t work) {
+  const int64_t want = (work + 255) / 256;
+  return static_cast<int>(want < kNumSMs * 16 ? (want > 0 ? want : 1) : kNumSMs * 16);
+}
+
+DVGO_API int64_t dvgo_mlp_xtile_bytes(int64_t surv_cap, int C, int pe_stride) {
+  if (surv_cap < 0 || C < 0 || pe_stride < 1 || C + pe_stride > 64) return DVGO_EINVAL;
+  return tc::tiles_for(surv_cap) * static_cast<int64_t>(tile_bytes(kTile, mlp_k1(C, pe_stride)));
+}
+DVGO_API int64_t dvgo_mlp_dztile_bytes(int64_t surv_cap) {
+  if (surv_cap < 0) return DVGO_EINVAL;
+  return tc::tiles_for(surv_cap) * static_cast<int64_t>(tile_bytes(kTile, 16));
+}
+
+DVGO_API int dvgo_mlp_pack_x(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
+                             const int32_t* counters, int64_t surv_cap, void* xt, dvgo_stream_t stream) {
+  if (!mlp_shape_ok(C, P, pe_stride) || surv_cap < 0) return DVGO_EINVAL;
+  if (surv_cap == 0) return 0;
+  if ((C > 0 && !feat) || !s_ray || (P > 0 && !pe) || !counters || !xt) return DVGO_EINVAL;
+  const int K1 = mlp_k1(C, pe_stride);
+  mlp_pack_x_kernel<<<pack_grid(surv_cap * (K1 / 4)), 256, 0, as_stream(stream)>>>(
+      feat, C, s_ray, pe, pe_stride, counters, surv_cap, K1, static_cast<uint8_t*>(xt));
+  return launch_status();
+}
+
+DVGO_API int dvgo_mlp_pack_dz(const float* rgb, const float* d_rgb, float grad_scale,
+                              const int32_t* counters, int64_t surv_cap, void* dzt, dvgo_stream_t stream) {
+  if (surv_cap < 0 || !(grad_scale > 0.f)) return DVGO_EINVAL;
+  if (surv_cap == 0) return 0;
+  if (!rgb || !d_rgb || !counters || !dzt) return DVGO_EINVAL;
+  mlp_pack_dz_kernel<<<pack_grid(surv_cap), 256, 0, as_stream(stream)>>>(rgb, d_rgb, grad_scale, counters, surv_cap,
+                                                                        static_cast<uint8_t*>(dzt));
+  return launch_status();
+}
+
+DVGO_API int dvgo_mlp_fwd_timed(const void* xt, int C, int P, int pe_stride, int32_t* counters, int64_t surv_cap,
+                                const void* wpack, float* rgb, long long* timeline, dvgo_stream_t stream) {
+  if (!mlp_shape_ok(C, P, pe_stride) || surv_cap < 0) return DVGO_EINVAL;
+  if (!xt || !counters || !wpack || !rgb) return DVGO_EINVAL;
   if (surv_cap == 0) return 0;
   const int K1 = mlp_k1(C, pe_stride);
   const size_t bytes = mlp_fwd_smem(K1);
@@ -1503,27 +1263,22 @@ DVGO_API int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, 
   if (e != cudaSuccess) return static_cast<int>(e);
   const int64_t tiles = (surv_cap + kTile - 1) / kTile;
   const int grid = static_cast<int>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
-  mlp_fwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap,
-                                                                 static_cast<const uint8_t*>(wpack), K1, pe_stride, rgb,
-                                                                 timeline);
+  mlp_fwd_kernel<<<grid, kMlpThreads, bytes, as_stream(stream)>>>(static_cast<const uint8_t*>(xt), counters, surv_cap,
+                                                                 static_cast<const uint8_t*>(wpack), K1, rgb, timeline);
   return launch_status();
 }
 
-DVGO_API int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                          int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb, dvgo_stream_t stream) {
-  return dvgo_mlp_fwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, wpack, rgb, nullptr, stream);
+DVGO_API int dvgo_mlp_fwd(const void* xt, int C, int P, int pe_stride, int32_t* counters, int64_t surv_cap,
+                          const void* wpack, float* rgb, dvgo_stream_t stream) {
+  return dvgo_mlp_fwd_timed(xt, C, P, pe_stride, counters, surv_cap, wpack, rgb, nullptr, stream);
 }
 
-DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                                int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb,
-                                const float* d_rgb, const float* dz3, float grad_scale, float* d_feat, float* gW1,
+DVGO_API int dvgo_mlp_bwd_timed(const void* xt, const void* dzt, int C, int P, int pe_stride, int32_t* counters,
+                                int64_t surv_cap, const void* wpack, float grad_scale, float* d_feat, float* gW1,
                                 float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, long long* timeline,
                                 dvgo_stream_t stream) {
-  if (C < 1 || C > 16 || P < 0 || C + P > 63 || surv_cap < 0 || !(grad_scale > 0.f) || pe_stride < P + 1)
-    return DVGO_EINVAL;
-  if (!feat || !s_ray || (P > 0 && !pe) || !counters || !wpack || (!dz3 && (!rgb || !d_rgb)) || !d_feat || !gW1 || !gb1 ||
-      !gW2 || !gb2 || !gW3 || !gb3)
-    return DVGO_EINVAL;
+  if (!mlp_shape_ok(C, P, pe_stride) || C < 1 || C > 16 || surv_cap < 0 || !(grad_scale > 0.f)) return DVGO_EINVAL;
+  if (!xt || !dzt || !counters || !wpack || !d_feat || !gW1 || !gb1 || !gW2 || !gb2 || !gW3 || !gb3) return DVGO_EINVAL;
   if (surv_cap == 0) return 0;
   const int K1 = mlp_k1(C, pe_stride);
   const size_t bytes = mlp_bwd_smem(K1);
@@ -1533,18 +1288,17 @@ DVGO_API int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, 
   const int64_t pairs = (tiles + 1) / 2;
   const int grid = static_cast<int>(pairs < kNumSMs ? pairs : kNumSMs);
   MlpG g{gW1, gb1, gW2, gb2, gW3, gb3};
-  mlp_bwd_kernel<<<grid, kBwdThreads, bytes, as_stream(stream)>>>(feat, C, s_ray, pe, P, counters, surv_cap,
-                                                                 static_cast<const uint8_t*>(wpack), K1, pe_stride, rgb,
-                                                                 d_rgb, dz3, grad_scale, d_feat, g, timeline);
+  mlp_bwd_kernel<<<grid, kBwdThreads, bytes, as_stream(stream)>>>(
+      static_cast<const uint8_t*>(xt), static_cast<const uint8_t*>(dzt), C, C + P, counters, surv_cap,
+      static_cast<const uint8_t*>(wpack), K1, grad_scale, d_feat, g, timeline);
   return launch_status();
 }
 
-DVGO_API int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                          int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
-                          const float* dz3, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2,
-                          float* gb2, float* gW3, float* gb3, dvgo_stream_t stream) {
-  return dvgo_mlp_bwd_timed(feat, C, s_ray, pe, P, pe_stride, counters, surv_cap, wpack, rgb, d_rgb, dz3, grad_scale,
-                            d_feat, gW1, gb1, gW2, gb2, gW3, gb3, nullptr, stream);
+DVGO_API int dvgo_mlp_bwd(const void* xt, const void* dzt, int C, int P, int pe_stride, int32_t* counters,
+                          int64_t surv_cap, const void* wpack, float grad_scale, float* d_feat, float* gW1, float* gb1,
+                          float* gW2, float* gb2, float* gW3, float* gb3, dvgo_stream_t stream) {
+  return dvgo_mlp_bwd_timed(xt, dzt, C, P, pe_stride, counters, surv_cap, wpack, grad_scale, d_feat, gW1, gb1, gW2, gb2,
+                            gW3, gb3, nullptr, stream);
 }
 
 DVGO_API int dvgo_tc_rate(int ctas, int N, int ksteps, int reps, int a_mn, int b_mn, int a_lbo, int a_sbo, int a_kstep,

@@ -115,8 +115,11 @@ struct Corner8 {
     return fmul(fmul((k & 1) ? wz1 : wz0, ((k >> 1) & 1) ? wy1 : wy0), (k >> 2) ? wx1 : wx0);
   }
 };
-__device__ __forceinline__ Corner8 corner8(const SceneDev& sc, float px, float py, float pz) {
-  const Tri t = tri_setup(px, py, pz, sc.lo, sc.hi, sc.X, sc.Y, sc.Z);
+// from the continuous voxel coordinates (what tri_setup derives from the point): the per-survivor record march_fwd
+// leaves for the k0 gather / scatter kernels, so that they do not redo the ray geometry (two IEEE divisions, a square
+// root and ~200 more instructions per thread -- the bulk of those kernels' instruction count in round 2's ncu profile)
+__device__ __forceinline__ Corner8 corner8_idx(const SceneDev& sc, float fx, float fy, float fz) {
+  const Tri t = tri_from_index(fx, fy, fz);
   Corner8 c;
   c.sy = sc.Z;
   c.sx = sc.Y * sc.Z;
@@ -131,6 +134,17 @@ __device__ __forceinline__ Corner8 corner8(const SceneDev& sc, float px, float p
     if (((vx >> (k >> 2)) & 1u) & ((vy >> ((k >> 1) & 1)) & 1u) & ((vz >> (k & 1)) & 1u)) v |= 1u << k;
   c.valid = v;
   return c;
+}
+__device__ __forceinline__ void voxel_coords(const SceneDev& sc, float px, float py, float pz, float& fx, float& fy,
+                                             float& fz) {
+  fx = unnorm_coord(px, sc.lo[0], sc.hi[0], sc.X);
+  fy = unnorm_coord(py, sc.lo[1], sc.hi[1], sc.Y);
+  fz = unnorm_coord(pz, sc.lo[2], sc.hi[2], sc.Z);
+}
+__device__ __forceinline__ Corner8 corner8(const SceneDev& sc, float px, float py, float pz) {
+  float fx, fy, fz;
+  voxel_coords(sc, px, py, pz, fx, fy, fz);
+  return corner8_idx(sc, fx, fy, fz);
 }
 
 }  // namespace dvgo

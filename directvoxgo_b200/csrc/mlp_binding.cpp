@@ -72,15 +72,19 @@ Tensor tc_rate(int ctas, int N, int ksteps, int reps, bool a_mn, bool b_mn, int 
   return out;
 }
 
-Tensor view_embedding(Tensor viewdirs, Tensor freq, int stride) {
+// C < 0: the fp32 table only.  C >= 0: also the rays' share of the X~ rows as fp16 ([N][K1] halves, zero elsewhere).
+std::vector<Tensor> view_embedding(Tensor viewdirs, Tensor freq, int stride, int C) {
   chkf(viewdirs, "viewdirs"); chkf(freq, "freq");
   TORCH_CHECK(viewdirs.dim() == 2 && viewdirs.size(1) == 3, "viewdirs must be [N,3]");
   const c10::cuda::CUDAGuard guard(viewdirs.device());
   auto out = torch::empty({viewdirs.size(0), stride}, viewdirs.options());
+  Tensor rows16;
+  if (C >= 0) rows16 = torch::zeros({viewdirs.size(0), ((C + stride + 15) / 16) * 16}, viewdirs.options().dtype(torch::kHalf));
   rc_check(dvgo_view_embedding(viewdirs.data_ptr<float>(), freq.numel() ? freq.data_ptr<float>() : nullptr,
                                static_cast<int>(freq.numel()), viewdirs.size(0), stride, out.data_ptr<float>(),
-                               cur_stream()), "view_embedding");
-  return out;
+                               C >= 0 ? rows16.data_ptr() : nullptr, C >= 0 ? C : 0, cur_stream()), "view_embedding");
+  if (C >= 0) return {out, rows16};
+  return {out};
 }
 
 inline void chki(const Tensor& t, const char* name) {
@@ -120,62 +124,110 @@ Tensor ensure_pack(c10::optional<Tensor> wpack, const Tensor& params, int C, int
   return t;
 }
 
-void mlp_fwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb,
-             c10::optional<Tensor> wpack) {
-  chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
-  chkf(rgb, "rgb");
+inline void chku8(const Tensor& t, int64_t bytes, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == torch::kUInt8 && t.numel() >= bytes &&
+              reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, name, ": 16-byte aligned uint8 CUDA tensor of >= ", bytes, " bytes");
+}
+
+// ---- survivor tiles (the kernels' input format; include/dvgo_b200_fused.h) ----
+int64_t mlp_xtile_bytes(int64_t cap, int C, int pe_stride) { return dvgo_mlp_xtile_bytes(cap, C, pe_stride); }
+int64_t mlp_dztile_bytes(int64_t cap) { return dvgo_mlp_dztile_bytes(cap); }
+
+void mlp_pack_x(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor xt) {
+  chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters");
   const int C = feat.size(1), pe_stride = pe.size(1);
   const int64_t cap = s_ray.numel();
-  TORCH_CHECK(feat.size(0) >= cap && rgb.numel() >= cap * 3, "stream buffers too small");
+  TORCH_CHECK(feat.size(0) >= cap, "feat shorter than the stream capacity");
+  chku8(xt, dvgo_mlp_xtile_bytes(cap, C, pe_stride), "xt");
   const c10::cuda::CUDAGuard guard(feat.device());
+  rc_check(dvgo_mlp_pack_x(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
+                           counters.data_ptr<int32_t>(), cap, xt.data_ptr(), cur_stream()), "mlp_pack_x");
+}
+
+void mlp_pack_dz(Tensor rgb, Tensor d_rgb, double grad_scale, Tensor counters, Tensor dzt) {
+  chkf(rgb, "rgb"); chkf(d_rgb, "d_rgb"); chki(counters, "counters");
+  const int64_t cap = rgb.numel() / 3;
+  TORCH_CHECK(d_rgb.numel() >= cap * 3, "d_rgb shorter than rgb");
+  chku8(dzt, dvgo_mlp_dztile_bytes(cap), "dzt");
+  const c10::cuda::CUDAGuard guard(rgb.device());
+  rc_check(dvgo_mlp_pack_dz(rgb.data_ptr<float>(), d_rgb.data_ptr<float>(), static_cast<float>(grad_scale),
+                            counters.data_ptr<int32_t>(), cap, dzt.data_ptr(), cur_stream()), "mlp_pack_dz");
+}
+
+void mlp_fwd_tiles(Tensor xt, int C, int P, int pe_stride, Tensor counters, int64_t cap, Tensor wpack, Tensor rgb,
+                   c10::optional<Tensor> timeline) {
+  chki(counters, "counters"); chkf(rgb, "rgb");
+  chku8(xt, dvgo_mlp_xtile_bytes(cap, C, pe_stride), "xt");
+  chku8(wpack, dvgo_mlp_wpack_bytes(C, pe_stride), "wpack");
+  TORCH_CHECK(rgb.numel() >= cap * 3, "rgb too small");
+  const c10::cuda::CUDAGuard guard(xt.device());
+  rc_check(dvgo_mlp_fwd_timed(xt.data_ptr(), C, P, pe_stride, counters.data_ptr<int32_t>(), cap, wpack.data_ptr(),
+                              rgb.data_ptr<float>(),
+                              timeline.has_value() ? reinterpret_cast<long long*>(timeline->data_ptr<int64_t>()) : nullptr,
+                              cur_stream()), "mlp_fwd");
+}
+
+void mlp_bwd_tiles(Tensor xt, Tensor dzt, int C, int P, int pe_stride, Tensor counters, int64_t cap, Tensor wpack,
+                   double grad_scale, Tensor d_feat, Tensor grads, c10::optional<Tensor> timeline) {
+  chki(counters, "counters"); chkf(d_feat, "d_feat"); chkf(grads, "grads");
+  chku8(xt, dvgo_mlp_xtile_bytes(cap, C, pe_stride), "xt");
+  chku8(dzt, dvgo_mlp_dztile_bytes(cap), "dzt");
+  chku8(wpack, dvgo_mlp_wpack_bytes(C, pe_stride), "wpack");
+  const Offsets o = offsets(C + P, 128);
+  TORCH_CHECK(grads.numel() == o.total, "grads has the wrong size");
+  TORCH_CHECK(d_feat.numel() >= cap * C, "d_feat too small");
+  const c10::cuda::CUDAGuard guard(xt.device());
+  float* g = grads.data_ptr<float>();
+  rc_check(dvgo_mlp_bwd_timed(xt.data_ptr(), dzt.data_ptr(), C, P, pe_stride, counters.data_ptr<int32_t>(), cap,
+                              wpack.data_ptr(), static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1,
+                              g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3,
+                              timeline.has_value() ? reinterpret_cast<long long*>(timeline->data_ptr<int64_t>()) : nullptr,
+                              cur_stream()), "mlp_bwd");
+}
+
+// ---- the same on fp32 streams: tiles built into temporaries first (tests, tools, one-off calls) ----
+Tensor tiles_from_streams(const Tensor& feat, const Tensor& s_ray, const Tensor& pe, int P, const Tensor& counters) {
+  auto xt = torch::zeros({dvgo_mlp_xtile_bytes(s_ray.numel(), feat.size(1), pe.size(1))},
+                         feat.options().dtype(torch::kUInt8));
+  mlp_pack_x(feat, s_ray, pe, P, counters, xt);
+  return xt;
+}
+
+void mlp_fwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb,
+             c10::optional<Tensor> wpack) {
+  chkf(params, "params");
+  const int C = feat.size(1), pe_stride = pe.size(1);
+  Tensor xt = tiles_from_streams(feat, s_ray, pe, P, counters);
   Tensor wp = ensure_pack(wpack, params, C, P, pe_stride, width);
-  rc_check(dvgo_mlp_fwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
-                        counters.data_ptr<int32_t>(), cap, wp.data_ptr(), rgb.data_ptr<float>(), cur_stream()), "mlp_fwd");
+  mlp_fwd_tiles(xt, C, P, pe_stride, counters, s_ray.numel(), wp, rgb, c10::nullopt);
 }
 
 Tensor mlp_fwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb) {
   const int C = feat.size(1), pe_stride = pe.size(1);
-  const c10::cuda::CUDAGuard guard(feat.device());
   auto tl = torch::zeros({128}, feat.options().dtype(torch::kInt64));
+  Tensor xt = tiles_from_streams(feat, s_ray, pe, P, counters);
   Tensor wp = ensure_pack(c10::nullopt, params, C, P, pe_stride, width);
-  rc_check(dvgo_mlp_fwd_timed(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
-                              counters.data_ptr<int32_t>(), s_ray.numel(), wp.data_ptr(), rgb.data_ptr<float>(),
-                              reinterpret_cast<long long*>(tl.data_ptr<int64_t>()), cur_stream()), "mlp_fwd_timed");
+  mlp_fwd_tiles(xt, C, P, pe_stride, counters, s_ray.numel(), wp, rgb, tl);
   return tl;
 }
 
 void mlp_bwd(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb, Tensor d_rgb,
-             double grad_scale, Tensor d_feat, Tensor grads, c10::optional<Tensor> wpack, c10::optional<Tensor> dz3) {
-  chkf(feat, "feat"); chki(s_ray, "s_ray"); chkf(pe, "pe"); chki(counters, "counters"); chkf(params, "params");
-  chkf(rgb, "rgb"); chkf(d_rgb, "d_rgb"); chkf(d_feat, "d_feat"); chkf(grads, "grads");
+             double grad_scale, Tensor d_feat, Tensor grads, c10::optional<Tensor> wpack, c10::optional<Tensor> timeline) {
+  chkf(params, "params");
   const int C = feat.size(1), pe_stride = pe.size(1);
-  const Offsets o = offsets(C + P, width);
-  TORCH_CHECK(params.numel() == o.total && grads.numel() == o.total, "params/grads have the wrong size");
   const int64_t cap = s_ray.numel();
-  const c10::cuda::CUDAGuard guard(feat.device());
+  TORCH_CHECK(rgb.numel() == cap * 3, "rgb must be [surv_cap,3]");
+  Tensor xt = tiles_from_streams(feat, s_ray, pe, P, counters);
+  auto dzt = torch::zeros({dvgo_mlp_dztile_bytes(cap)}, feat.options().dtype(torch::kUInt8));
+  mlp_pack_dz(rgb, d_rgb, grad_scale, counters, dzt);
   Tensor wp = ensure_pack(wpack, params, C, P, pe_stride, width);
-  float* g = grads.data_ptr<float>();
-  if (dz3.has_value()) { chkf(*dz3, "dz3"); TORCH_CHECK(dz3->numel() >= cap * 4, "dz3 must be [surv_cap,4]"); }
-  rc_check(dvgo_mlp_bwd(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
-                        counters.data_ptr<int32_t>(), cap, wp.data_ptr(), rgb.data_ptr<float>(), d_rgb.data_ptr<float>(),
-                        dz3.has_value() ? dz3->data_ptr<float>() : nullptr, static_cast<float>(grad_scale),
-                        d_feat.data_ptr<float>(), g + o.W1, g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3, cur_stream()),
-           "mlp_bwd");
+  mlp_bwd_tiles(xt, dzt, C, P, pe_stride, counters, cap, wp, grad_scale, d_feat, grads, timeline);
 }
 
 Tensor mlp_bwd_timeline(Tensor feat, Tensor s_ray, Tensor pe, int P, Tensor counters, Tensor params, int width, Tensor rgb,
                         Tensor d_rgb, double grad_scale, Tensor d_feat, Tensor grads) {
-  const int C = feat.size(1), pe_stride = pe.size(1);
-  const Offsets o = offsets(C + P, width);
-  const c10::cuda::CUDAGuard guard(feat.device());
   auto tl = torch::zeros({128}, feat.options().dtype(torch::kInt64));
-  Tensor wp = ensure_pack(c10::nullopt, params, C, P, pe_stride, width);
-  float* g = grads.data_ptr<float>();
-  rc_check(dvgo_mlp_bwd_timed(feat.data_ptr<float>(), C, s_ray.data_ptr<int32_t>(), pe.data_ptr<float>(), P, pe_stride,
-                              counters.data_ptr<int32_t>(), s_ray.numel(), wp.data_ptr(), rgb.data_ptr<float>(),
-                              d_rgb.data_ptr<float>(), nullptr, static_cast<float>(grad_scale), d_feat.data_ptr<float>(), g + o.W1,
-                              g + o.b1, g + o.W2, g + o.b2, g + o.W3, g + o.b3,
-                              reinterpret_cast<long long*>(tl.data_ptr<int64_t>()), cur_stream()), "mlp_bwd_timed");
+  mlp_bwd(feat, s_ray, pe, P, counters, params, width, rgb, d_rgb, grad_scale, d_feat, grads, c10::nullopt, tl);
   return tl;
 }
 }  // namespace
@@ -187,7 +239,8 @@ void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("tc_ts_probe", &tc_ts_probe);
   m.def("tc_ldtm_rate", &tc_ldtm_rate);
   m.def("tc_contention", &tc_contention);
-  m.def("view_embedding", &view_embedding);
+  m.def("view_embedding", &view_embedding, pybind11::arg("viewdirs"), pybind11::arg("freq"), pybind11::arg("stride"),
+        pybind11::arg("C") = -1);
   m.def("mlp_wpack_bytes", &mlp_wpack_bytes);
   m.def("mlp_pack", &mlp_pack);
   m.def("mlp_fwd", &mlp_fwd, pybind11::arg("feat"), pybind11::arg("s_ray"), pybind11::arg("pe"), pybind11::arg("P"),
@@ -197,6 +250,17 @@ void dvgo_bind_mlp(pybind11::module_& m) {
   m.def("mlp_bwd", &mlp_bwd, pybind11::arg("feat"), pybind11::arg("s_ray"), pybind11::arg("pe"), pybind11::arg("P"),
         pybind11::arg("counters"), pybind11::arg("params"), pybind11::arg("width"), pybind11::arg("rgb"),
         pybind11::arg("d_rgb"), pybind11::arg("grad_scale"), pybind11::arg("d_feat"), pybind11::arg("grads"),
-        pybind11::arg("wpack") = pybind11::none(), pybind11::arg("dz3") = pybind11::none());
+        pybind11::arg("wpack") = pybind11::none(), pybind11::arg("timeline") = pybind11::none());
+  m.def("mlp_xtile_bytes", &mlp_xtile_bytes);
+  m.def("mlp_dztile_bytes", &mlp_dztile_bytes);
+  m.def("mlp_pack_x", &mlp_pack_x);
+  m.def("mlp_pack_dz", &mlp_pack_dz);
+  m.def("mlp_fwd_tiles", &mlp_fwd_tiles, pybind11::arg("xt"), pybind11::arg("C"), pybind11::arg("P"),
+        pybind11::arg("pe_stride"), pybind11::arg("counters"), pybind11::arg("cap"), pybind11::arg("wpack"),
+        pybind11::arg("rgb"), pybind11::arg("timeline") = pybind11::none());
+  m.def("mlp_bwd_tiles", &mlp_bwd_tiles, pybind11::arg("xt"), pybind11::arg("dzt"), pybind11::arg("C"), pybind11::arg("P"),
+        pybind11::arg("pe_stride"), pybind11::arg("counters"), pybind11::arg("cap"), pybind11::arg("wpack"),
+        pybind11::arg("grad_scale"), pybind11::arg("d_feat"), pybind11::arg("grads"),
+        pybind11::arg("timeline") = pybind11::none());
   m.def("mlp_bwd_timeline", &mlp_bwd_timeline);
 }

@@ -45,6 +45,26 @@ __host__ __device__ constexpr uint32_t tile_bytes(int rows, int cols) {
 __host__ __device__ constexpr uint32_t group_stride(int cols) { return static_cast<uint32_t>((cols / 8) * 128); }
 constexpr int kMmaK = 16;  // K elements consumed by one kind::f16 tcgen05.mma
 
+// fp32 pair -> packed fp16 pair, round-to-nearest, SATURATING to +-65504 (one F2FP.SATFINITE instruction): a
+// feature / activation / scaled gradient beyond FP16's range clamps instead of becoming inf and poisoning the
+// training state through Adam (the reference's fp32 nn.Linear has no such range limit).  NaN stays NaN and is
+// reported through the status word (counters[1] bit 1).
+__device__ __forceinline__ __half2 pack2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
+__device__ __forceinline__ uint2 pack4(const float4& v) {
+  const __half2 a = pack2_sat(v.x, v.y), b = pack2_sat(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+// Survivor tiles in global memory ("X~ tiles" / "dZ3 tiles"): tile t holds survivors [128 t, 128 t + 128) as one
+// [128 rows][cols] fp16 block in the canonical operand layout above, so a CTA pulls a whole tile with ONE bulk copy
+// and hands it to the tensor core untouched.  Producers cover the rows up to the next multiple of 256 with zeros (the
+// backward kernel works on tile pairs) and the buffers hold one tile more than ceil(capacity / 128).
+__host__ __device__ constexpr int64_t tiles_for(int64_t surv_cap) { return (surv_cap + 127) / 128 + 1; }
+
 // One elected lane of a fully converged warp (elect.sync).  MMA issue MUST sit under this predicate inside a
 // warp-uniform branch: under a plain `if (threadIdx.x == 0)` nvcc cannot prove a single active thread and wraps EVERY
 // tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop (measured round 1 as "no MMA issues faster than 49-72 cycles");
@@ -169,6 +189,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar_saddr, uint32_t parity) {
         : "memory");
     if (spin > (1u << 22)) __trap();
   }
+}
+
+// ---- bulk asynchronous copy global -> shared (the TMA engine's 1-D form; SASS UBLKCP) ----
+// One thread arms the mbarrier with the byte count, then issues the copy; the barrier's phase completes when the
+// bytes have landed (complete_tx).  dst / src 16-byte aligned, bytes a multiple of 16.  No registers, no scoreboard:
+// the survivor tiles of the rgbnet kernels arrive this way (their producers write them in the operand layout).
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_saddr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint32_t bar_saddr) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(dst_saddr), "l"(src), "r"(bytes), "r"(bar_saddr)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // Non-blocking test of an mbarrier phase (the polling MMA issuer serves whichever tile context is ready first).

@@ -58,6 +58,7 @@ class _Workspace:
         self.s_ray = torch.empty(cap, **i32)
         self.s_slot = torch.empty(cap, **i32)
         self.s_weight = torch.empty(cap, **f32)
+        self.s_pos = torch.empty(cap, 4, **f32)   # per survivor: continuous voxel coordinates + ray index (int bits)
         self.rgb = torch.empty(cap, 3, **f32)
         self.alphainv_last = torch.empty(n_rays, **f32)
         # one zero-able block: counters(2) | loss(2) | rgb_acc(3N) | depth_acc(N)
@@ -72,7 +73,16 @@ class _Workspace:
             self.d_rgb = torch.empty(cap, 3, **f32)
             self.d_w = torch.empty(cap, **f32)
             self.d_feat = torch.empty(cap, C, **f32)
-            self.dz3 = torch.empty(cap, 4, **f32)     # d_rgb * rgb (1 - rgb): loss kernel -> rgbnet backward
+
+    def tiles(self, C, pe_stride, train):
+        """Survivor tiles of the tensor-core rgbnet (fp16, operand layout): X~ written by k0_gather_tiles, dZ3 by
+        sample_grad; zero-initialised once (rows past the count are only ever rewritten with zeros)."""
+        if getattr(self, "_xt_key", None) != (C, pe_stride):
+            self.xt = torch.zeros(ext.mlp_xtile_bytes(self.cap, C, pe_stride), dtype=torch.uint8, device=self.rgb.device)
+            self._xt_key = (C, pe_stride)
+        if train and getattr(self, "dzt", None) is None:
+            self.dzt = torch.zeros(ext.mlp_dztile_bytes(self.cap), dtype=torch.uint8, device=self.rgb.device)
+        return self.xt
 
 
 def view_embedding(viewdirs, viewfreq):
@@ -159,7 +169,9 @@ class _FusedBase:
         """Host check of the device status bits; call where the host synchronises anyway."""
         self.stats_snapshot()
 
-    def _march(self, ws, rays_o, rays_d):
+    def _march(self, ws, rays_o, rays_d, pe=None):
+        """pe (tensor-core rgbnet): (padded view-embedding table, its fp16 row form) as TensorCoreMLP.embed(.., C) returns
+        them; the k0 gather then writes the rgbnet's X~ tiles (ws.xt) instead of the fp32 feature stream ws.feat."""
         ext.step_begin(ws.zblock, self.stats if self._last_ws is ws else None)
         if self._last_ws is not None and self._last_ws is not ws:   # switching workspaces: fold the other one in now
             c = self._last_ws.counters
@@ -169,10 +181,14 @@ class _FusedBase:
         self._last_ws = ws
         ext.ray_setup(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off)
         # density march (scan-bound, per ray) then the k0 gather over the compacted stream (fully parallel)
-        ext.march_fwd(self.scene, rays_o, rays_d, self.density, None if self.split_k0 else self.k0, ws.t_min,
+        ext.march_fwd(self.scene, rays_o, rays_d, self.density, None if (self.split_k0 or pe is not None) else self.k0, ws.t_min,
                       ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T, ws.slot_expd, ws.slot_code, ws.feat, ws.s_ray,
-                      ws.s_slot, ws.s_weight, ws.alphainv_last, ws.counters)
-        if self.split_k0:
+                      ws.s_slot, ws.s_weight, ws.alphainv_last, ws.counters, ws.s_pos)
+        if pe is not None:
+            ext.k0_gather_tiles(self.scene, rays_o, rays_d, self.k0, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot,
+                                ws.counters, ws.s_pos, pe[1], pe[0].shape[1],
+                                ws.tiles(self.C, pe[0].shape[1], hasattr(ws, "d_feat")))
+        elif self.split_k0:
             ext.k0_gather(self.scene, rays_o, rays_d, self.k0, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot,
                           ws.counters, ws.feat)
 
@@ -227,11 +243,13 @@ class FusedRenderer(_FusedBase):
     def render(self, rays_o, rays_d, viewdirs, render_depth=True):
         n = rays_o.shape[0]
         ws = self._workspace(n, False)
-        self._march(ws, rays_o.contiguous(), rays_d.contiguous())
+        tc = self.model.rgbnet is not None and self.mlp_mode == "tc"
+        pe = self._tc_embed(viewdirs) if tc else None
+        self._march(ws, rays_o.contiguous(), rays_d.contiguous(), pe)
         if self.model.rgbnet is None:
             ext.rgb_direct(ws.feat, ws.counters, ws.rgb)
-        elif self.mlp_mode == "tc":
-            self._tc_forward(ws, viewdirs)
+        elif tc:
+            self._tc.forward_tiles(ws.xt, self.C, pe[0].shape[1], ws.counters, ws.cap, ws.rgb)
         else:
             m4 = int(ws.counters[0].item())
             if m4:
@@ -276,12 +294,11 @@ class FusedRenderer(_FusedBase):
             res["depth"] = depth.reshape(H, W)
         return res
 
-    def _tc_forward(self, ws, viewdirs):
+    def _tc_embed(self, viewdirs):
         from .fused_mlp import TensorCoreMLP
         if not hasattr(self, "_tc"):
             self._tc = TensorCoreMLP(self.model.rgbnet, self.device)
-        pe = self._tc.embed(viewdirs, self._viewfreq())
-        self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
+        return self._tc.embed(viewdirs, self._viewfreq(), self.C)
 
 
 class FusedTrainer(_FusedBase):
@@ -467,8 +484,11 @@ class FusedTrainer(_FusedBase):
         self.global_step += 1
         ws = self._workspace(n, True)
         rays_o, rays_d, target = rays_o.contiguous(), rays_d.contiguous(), target.contiguous()
+        tc = model.rgbnet is not None and self.mlp_mode == "tc"
         self._mark("start")
-        self._march(ws, rays_o, rays_d)
+        pe = self._tc.embed(viewdirs, self._viewfreq(), self.C) if tc else None
+        self._mark("embed")
+        self._march(ws, rays_o, rays_d, pe)
         self._mark("march_fwd")
 
         dens_async = False
@@ -477,7 +497,6 @@ class FusedTrainer(_FusedBase):
         w_per = float(cfg.get("weight_rgbper", 0.0))
         bg = float(self.rk["bg"])
 
-        use_dz3 = model.rgbnet is not None and self.mlp_mode == "tc"
 
         def density_backward_async():
             """alpha2weight / raw2alpha backward + density scatter (march_bwd) depend on d_w from the loss kernels only,
@@ -505,21 +524,19 @@ class FusedTrainer(_FusedBase):
             ext.ray_finish(ws.rgb_acc, ws.alphainv_last, target, bg, n, n_global, w_main, w_ent, ws.G, ws.g_last,
                            ws.loss_acc)
             ext.sample_grad(ws.rgb, ws.s_weight, ws.s_ray, ws.G, target, ws.counters, n_global, w_per, ws.d_rgb,
-                            ws.d_w, ws.loss_acc, ws.dz3 if use_dz3 else None)
+                            ws.d_w, ws.loss_acc, ws.dzt if tc else None, self._tc.grad_scale(n_global) if tc else 1.0)
 
         if model.rgbnet is None:
             ext.rgb_direct(ws.feat, ws.counters, ws.rgb)
             after_rgb()
             ext.rgb_direct_bwd(ws.rgb, ws.d_rgb, ws.counters, ws.d_feat)
-        elif self.mlp_mode == "tc":
-            pe = self._tc.embed(viewdirs, self._viewfreq())
-            self._mark("embed")
-            self._tc.forward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb)
+        elif tc:
+            self._tc.forward_tiles(ws.xt, self.C, pe[0].shape[1], ws.counters, ws.cap, ws.rgb)
             self._mark("mlp_fwd")
             after_rgb()
             self._mark("loss")
             dens_async = density_backward_async()
-            self._tc.backward(ws.feat, ws.s_ray, pe, ws.counters, ws.rgb, ws.d_rgb, ws.d_feat, n_global, ws.dz3)
+            self._tc.backward_tiles(ws.xt, ws.dzt, self.C, pe[0].shape[1], ws.counters, ws.cap, ws.d_feat, n_global)
         else:
             m4 = int(ws.counters[0].item())  # parity mode: one host read of the survivor count
             for p in model.rgbnet.parameters():
@@ -540,7 +557,7 @@ class FusedTrainer(_FusedBase):
                           None if self.split_k0 else self.g_k0)
         if self.split_k0:
             ext.k0_scatter(self.scene, rays_o, rays_d, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot, ws.counters,
-                           ws.d_feat, self.g_k0)
+                           ws.d_feat, self.g_k0, ws.s_pos)
         if dens_async:
             torch.cuda.current_stream().wait_event(self._dens_done)
         self._mark("march_bwd")

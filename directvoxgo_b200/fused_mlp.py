@@ -58,11 +58,13 @@ class TensorCoreMLP:
         self._P = P
         return out
 
-    def embed(self, viewdirs, viewfreq):
-        """The padded view-embedding table of `pad_embedding(view_embedding(...))` in one kernel."""
+    def embed(self, viewdirs, viewfreq, C=None):
+        """The padded view-embedding table of `pad_embedding(view_embedding(...))` in one kernel.  With C (the k0
+        channel count) also the rays' share of the X~ rows as fp16 ([N, K1]; what k0_gather_tiles copies): (pe, rows16)."""
         P = 3 + 6 * int(viewfreq.numel())
         self._P = P
-        return ext.view_embedding(viewdirs.contiguous(), viewfreq, (P + 1 + 3) // 4 * 4)
+        out = ext.view_embedding(viewdirs.contiguous(), viewfreq, (P + 1 + 3) // 4 * 4, -1 if C is None else C)
+        return out[0] if C is None else (out[0], out[1])
 
     def pack(self, C, pe_stride):
         """fp32 master weights -> the fp16 operand tiles the kernels bulk-copy (one tiny kernel; called by forward(),
@@ -74,20 +76,34 @@ class TensorCoreMLP:
         ext.mlp_pack(self.params, C, self.d_in - C, pe_stride, self.WIDTH, self._wpack)
         return self._wpack
 
+    def grad_scale(self, n_global):
+        """Power of two applied to the backward's fp16 operands: d_rgb <= ~2/(3 n_global), so 256 n_global brings the
+        largest of them to O(100); removed exactly in the fp32 epilogues."""
+        return 2.0 ** math.floor(math.log2(256.0 * n_global))
+
     def forward(self, feat, s_ray, pe_pad, counters, rgb):
+        """From fp32 streams (the tiles are built into a temporary first)."""
         wp = self.pack(feat.shape[1], pe_pad.shape[1])
         ext.mlp_fwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb, wp)
 
-    def backward(self, feat, s_ray, pe_pad, counters, rgb, d_rgb, d_feat, n_global, dz3=None):
-        """Accumulates weight gradients into self.grad_flat (zeroed here) and writes d_feat.  dz3: the [cap,4] buffer
-        ext.sample_grad filled with d_rgb * rgb * (1 - rgb) (optional; computed in the kernel otherwise)."""
+    def backward(self, feat, s_ray, pe_pad, counters, rgb, d_rgb, d_feat, n_global):
+        """From fp32 streams.  Accumulates weight gradients into self.grad_flat (zeroed here) and writes d_feat."""
         ext.zero_(self.grad_flat)
-        # d_rgb <= ~2/(3 n_global): scale so that the largest FP16 backward operand is O(100)
-        scale = 2.0 ** math.floor(math.log2(256.0 * n_global))
         wp = self._wpack if getattr(self, "_wpack_key", None) == (feat.shape[1], pe_pad.shape[1]) else \
             self.pack(feat.shape[1], pe_pad.shape[1])
         ext.mlp_bwd(feat, s_ray, pe_pad, self.d_in - feat.shape[1], counters, self.params, self.WIDTH, rgb, d_rgb,
-                    scale, d_feat, self.grad_flat, wp, dz3)
+                    self.grad_scale(n_global), d_feat, self.grad_flat, wp)
+
+    # the fused step's calls: survivor tiles written by their producers (k0_gather_tiles / sample_grad)
+    def forward_tiles(self, xt, C, pe_stride, counters, cap, rgb):
+        wp = self.pack(C, pe_stride)
+        ext.mlp_fwd_tiles(xt, C, self.d_in - C, pe_stride, counters, cap, wp, rgb)
+
+    def backward_tiles(self, xt, dzt, C, pe_stride, counters, cap, d_feat, n_global):
+        ext.zero_(self.grad_flat)
+        wp = self._wpack if getattr(self, "_wpack_key", None) == (C, pe_stride) else self.pack(C, pe_stride)
+        ext.mlp_bwd_tiles(xt, dzt, C, self.d_in - C, pe_stride, counters, cap, wp, self.grad_scale(n_global), d_feat,
+                          self.grad_flat)
 
     def adam_step(self, step, beta1, beta2, lr, eps):
         adam_upd_cuda.adam_upd(self.params, self.grad_flat, self.exp_avg, self.exp_avg_sq, step, beta1, beta2, lr, eps)

@@ -87,7 +87,7 @@ int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, const dvgo_sc
                          int64_t surv_cap, float* slot_alpha, float* slot_T, float* slot_expd,
                          int32_t* slot_code, float* feat, int32_t* s_ray, int32_t* s_slot,
                          float* s_weight, float* alphainv_last, int32_t* counters,
-                         dvgo_stream_t stream);
+                         float* s_pos, dvgo_stream_t stream);
 
 /* k0 gather / scatter over the survivor stream (one thread per survivor and 16-byte channel group).
  * march_fwd with k0_cl == NULL followed by k0_gather is equivalent to march_fwd with k0_cl; likewise
@@ -97,10 +97,24 @@ int dvgo_fused_k0_gather(const float* rays_o, const float* rays_d, const dvgo_sc
                          const float* k0_cl, const float* t_min, const int32_t* ray_off,
                          const int32_t* s_ray, const int32_t* s_slot, const int32_t* counters,
                          int64_t surv_cap, float* feat, dvgo_stream_t stream);
+/* k0_gather whose output is the rgbnet's X~ tiles (fp16, operand layout; see dvgo_mlp_fwd below) instead of the
+ * fp32 feature stream: features, the embedding share of the survivor's ray (pe_rows16 [n_rays][K1] halves as
+ * dvgo_view_embedding writes them; pe_stride = the fp32 table's row length) and the zero padding, rows up to the next
+ * multiple of 256 zeroed.  Same bytes as dvgo_fused_k0_gather followed by dvgo_mlp_pack_x, without the
+ * 2 x M4 x C x 4 bytes of feature traffic in between. */
+int dvgo_fused_k0_gather_tiles(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
+                               const float* k0_cl, const float* t_min, const int32_t* ray_off,
+                               const int32_t* s_ray, const int32_t* s_slot, const int32_t* counters,
+                               int64_t surv_cap, const float* s_pos, const void* pe_rows16, int pe_stride,
+                               void* xt, dvgo_stream_t stream);
+/* s_pos (optional in gather_tiles / scatter, [surv_cap,4] floats, 16-byte aligned): the per-survivor record
+ * dvgo_fused_march_fwd writes when given the buffer -- the sample's continuous voxel coordinates (what ATen's
+ * grid_sampler derives from the point, lib/dvgo.py:316-321) and the ray index as int bits.  With it the k0 kernels
+ * skip the per-thread ray geometry (same floats, so the results are bit-identical); NULL recomputes it. */
 int dvgo_fused_k0_scatter(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
                           const float* t_min, const int32_t* ray_off, const int32_t* s_ray,
                           const int32_t* s_slot, const int32_t* counters, int64_t surv_cap,
-                          const float* d_feat, float* grad_k0_cl, dvgo_stream_t stream);
+                          const float* s_pos, const float* d_feat, float* grad_k0_cl, dvgo_stream_t stream);
 
 /* rgb = sigmoid(feat) for models without rgbnet (lib/dvgo.py:512-514); rgb [M4,3], C must be 3. */
 int dvgo_fused_rgb_direct(const float* feat, const int32_t* counters, int64_t surv_cap, float* rgb,
@@ -129,12 +143,13 @@ int dvgo_fused_ray_finish(float* rgb_acc, const float* alphainv_last, const floa
  *   d_rgb[i] = w_i*G[r] + weight_rgbper * 2 w_i (rgb_i - target[r]) / n_global
  *   d_w[i]   = sum_c G[r,c]*rgb_i,c                       (weights are detached in the rgbper term)
  *   loss_acc[0] += weight_rgbper * w_i * |rgb_i - target[r]|^2 / n_global
- * dz3 (optional, [surv_cap,4], 16-byte aligned): d_rgb[i] * rgb_i * (1 - rgb_i) (the gradient through the sigmoid of
- * lib/dvgo.py:539) and a zero, one float4 per survivor -- the input of dvgo_mlp_bwd. */
+ * dzt (optional, dvgo_mlp_dztile_bytes(surv_cap) bytes): the rgbnet backward's dZ3 tiles, grad_scale * d_rgb[i] *
+ * rgb_i * (1 - rgb_i) (the gradient through the sigmoid of lib/dvgo.py:539) as saturated fp16 in the operand layout,
+ * rows up to the next multiple of 256 zeroed -- the input of dvgo_mlp_bwd. */
 int dvgo_fused_sample_grad(const float* rgb, const float* s_weight, const int32_t* s_ray,
                            const float* G, const float* target, const int32_t* counters,
                            int64_t surv_cap, int n_global, float weight_rgbper, float* d_rgb,
-                           float* d_w, float* loss_acc, float* dz3, dvgo_stream_t stream);
+                           float* d_w, float* loss_acc, void* dzt, float grad_scale, dvgo_stream_t stream);
 
 /* march_bwd: accumulates into grad_density [X,Y,Z] and grad_k0_cl [X,Y,Z,C] (fp32 atomics).
  * d_feat [M4,C] = dL/d(k0 features), d_w [M4] = dL/d(weights), g_last [N] = dL/d(alphainv_last). */
@@ -183,42 +198,56 @@ int dvgo_grid_cl_to_ncdhw(const float* src, float* dst, int C, int64_t G, dvgo_s
 /* rgbnet on the tensor cores (fused_mlp.cu): x = [feat (C) | pe[s_ray] (P)] -> Linear(C+P, 128) -> ReLU
  * -> Linear(128,128) -> ReLU -> Linear(128,3) -> sigmoid   (lib/dvgo.py:123-131, :524-539 with
  * rgbnet_direct=True, rgbnet_depth=3, rgbnet_width=128 -- the configs' default).
- * feat [surv_cap,C], s_ray [surv_cap] int32, counters[0] = M4, counters[1] |= 2 on a non-finite value.
- * pe [n_rays, pe_stride] is the per-ray view embedding table padded so that column P holds the constant 1 (it
- * carries b1 through the first GEMM) and the remaining columns are 0; pe_stride >= P+1, a multiple of 4 (with C a
- * multiple of 4) enables the coalesced staging path.
+ * counters[0] = M4 (survivors), counters[1] |= 2 on a non-finite value.
+ *
+ * Per-survivor inputs are fp16 TILES in the tensor core's canonical shared-memory operand layout, so that a CTA
+ * fetches a tile with one bulk copy (cp.async.bulk) and hands it to the MMA untouched:
+ *   X~ tiles  (xt):  tile t = survivors [128 t, 128 t + 128) as [128][K1] halves, K1 = round_up(C + pe_stride, 16):
+ *                    columns [0,C) k0 features, [C, C+pe_stride) the survivor's ray's row of the padded view-embedding
+ *                    table pe [n_rays, pe_stride] (P embedding values, then the constant 1 that carries b1, then 0), rest 0.
+ *   dZ3 tiles (dzt): [128][16] halves, columns 0..2 = grad_scale * d_rgb * rgb * (1 - rgb) (the gradient at the output
+ *                    layer's pre-activation; lib/dvgo.py:539), rest 0.
+ * byte offset of (row r, column c) in a tile of `cols` columns: (r/8)*(cols/8)*128 + (c/8)*128 + (r%8)*16 + (c%8)*2.
+ * Rows past M4 up to the next multiple of 256 must be ZERO (the backward kernel works on tile pairs); buffers hold
+ * dvgo_mlp_xtile_bytes / dvgo_mlp_dztile_bytes bytes (one tile more than ceil(surv_cap / 128)), 16-byte aligned, and
+ * must be ZERO-INITIALISED by the caller once: the producers never write a 16-byte chunk that holds padding columns
+ * only (X~ columns >= round_up(C + pe_stride, 8), dZ3 columns 8..15).
+ * Producers: dvgo_fused_k0_gather_tiles and dvgo_fused_sample_grad write them in the fused step; dvgo_mlp_pack_x /
+ * dvgo_mlp_pack_dz build them from fp32 streams (feat [surv_cap,C], s_ray [surv_cap]; rgb / d_rgb [surv_cap,3]).
+ * Conversion to fp16 saturates (cvt.rn.satfinite).
+ *
  * Weights: fp32 masters in torch nn.Linear layout ([out][in]) are converted ONCE per step by dvgo_mlp_pack_weights
- * into `wpack` (dvgo_mlp_wpack_bytes bytes of device memory: the fp16 operand tiles in the tensor core's canonical
- * shared-memory layout, saturating conversion), which every CTA of the forward / backward kernels bulk-copies.
- * GEMM operands are FP16, accumulation is fp32.  rgb [surv_cap,3].  width must be 128. */
+ * into `wpack` (dvgo_mlp_wpack_bytes bytes of device memory: fp16 operand tiles, saturating conversion), which every
+ * CTA of the forward / backward kernels copies.  GEMM operands are FP16, accumulation is fp32.  rgb [surv_cap,3].
+ * width must be 128. */
 int64_t dvgo_mlp_wpack_bytes(int C, int pe_stride);
 int dvgo_mlp_pack_weights(int C, int P, int pe_stride, const float* W1, const float* b1, const float* W2,
                           const float* b2, const float* W3, const float* b3, int width, void* wpack,
                           dvgo_stream_t stream);
-int dvgo_mlp_fwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                 int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb, dvgo_stream_t stream);
+int64_t dvgo_mlp_xtile_bytes(int64_t surv_cap, int C, int pe_stride);
+int64_t dvgo_mlp_dztile_bytes(int64_t surv_cap);
+int dvgo_mlp_pack_x(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
+                    const int32_t* counters, int64_t surv_cap, void* xt, dvgo_stream_t stream);
+int dvgo_mlp_pack_dz(const float* rgb, const float* d_rgb, float grad_scale,
+                     const int32_t* counters, int64_t surv_cap, void* dzt, dvgo_stream_t stream);
+int dvgo_mlp_fwd(const void* xt, int C, int P, int pe_stride, int32_t* counters, int64_t surv_cap, const void* wpack,
+                 float* rgb, dvgo_stream_t stream);
 /* Same as dvgo_mlp_fwd; if `timeline` is non-NULL, CTA 0 records clock64() at every phase boundary of its
  * first tiles into timeline[0..63] (thread 0) and timeline[64..127] (thread 255) -- kernel-author tooling. */
-int dvgo_mlp_fwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                       int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb, long long* timeline,
-                       dvgo_stream_t stream);
+int dvgo_mlp_fwd_timed(const void* xt, int C, int P, int pe_stride, int32_t* counters, int64_t surv_cap,
+                       const void* wpack, float* rgb, long long* timeline, dvgo_stream_t stream);
 /* Backward with forward recompute: d_feat [surv_cap,C] = dL/dfeat, and gW*, gb* += weight gradients
- * (accumulated in TMEM per CTA, flushed with atomics; the caller zeroes them).  d_rgb = dL/d(rgb) (after
- * the sigmoid).  grad_scale: power of two applied to the FP16 backward operands and removed exactly in
- * the fp32 epilogues.  `wpack` must hold the same weights the forward used.  `dz3` (optional, [surv_cap,4]): the
- * pre-activation gradient d_rgb * rgb * (1 - rgb) as dvgo_fused_sample_grad writes it (one 16-byte load per sample
- * instead of six scalar ones); when NULL it is computed from rgb and d_rgb. */
-int dvgo_mlp_bwd(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                 int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
-                 const float* dz3, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2,
+ * (accumulated in TMEM per CTA, flushed with atomics; the caller zeroes them).  grad_scale: the power of two the dZ3
+ * tiles were scaled by (keeps the FP16 backward operands in normal range); removed exactly in the fp32 epilogues.
+ * `wpack` and `xt` must be the ones the forward used. */
+int dvgo_mlp_bwd(const void* xt, const void* dzt, int C, int P, int pe_stride, int32_t* counters, int64_t surv_cap,
+                 const void* wpack, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2,
                  float* gW3, float* gb3, dvgo_stream_t stream);
-
-/* dvgo_mlp_bwd with an optional in-kernel timeline (CTA 0: context-0 thread 0 -> timeline[0..63], issuer ->
+/* dvgo_mlp_bwd with an optional in-kernel timeline (CTA 0: epilogue thread 0 -> timeline[0..63], issuer ->
  * timeline[64..127], clock64 at every phase boundary of the first tiles) -- kernel-author tooling. */
-int dvgo_mlp_bwd_timed(const float* feat, int C, const int32_t* s_ray, const float* pe, int P, int pe_stride,
-                       int32_t* counters, int64_t surv_cap, const void* wpack, const float* rgb, const float* d_rgb,
-                       const float* dz3, float grad_scale, float* d_feat, float* gW1, float* gb1, float* gW2, float* gb2,
-                       float* gW3, float* gb3, long long* timeline, dvgo_stream_t stream);
+int dvgo_mlp_bwd_timed(const void* xt, const void* dzt, int C, int P, int pe_stride, int32_t* counters,
+                       int64_t surv_cap, const void* wpack, float grad_scale, float* d_feat, float* gW1, float* gb1,
+                       float* gW2, float* gb2, float* gW3, float* gb3, long long* timeline, dvgo_stream_t stream);
 
 /* Cross-GPU barrier on the stream without a collective library: flags_peers_host[r] = rank r's array of n_peers int32
  * flags (symmetric memory, zero-initialised, peer-mapped); the kernel stores `epoch` into slot self_rank of every rank's
@@ -241,9 +270,12 @@ int dvgo_tc_selftest(const float* A, const float* B, float* D, int N, int K, int
 /* Descriptor probe (debug aid for the kernel author): A [128][K] K-major, the B operand region is
  * filled verbatim from Braw [nwords] and described with the given LBO/SBO/k-step (bytes). */
 /* View-direction encoding of lib/dvgo.py:524-525 written into the padded table the rgbnet kernels read:
- * out [n_rays, stride] = [viewdirs | sin(v*f) | cos(v*f) | 1 | 0...], stride >= 3 + 6*n_freq + 1. */
+ * out [n_rays, stride] = [viewdirs | sin(v*f) | cos(v*f) | 1 | 0...], stride >= 3 + 6*n_freq + 1.
+ * rows16 (optional, [n_rays][K1] halves, K1 = round_up(C + stride, 16), ZERO-initialised by the caller): the same
+ * values as saturated fp16 in columns [C, C + stride) -- the ray's share of an X~ row, which
+ * dvgo_fused_k0_gather_tiles copies 16 bytes at a time instead of converting it again for every survivor. */
 int dvgo_view_embedding(const float* viewdirs, const float* freq, int n_freq, int64_t n_rays, int stride,
-                        float* out, dvgo_stream_t stream);
+                        float* out, void* rows16, int C, dvgo_stream_t stream);
 
 /* Tensor-core issue-rate probe (tools/mma_rate.py): `reps` x `ksteps` M=128 MMAs of width N issued by one thread per
  * CTA from zero-filled shared memory with the given descriptor fields; out[cta] = cycles. */

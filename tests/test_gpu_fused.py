@@ -343,3 +343,86 @@ def test_sphere_scene_trainer_rgb_matches_module_path():
         assert torch.allclose(out["rgb_marched"], want["rgb_marched"], atol=2e-5), \
             float((out["rgb_marched"] - want["rgb_marched"]).abs().max())
         assert torch.allclose(out["depth"], want["depth"], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("rgbnet_dim,n_rays", [(12, 1500), (9, 700), (4, 333), (16, 1000)])
+def test_survivor_tile_producers_match_pack_kernels(rgbnet_dim, n_rays):
+    """The X~ tiles written by k0_gather_tiles are byte-identical to k0_gather -> mlp_pack_x, the dZ3 tiles written by
+    sample_grad to mlp_pack_dz of its fp32 outputs, and both are zero from the survivor count to the end of the pair."""
+    from directvoxgo_b200 import ext, synthetic as syn
+    from directvoxgo_b200.dvgo import DirectVoxGO
+    from directvoxgo_b200.fused import FusedRenderer
+    lo, hi = syn.fine_bbox()
+    kw = dict(syn.FINE_MODEL, num_voxels=36 ** 3, num_voxels_base=36 ** 3, rgbnet_dim=rgbnet_dim)
+    torch.manual_seed(0)
+    m = DirectVoxGO(lo, hi, **kw)
+    syn.randomize_grids_(m, 3)
+    with torch.no_grad():
+        m.density.mul_(3.0)
+    m = m.to(DEV)
+    rk = dict(syn.RENDER_KWARGS)
+    ro, rd, vd, _ = syn.random_training_rays(n_rays, n_views=20, seed=5, device=DEV)
+    fr = FusedRenderer(m, rk, mlp="tc")
+    ws = fr._workspace(n_rays, False)
+    pe, pe16 = fr._tc_embed(vd)
+    C, ps = rgbnet_dim, pe.shape[1]
+    P = 3 + 6 * int(fr._viewfreq().numel())
+    ws.tiles(C, ps, False)                              # allocated zeroed: padding-only chunks are never written
+    K1 = (C + ps + 15) // 16 * 16
+
+    def row_of(t, p):
+        return np.array([t[(p // 128) * 128 * K1 + (((p % 128) // 8) * (K1 // 8) * 128 + (c // 8) * 128 + (p % 8) * 16 + (c % 8) * 2) // 2]
+                         for c in range(K1)], np.float32)
+
+    m4_prev = 0
+    for n_use in (n_rays, n_rays // 2):                 # second pass: fewer survivors over the first pass's stale rows
+        fr._march(ws, ro[:n_use].contiguous(), rd[:n_use].contiguous(), (pe, pe16))
+        torch.cuda.synchronize()
+        got = ws.xt.clone()
+        m4 = int(ws.counters[0])
+        assert m4 > 256 and m4 != m4_prev
+        # the fp32 feature stream of the SAME survivor stream (its order is not reproducible across marches)
+        ext.k0_gather(fr.scene, ro[:n_use].contiguous(), rd[:n_use].contiguous(), fr.k0, ws.t_min, ws.ray_off, ws.s_ray,
+                      ws.s_slot, ws.counters, ws.feat)
+        want = torch.zeros_like(got)
+        ext.mlp_pack_x(ws.feat, ws.s_ray, pe, P, ws.counters, want)
+        torch.cuda.synchronize()
+        used = (m4 + 255) // 256 * 256 * K1 * 2         # bytes of the tiles up to the end of the last pair
+        assert torch.equal(got[:used], want[:used])
+        if m4_prev == 0:
+            assert torch.all(got[used:] == 0)           # nothing written past the pair
+        t = got[:used].cpu().numpy().view(np.float16)
+        for p in (0, 7, 129, m4 - 1):                   # decode the operand layout on the host
+            row = row_of(t, p)
+            x = torch.cat([ws.feat[p], pe[int(ws.s_ray[p])]]).half().float().cpu().numpy()
+            np.testing.assert_array_equal(row[:C + ps], x)
+            assert np.all(row[C + ps:] == 0)
+        for p in range(m4, (m4 + 255) // 256 * 256, 37):  # rows between the count and the end of the pair are zero
+            assert np.all(row_of(t, p) == 0)
+        m4_prev = m4
+
+    # dZ3 tiles from sample_grad
+    g = torch.Generator().manual_seed(1)
+    cap = ws.cap
+    rgb = torch.rand(cap, 3, generator=g).to(DEV)
+    w = torch.rand(cap, generator=g).to(DEV)
+    G = (torch.randn(n_rays, 3, generator=g) / n_rays).to(DEV)
+    tgt = torch.rand(n_rays, 3, generator=g).to(DEV)
+    d_rgb, d_w = torch.empty(cap, 3, device=DEV), torch.empty(cap, device=DEV)
+    loss = torch.zeros(2, device=DEV)
+    dzt = torch.zeros(ext.mlp_dztile_bytes(cap), dtype=torch.uint8, device=DEV)
+    dzt.view(-1, 128)[0::2] = 0xCD                      # stale bytes in every written chunk (columns 0..7 of all rows)
+    S = 2.0 ** 18
+    ext.sample_grad(rgb, w, ws.s_ray, G, tgt, ws.counters, n_rays, 0.01, d_rgb, d_w, loss, dzt, S)
+    want = torch.zeros_like(dzt)
+    ext.mlp_pack_dz(rgb, d_rgb, S, ws.counters, want)
+    torch.cuda.synchronize()
+    used = (m4 + 255) // 256 * 256 * 32
+    assert torch.equal(dzt[:used], want[:used])
+    assert torch.all(dzt[used:].view(-1, 128)[0::2] == 0xCD)       # nothing written past the pair
+    z = (d_rgb[:m4] * rgb[:m4] * (1 - rgb[:m4]) * S).half().cpu().numpy()
+    t = dzt[:used].cpu().numpy().view(np.float16)
+    for p in (0, 200, m4 - 1):
+        off = (p // 128) * 2048 + ((p % 128) // 8) * 128 + (p % 8) * 8
+        np.testing.assert_array_equal(t[off:off + 3], z[p])
+        assert np.all(t[off + 3:off + 8] == 0) and np.all(t[off + 64:off + 72] == 0)

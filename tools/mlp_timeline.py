@@ -28,7 +28,7 @@ def show(who, t, names, first_tile=2, n_show=3):
 for _ in range(2):
     tl = ext.mlp_fwd_timeline(feat, s_ray, pe_pad, 27, counters, tc.params, 128, rgb)
 torch.cuda.synchronize()
-fwd = ["rays + wait L1", "e1->TMEM+sync", "issue L2 + stage next", "wait L2", "e2->TMEM+sync", "issue L3, L1(next) + wait L3", "e3 sigmoid+store", "loop"]
+fwd = ["wait L1 + refill X", "e1->TMEM+sync", "issue L2", "wait L2", "e2->TMEM+sync", "issue L3, L1(next) + wait L3", "e3 sigmoid+store", "loop"]
 t0 = tl[0:64].cpu().tolist()
 print("forward prologue (entry -> first loop top): %d cycles" % (t0[1] - t0[0]))
 show("forward, thread 0", t0[1:], fwd)
@@ -40,7 +40,7 @@ d_feat = torch.zeros(cap, 12, device="cuda")
 for _ in range(2):
     tl = ext.mlp_bwd_timeline(feat, s_ray, pe_pad, 27, counters, tcb.params, 128, rgb, d_rgb, 2.0 ** 21, d_feat, tcb.grad_flat)
 torch.cuda.synchronize()
-epi = ["stage A+B"] + [x for ph in ("relu1", "relu2", "mask2", "mask1") for x in
+epi = ["loop top"] + [x for ph in ("relu1", "relu2", "mask2", "mask1") for x in
                        ("wait A", ph + " A", "wait B", ph + " B")] + ["wait A", "dx A + wait B", "dx B"]
 t0 = tl[0:64].cpu().tolist()
 show("backward, epilogue thread 0", t0, epi, first_tile=1)
