@@ -29,7 +29,7 @@ def _load_native():
         raise ImportError(
             "directvoxgo_b200: the native extension directvoxgo_b200/_C*.so (and libdvgo_b200.so) "
             "is missing or does not load (%s). Build it in-tree with "
-            "`python -m directvoxgo_b200.build`; there is no CPU/PyTorch fallback." % (e,)) from e
+            "`python directvoxgo_b200/build.py`; there is no CPU/PyTorch fallback." % (e,)) from e
 
 
 _C = _load_native()

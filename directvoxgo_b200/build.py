@@ -3,7 +3,8 @@
   directvoxgo_b200/libdvgo_b200.so   nvcc, sm_100a only, CUDA headers only  -> the C ABI
   directvoxgo_b200/_C<ext>.so        g++,  torch headers                    -> the thin torch binding
 
-`python -m directvoxgo_b200.build [--force]`; also called by __graft_entry__.build().
+`python directvoxgo_b200/build.py [--force]` (run as a script: the package itself refuses to import
+before these exist); also called by __graft_entry__.build().
 """
 import hashlib
 import os
