@@ -80,6 +80,7 @@ void march_fwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor density, c1
   F32(rays_o); F32(rays_d); F32(density); F32(t_min); I32(n_steps); I32(ray_off); F32(slot_alpha);
   F32(slot_T); F32(slot_expd); I32(slot_code); F32(feat); I32(s_ray); I32(s_slot); F32(s_weight);
   F32(alphainv_last); I32(counters);
+  const bool keep_slots = slot_code.numel() > 0;   // empty slot arrays = forward-only (rendering): no per-slot record
   if (k0_cl.has_value()) { F32((*k0_cl)); TORCH_CHECK(k0_cl->numel() == density.numel() * sc.s.C, "k0_cl must be [X,Y,Z,C]"); }
   TORCH_CHECK(density.numel() == (int64_t)sc.s.X * sc.s.Y * sc.s.Z, "density must be [X,Y,Z]");
   const int n = rays_o.size(0);
@@ -90,8 +91,9 @@ void march_fwd(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor density, c1
   if (s_pos.has_value()) { F32((*s_pos)); TORCH_CHECK(s_pos->numel() >= surv_cap * 4, "s_pos must be [surv_cap,4]"); }
   const c10::cuda::CUDAGuard guard(rays_o.device());
   rc_check(dvgo_fused_march_fwd(fp(rays_o), fp(rays_d), &sc.s, fp(density), fp_opt(k0_cl), n, fp(t_min),
-                                ipm(n_steps), ipm(ray_off), slot_cap, surv_cap, fpm(slot_alpha), fpm(slot_T),
-                                fpm(slot_expd), ipm(slot_code), fpm(feat), ipm(s_ray), ipm(s_slot),
+                                ipm(n_steps), ipm(ray_off), slot_cap, surv_cap, keep_slots ? fpm(slot_alpha) : nullptr,
+                                keep_slots ? fpm(slot_T) : nullptr, keep_slots ? fpm(slot_expd) : nullptr,
+                                keep_slots ? ipm(slot_code) : nullptr, fpm(feat), ipm(s_ray), ipm(s_slot),
                                 fpm(s_weight), fpm(alphainv_last), ipm(counters),
                                 s_pos.has_value() ? s_pos->data_ptr<float>() : nullptr, cur_stream()), "march_fwd");
 }
@@ -120,6 +122,29 @@ void k0_gather_tiles(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor k0_cl
                                       ipm(s_slot), ipm(counters), s_ray.numel(),
                                       s_pos.has_value() ? s_pos->data_ptr<float>() : nullptr, pe16.data_ptr(), pe_stride,
                                       xt.data_ptr(), cur_stream()), "k0_gather_tiles");
+}
+
+// k0 gather + rgbnet forward in one kernel (mlp_fwd_gather_kernel): rgb [surv_cap,3]; xt (training): the X~ tiles the
+// backward kernel reads, written by one bulk copy per tile; None (rendering): the tiles never leave shared memory.
+void mlp_fwd_gather(const Scene& sc, Tensor k0_cl, Tensor s_pos, Tensor pe16, int P, int pe_stride, Tensor counters,
+                    int64_t cap, Tensor wpack, Tensor rgb, c10::optional<Tensor> xt) {
+  F32(k0_cl); F32(s_pos); I32(counters); F32(rgb);
+  TORCH_CHECK(s_pos.numel() >= cap * 4, "s_pos must be [surv_cap,4]");
+  TORCH_CHECK(rgb.numel() >= cap * 3, "rgb too small");
+  TORCH_CHECK(pe16.is_cuda() && pe16.is_contiguous() && pe16.scalar_type() == torch::kHalf && pe16.dim() == 2 &&
+              pe16.size(1) == ((sc.s.C + pe_stride + 15) / 16) * 16,
+              "pe16 must be the [n_rays, K1] half table view_embedding(..., C) returns");
+  TORCH_CHECK(wpack.is_cuda() && wpack.is_contiguous() && wpack.scalar_type() == torch::kUInt8 &&
+              wpack.numel() >= dvgo_mlp_wpack_bytes(sc.s.C, pe_stride) &&
+              reinterpret_cast<uintptr_t>(wpack.data_ptr()) % 16 == 0, "wpack: uint8 CUDA tensor of mlp_wpack_bytes bytes");
+  if (xt.has_value())
+    TORCH_CHECK(xt->is_cuda() && xt->is_contiguous() && xt->scalar_type() == torch::kUInt8 &&
+                xt->numel() >= dvgo_mlp_xtile_bytes(cap, sc.s.C, pe_stride) &&
+                reinterpret_cast<uintptr_t>(xt->data_ptr()) % 16 == 0, "xt: uint8 CUDA tensor of mlp_xtile_bytes bytes");
+  const c10::cuda::CUDAGuard guard(k0_cl.device());
+  rc_check(dvgo_mlp_fwd_gather(&sc.s, fp(k0_cl), fp(s_pos), pe16.data_ptr(), P, pe_stride, ipm(counters), cap,
+                               wpack.data_ptr(), fpm(rgb), xt.has_value() ? xt->data_ptr() : nullptr, cur_stream()),
+           "mlp_fwd_gather");
 }
 
 void k0_scatter(const Scene& sc, Tensor rays_o, Tensor rays_d, Tensor t_min, Tensor ray_off, Tensor s_ray, Tensor s_slot,
@@ -431,6 +456,7 @@ void dvgo_bind_fused(pybind11::module_& m) {
   m.def("march_fwd", &march_fwd, pybind11::arg("scene"), pybind11::arg("rays_o"), pybind11::arg("rays_d"), pybind11::arg("density"), pybind11::arg("k0_cl"), pybind11::arg("t_min"), pybind11::arg("n_steps"), pybind11::arg("ray_off"), pybind11::arg("slot_alpha"), pybind11::arg("slot_T"), pybind11::arg("slot_expd"), pybind11::arg("slot_code"), pybind11::arg("feat"), pybind11::arg("s_ray"), pybind11::arg("s_slot"), pybind11::arg("s_weight"), pybind11::arg("alphainv_last"), pybind11::arg("counters"), pybind11::arg("s_pos") = pybind11::none());
   m.def("k0_gather", &k0_gather);
   m.def("k0_gather_tiles", &k0_gather_tiles);
+  m.def("mlp_fwd_gather", &mlp_fwd_gather);
   m.def("k0_scatter", &k0_scatter, pybind11::arg("scene"), pybind11::arg("rays_o"), pybind11::arg("rays_d"), pybind11::arg("t_min"), pybind11::arg("ray_off"), pybind11::arg("s_ray"), pybind11::arg("s_slot"), pybind11::arg("counters"), pybind11::arg("d_feat"), pybind11::arg("grad_k0_cl"), pybind11::arg("s_pos") = pybind11::none());
   m.def("rgb_direct", &rgb_direct);
   m.def("rgb_direct_bwd", &rgb_direct_bwd);

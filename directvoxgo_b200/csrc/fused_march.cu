@@ -15,6 +15,7 @@
 // Arithmetic follows the reference expression trees exactly where integer / boolean results depend
 // on it (common.cuh); see include/dvgo_b200_fused.h for the data layout.
 #include "fused_scene.cuh"
+#include "k0_tiles.cuh"
 #include "tc_common.cuh"
 
 namespace dvgo {
@@ -194,7 +195,9 @@ __global__ void __launch_bounds__(256, 3) march_fwd_kernel(
         base4 = __shfl_sync(0xffffffffu, base4, 0);
         if (surv) idx4 = base4 + __popc(smask & ((1u << lane) - 1u));
       }
-      if (valid && slot < slot_cap) {
+      if (!slot_code) {
+        // forward-only call (rendering): no backward pass will read the per-slot record
+      } else if (valid && slot < slot_cap) {
         slot_code[slot] = surv ? idx4 : (in_scan ? -1 : -2);
         if (in_scan) { slot_alpha[slot] = alpha; slot_T[slot] = T_before; slot_expd[slot] = e; }
       } else if (valid) {
@@ -381,15 +384,10 @@ __global__ void __launch_bounds__(256) k0_gather_kernel(
 
 // k0_gather with the rgbnet's X~ tiles as output (tc_common.cuh: tiles_for; include/dvgo_b200_fused.h): row p of
 // the tile stream = [k0 features (C) | pe[s_ray[p]] (pe_stride) | 0 ...] as saturated fp16 in the tensor core's operand
-// layout, K1 columns.  In that layout a row is K1/8 CHUNKS of 16 bytes, one per 128-byte core matrix, and the same
-// chunk of 8 consecutive rows is one contiguous 128-byte line: every store below is a 16-byte chunk and the G = C/4
-// threads of consecutive survivors write the same chunk index in the same instruction, so the stores leave the SM as
-// full 32-byte sectors (a first version with 8-byte stores per thread cost +47 us per step in partial-sector writes).
-//   chunk k < ceil(G/2)  : feature units 2k, 2k+1 -> thread 2k of the survivor (unit 2k+1 arrives by one shuffle)
-//   other chunks         : embedding / padding columns, dealt round-robin to the G threads
-//   chunks that lie entirely past C + pe_stride are never written: the buffer is allocated zeroed
-// Rows from the survivor count to the next multiple of 256 are written as zeros (the backward kernel consumes tile
-// pairs).  A warp holds 32/G whole survivors (30 active lanes for G = 3).
+// layout, K1 columns (the row itself: k0_tiles.cuh).  Rows from the survivor count to the next multiple of 256 are
+// written as zeros (the backward kernel consumes tile pairs).  A warp holds 32/G whole survivors (30 active lanes for
+// G = 3).  The fused step / renderer use mlp_fwd_gather_kernel (fused_mlp.cu) instead, which builds the same rows
+// straight into the shared-memory tile; this kernel serves callers that want the tiles in global memory.
 template <int C>
 __global__ void __launch_bounds__(256, 3) k0_gather_tiles_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
@@ -397,9 +395,8 @@ __global__ void __launch_bounds__(256, 3) k0_gather_tiles_kernel(
     const int32_t* __restrict__ s_ray, const int32_t* __restrict__ s_slot,
     const int32_t* __restrict__ counters, int64_t surv_cap, const float4* __restrict__ s_pos,
     const uint8_t* __restrict__ pe16, int pe_stride, int K1, uint8_t* __restrict__ xt) {
-  constexpr int G = (C % 4 == 0) ? C / 4 : 1;   // threads per survivor
-  constexpr int SPW = 32 / G;                   // survivors per warp
-  constexpr int FC = (G + 1) / 2;               // chunks that hold feature columns (C % 4 == 0 path)
+  constexpr int G = K0TileShape<C>::G;           // threads per survivor
+  constexpr int SPW = K0TileShape<C>::SPW;       // survivors per warp
   const SceneDev sc = load_scene(a);
   int64_t n = counters[0];
   if (n > surv_cap) n = surv_cap;
@@ -415,7 +412,6 @@ __global__ void __launch_bounds__(256, 3) k0_gather_tiles_kernel(
     const bool active = sub < SPW && p < rows;
     const bool live = active && p < n;
     uint8_t* __restrict__ trow = xt + (p >> 7) * xb + tc::tile_off(static_cast<int>(p & 127), 0, K1);
-    auto chunk_ptr = [&](int k) { return reinterpret_cast<uint4*>(trow + k * 128); };
     int r = 0;
     Corner8 cn;
     cn.valid = 0u;
@@ -433,84 +429,7 @@ __global__ void __launch_bounds__(256, 3) k0_gather_tiles_kernel(
         cn = corner8(sc, px, py, pz);
       }
     }
-    // the ray's share of the row, already fp16 (view_embedding's rows16): chunk k at byte 16 k
-    const uint8_t* __restrict__ e = pe16 + static_cast<int64_t>(r) * (K1 * 2);
-    if (C % 4 == 0) {
-      // Every lane runs the same instruction stream (predicated): embedding chunk loads, the eight corner loads, then
-      // the stores.  (Dealing the chunks out under divergent branches serialised one load round trip per branch.)
-      constexpr int NJ = (8 - FC + G - 1) / G;          // embedding / padding chunks per thread, at most
-      const int k_first = FC + (q + G - 1) % G;         // this thread's chunks: k_first + j G
-      uint4 pv[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int k = k_first + j * G;
-        pv[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (live && k < used_chunks) pv[j] = __ldg(reinterpret_cast<const uint4*>(e + 16 * k));
-      }
-      const bool odd_tail = (q & 1) == 0 && q + 1 >= G;  // last feature chunk of an odd G: its upper unit is embedding
-      uint2 ph = make_uint2(0u, 0u);
-      if (live && odd_tail) ph = __ldg(reinterpret_cast<const uint2*>(e + 8 * (q + 1)));
-      // All eight corner loads are issued unconditionally (a corner outside the grid reads voxel 0 and is skipped by
-      // the predicated multiply-add below): with predicated loads ptxas gave successive loads the same destination
-      // registers and waited for each before issuing the next -- 7 dependent memory round trips per thread, 65 % of
-      // the kernel's stall samples (ncu, round 2).
-      float4 f[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        f[k] = __ldg(reinterpret_cast<const float4*>(k0 + static_cast<int64_t>(cn.ok(k) ? cn.off(k) : 0) * C + q * 4));
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (!cn.ok(k)) continue;
-        const float wk = cn.w(k);
-        acc[0] = fma_(f[k].x, wk, acc[0]); acc[1] = fma_(f[k].y, wk, acc[1]);
-        acc[2] = fma_(f[k].z, wk, acc[2]); acc[3] = fma_(f[k].w, wk, acc[3]);
-      }
-      const uint2 mine = tc::pack4(make_float4(acc[0], acc[1], acc[2], acc[3]));
-      uint2 nb;                         // the feature unit of the next thread of the same survivor
-      nb.x = __shfl_down_sync(0xffffffffu, mine.x, 1);
-      nb.y = __shfl_down_sync(0xffffffffu, mine.y, 1);
-      if (active) {
-        if ((q & 1) == 0) {             // feature chunk q/2: units q (mine) and q + 1 (neighbour, or embedding)
-          const uint2 hi = odd_tail ? ph : nb;
-          *chunk_ptr(q >> 1) = make_uint4(mine.x, mine.y, hi.x, hi.y);
-        }
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int k = k_first + j * G;
-          if (k < used_chunks) *chunk_ptr(k) = pv[j];
-        }
-      }
-    } else if (active) {   // one thread per survivor, channel counts that are no multiple of 4 (3, 6, 9)
-      float acc[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (!cn.ok(k)) continue;
-        const float* __restrict__ v = k0 + static_cast<int64_t>(cn.off(k)) * C;
-        const float wk = cn.w(k);
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = fma_(__ldg(v + c), wk, acc[c]);
-      }
-      constexpr int CK = (C + 7) / 8;      // chunks that hold at least one feature column
-#pragma unroll
-      for (int k = 0; k < CK; ++k) {       // feature halves, then whatever the ray's row holds in the rest of the chunk
-        uint4 rowc = make_uint4(0u, 0u, 0u, 0u);
-        if (live) rowc = __ldg(reinterpret_cast<const uint4*>(e + 16 * k));
-        __half h[8];
-        *reinterpret_cast<uint4*>(h) = rowc;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (8 * k + j < C) h[j] = __low2half(tc::pack2_sat(acc[8 * k + j], 0.f));
-        *chunk_ptr(k) = *reinterpret_cast<const uint4*>(h);
-      }
-      for (int k = CK; k < used_chunks; ++k) {
-        uint4 rowc = make_uint4(0u, 0u, 0u, 0u);
-        if (live) rowc = __ldg(reinterpret_cast<const uint4*>(e + 16 * k));
-        *chunk_ptr(k) = rowc;
-      }
-    }
+    k0_tile_row<C, false>(k0, cn, r, active, live, pe16, K1, used_chunks, trow, q);
   }
 }
 
@@ -598,18 +517,6 @@ DVGO_API int dvgo_fused_ray_setup(const float* rays_o, const float* rays_d, cons
   return launch_status(n_rays > 0 ? 2 : 1);
 }
 
-#define DVGO_DISPATCH_C(Cval, ...)                       \
-  switch (Cval) {                                        \
-    case 3: { constexpr int kC = 3; __VA_ARGS__; } break;   \
-    case 4: { constexpr int kC = 4; __VA_ARGS__; } break;   \
-    case 6: { constexpr int kC = 6; __VA_ARGS__; } break;   \
-    case 8: { constexpr int kC = 8; __VA_ARGS__; } break;   \
-    case 9: { constexpr int kC = 9; __VA_ARGS__; } break;   \
-    case 12: { constexpr int kC = 12; __VA_ARGS__; } break; \
-    case 16: { constexpr int kC = 16; __VA_ARGS__; } break; \
-    default: return DVGO_EINVAL;                         \
-  }
-
 DVGO_API int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
                                   const float* density, const float* k0_cl, int n_rays,
                                   const float* t_min, const int32_t* n_steps, const int32_t* ray_off,
@@ -619,10 +526,12 @@ DVGO_API int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, cons
                                   int32_t* counters, float* s_pos, dvgo_stream_t stream) {
   if (n_rays < 0 || !scene) return DVGO_EINVAL;
   if (n_rays == 0) return 0;
-  if (!rays_o || !rays_d || !density || !t_min || !n_steps || !ray_off || !slot_alpha || !slot_T ||
-      !slot_expd || !slot_code || !s_ray || !s_slot || !s_weight || !alphainv_last || !counters ||
-      (k0_cl && !feat))
+  if (!rays_o || !rays_d || !density || !t_min || !n_steps || !ray_off || !s_ray || !s_slot || !s_weight ||
+      !alphainv_last || !counters || (k0_cl && !feat))
     return DVGO_EINVAL;
+  // the four slot arrays come together or not at all (all NULL = forward-only: nothing is kept for march_bwd)
+  const int n_slot_arrays = (slot_alpha != nullptr) + (slot_T != nullptr) + (slot_expd != nullptr) + (slot_code != nullptr);
+  if (n_slot_arrays != 0 && n_slot_arrays != 4) return DVGO_EINVAL;
   // 2 rays (warps) per CTA: a CTA holds its slot until its longest ray ends, so small CTAs pack the SMs better
   // (measured on B200, 8192 rays: 8 warps/CTA 0.205 + 0.243 ms for the two march stages, 2 warps/CTA 0.198 + 0.231 ms)
   const int wpb = 2;

@@ -10,6 +10,8 @@
 // Stated tolerance vs the exact-fp32 path: 2e-3 abs on rgb (tests/test_gpu_mlp.py).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "fused_scene.cuh"
+#include "k0_tiles.cuh"
 #include "../../include/dvgo_b200_fused.h"
 
 namespace dvgo {
@@ -272,6 +274,7 @@ __device__ __forceinline__ void relu_pack32(uint32_t taddr, uint32_t* u) {
 // No thread of this kernel issues a global LOAD inside the loop: round 2's register-staged version lost 20-30 % of
 // every tile to scoreboard-shared stalls around its prefetch registers.
 constexpr uint32_t kFwdTH = 128, kFwdTD3 = 224;
+constexpr int kFwdIssuer = 4;   // the MMA-issuing warp: one of the four (half 1) that have no rgb epilogue to do
 
 __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     const uint8_t* __restrict__ xt, int32_t* __restrict__ counters, int64_t surv_cap,
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
   };
   // one elected thread: arm the buffer's barrier and start the bulk copy of tile t into X buffer b
   auto load_x = [&](int64_t t, uint32_t b) {
-    if (warp == 0) {
+    if (warp == kFwdIssuer) {
       if (elect_one()) {
         mbar_expect_tx(xbar + 8u * b, x_bytes);
         bulk_g2s(smem_u32(sXb) + b * x_bytes, xt + t * static_cast<int64_t>(x_bytes), x_bytes, xbar + 8u * b);
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     fence_after_sync();
   };
   auto issue_l1 = [&](uint32_t b) {       // waits for the tile in X buffer b, then queues layer 1 on it
-    if (warp == 0) {
+    if (warp == kFwdIssuer) {
       if (elect_one()) {
         mbar_wait(xbar + 8u * b, (xphase >> b) & 1u);
         gemm_kk(tD, smem_u32(sXb) + b * x_bytes, K1, smem_u32(sW1), K1, kHid, K1, false);
@@ -361,14 +364,31 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     xphase ^= 1u << b;
   };
 
+  // layer-3 epilogue of the tile at sample offset s_prev: sigmoid(D3 + b3) -> rgb (half 0 only; warp-uniform)
+  auto epilogue_rgb = [&](int64_t s_prev) {
+    if (half == 0) {                                         // tcgen05.ld is warp-collective
+      float z[16];
+      tmem_ld16(tD3 + lane_sel, z);
+      tmem_ld_wait();
+      if (s_prev + row < count) {
+        const float z0 = z[0] + sB3[0], z1 = z[1] + sB3[1], z2 = z[2] + sB3[2];
+        float* __restrict__ o = rgb + (s_prev + row) * 3;
+        o[0] = __frcp_rn(1.f + expf(-z0));   // correctly rounded reciprocal == 1.f / x without the division's range fix-ups
+        o[1] = __frcp_rn(1.f + expf(-z1));
+        o[2] = __frcp_rn(1.f + expf(-z2));
+        if (!(fabsf(z0) + fabsf(z1) + fabsf(z2) < 3.0e38f)) counters[1] = counters[1] | 2;  // NaN / inf logit
+      }
+    }
+  };
+
   const int64_t step = gridDim.x;
   int64_t tile = blockIdx.x;
   load_x(tile, 0u);
   if (tile + step < n_tiles) load_x(tile + step, 1u);
   issue_l1(0u);
   uint32_t buf = 0u;
+  int64_t s_prev = -1;
   for (; tile < n_tiles; tile += step, buf ^= 1u) {
-    const int64_t s0 = tile * kTile;
     const bool has_next = tile + step < n_tiles;
     stamp();
     mma_wait(chain);                                       // L1(tile): X buffer `buf` is free again
@@ -376,7 +396,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
     stamp();
     epilogue_to_h();                                       // H1
     stamp();
-    if (warp == 0) {
+    if (warp == kFwdIssuer) {
       if (elect_one()) {
         gemm_ts(tD, tH, desc_kmajor(smem_u32(sW2), kHidA), 256u, idesc128, kHidA / kMmaK, false);
         mma_commit(chain.bar);
@@ -384,11 +404,20 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
       __syncwarp();
     }
     stamp();
+    // The previous tile's rgb epilogue runs HERE, in the shadow of this tile's layer-2 MMAs (576 cycles of tensor time
+    // during which the CTA had nothing to do), by the four warps that do not issue.  It used to sit between L3 and the
+    // next tile's first epilogue: ~670 cycles of every tile's dependency chain (tools/mlp_timeline.py).  L3 of THIS
+    // tile, the next writer of D3, is issued after the CTA barrier of the H2 epilogue below.
+    if (s_prev >= 0) {
+      mma_wait(out3);                                      // L3(previous tile): long done
+      epilogue_rgb(s_prev);
+    }
+    stamp();
     mma_wait(chain);                                       // L2(tile)
     stamp();
     epilogue_to_h();                                       // H2 (b2 came through the constant-1 K step)
     stamp();
-    if (warp == 0) {
+    if (warp == kFwdIssuer) {
       if (elect_one()) {
         gemm_ts(tD3, tH, desc_kmajor(smem_u32(sW3), kHid), 256u, idesc16, kHid / kMmaK, false);
         mma_commit(out3.bar);
@@ -396,26 +425,221 @@ __global__ void __launch_bounds__(kMlpThreads, 2) mlp_fwd_kernel(
       __syncwarp();
     }
     if (has_next) issue_l1(buf ^ 1u);                      // L1 of the next tile queues behind L3: D is free, H is not touched
-    mma_wait(out3);                                        // L3(tile)
+    s_prev = tile * kTile;
     stamp();
-    if (half == 0) {                                       // warp-uniform: tcgen05.ld is warp-collective
+  }
+  mma_wait(out3);                                          // L3 of the CTA's last tile
+  epilogue_rgb(s_prev);
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ---- forward with the k0 gather fused in --------------------------------------------------------------
+// mlp_fwd_kernel plus four PRODUCER warps per CTA that build the X~ tile straight into the shared-memory buffer the
+// layer-1 MMA reads (the row code of k0_gather_tiles_kernel: k0_tiles.cuh): the trilinear k0 gather (8 corners x C
+// floats per survivor, L1-wavefront bound: ncu l1tex data-pipe 71 % in the stand-alone kernel) runs in the shadow of
+// the tensor-core chain of the previous tiles instead of in front of it, and the tiles no longer travel through HBM
+// (96 B written + 96 B read per survivor; 800x800 dense render: 18 GB per frame each way).
+//   producers (warps 8..11): wait xempty[b] -> rows of tile j into X buffer b = j & 1 -> fence.proxy.async -> one
+//                            arrival per warp on xfull[b]
+//   issuer (warp 4)        : wait xfull[b] -> [training: one bulk copy shared -> global of the finished tile, the
+//                            backward kernel's input] -> layer-1 MMAs -> commit on `chain` and on xempty[b]
+// The eight consumer warps run mlp_fwd_kernel's loop unchanged; their CTA-wide barriers become a named barrier of 256.
+constexpr int kFgProducerWarps = 4;
+constexpr int kFgThreads = kMlpThreads + 32 * kFgProducerWarps;
+
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kMlpThreads) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_saddr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_saddr), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_s2g_wait_read() {   // the source buffer may be overwritten
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kFgThreads, 2) mlp_fwd_gather_kernel(
+    SceneArgs a, const float* __restrict__ k0, const float4* __restrict__ s_pos, const uint8_t* __restrict__ pe16,
+    int pe_stride, int32_t* __restrict__ counters, int64_t surv_cap, const uint8_t* __restrict__ wpack, int K1,
+    float* __restrict__ rgb, uint8_t* __restrict__ xt_out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[6];   // chain (L1 / L2), out3 (L3), xfull[0,1], xempty[0,1]
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sB3[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int64_t count = counters[0];
+  if (count > surv_cap) count = surv_cap;
+  const int64_t n_tiles = (count + kTile - 1) / kTile;
+  // training: the backward kernel consumes tile PAIRS, so an odd tile count is completed by one all-zero tile
+  const int64_t n_proc = xt_out ? 2 * ((n_tiles + 1) / 2) : n_tiles;
+  if (static_cast<int64_t>(blockIdx.x) >= n_proc) return;  // uniform per CTA, before any allocation
+
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW1 = base;                                        // [128 out][K1]   K-major B of layer 1
+  uint8_t* sW2 = sW1 + align1k(tile_bytes(kHid, K1));         // [128 out][144]  K-major B of layer 2 (col 128 = b2)
+  uint8_t* sW3 = sW2 + align1k(tile_bytes(kHid, kHidA));      // [16 out][128]   K-major B of layer 3 (rows >= 3 zero)
+  uint8_t* sXb = sW3 + align1k(tile_bytes(16, kHid));         // 2 x [128 samples][K1] (double-buffered)
+  const uint32_t x_bytes = tile_bytes(kTile, K1);             // K1 * 256: a multiple of 1024
+
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), kFgProducerWarps);
+    mbar_init(smem_u32(&bars[3]), kFgProducerWarps);
+    mbar_init(smem_u32(&bars[4]), 1);
+    mbar_init(smem_u32(&bars[5]), 1);
+    mbar_init_fence();
+  }
+  const WPack wl = wpack_layout(K1);
+  copy_to_smem(sW1, wpack, wl.offW3p);      // W1~ | W2~ | W3 tiles, same offsets in shared memory as in the pack
+  for (uint32_t i = tid; i < 2u * x_bytes / 16u; i += blockDim.x)   // padding chunks of the rows are never rewritten
+    reinterpret_cast<uint4*>(sXb)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 3) sB3[tid] = reinterpret_cast<const float*>(wpack + wl.offB3)[tid];
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t xfull = smem_u32(&bars[2]), xempty = smem_u32(&bars[4]);
+  const int64_t step = gridDim.x;
+
+  if (warp >= kMlpThreads / 32) {
+    // ---- producers ----
+    constexpr int G = K0TileShape<C>::G, SPW = K0TileShape<C>::SPW;
+    const SceneDev sc = load_scene(a);
+    const int pw = warp - kMlpThreads / 32;
+    const int q = lane % G, sub = lane / G;
+    const int used_chunks = (C + pe_stride + 7) >> 3;
+    uint32_t ephase = 0u, j = 0u;
+    for (int64_t tile = blockIdx.x; tile < n_proc; tile += step, ++j) {
+      const uint32_t b = j & 1u;
+      if (j >= 2u) {                       // the layer-1 MMAs (and the copy-out) of the buffer's previous tile are done
+        mbar_wait(xempty + 8u * b, (ephase >> b) & 1u);
+        ephase ^= 1u << b;
+      }
+      uint8_t* sx = sXb + b * x_bytes;
+      for (int pass = pw; pass * SPW < kTile; pass += kFgProducerWarps) {   // warp-uniform trip count
+        const int row = pass * SPW + sub;
+        const bool active = sub < SPW && row < kTile;
+        const int64_t p = tile * kTile + row;
+        const bool live = active && p < count;
+        int r = 0;
+        Corner8 cn;
+        cn.valid = 0u;
+        if (live) {
+          const float4 rec = __ldg(s_pos + p);
+          r = __float_as_int(rec.w);
+          cn = corner8_idx(sc, rec.x, rec.y, rec.z);
+        }
+        k0_tile_row<C, true>(k0, cn, r, active, live, pe16, K1, used_chunks, sx + tile_off(active ? row : 0, 0, K1), q);
+      }
+      fence_async_smem();                  // this lane's rows -> visible to the tensor core / the bulk copy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xfull + 8u * b);
+    }
+    return;
+  }
+
+  // ---- consumers: mlp_fwd_kernel's loop ----
+  const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+  const uint32_t tD = tmem, tH = tmem + kFwdTH, tD3 = tmem + kFwdTD3;
+  if (half == 0) {   // K = 128..143 of H: the constant 1 (fp16 0x3C00 in the low half of column 64), written once
+    const uint32_t one[8] = {0x3C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tmem_st8(tH + lane_sel + 64, one);
+    tmem_st_wait();
+  }
+  MmaCtx chain{smem_u32(&bars[0]), 0u};
+  MmaCtx out3{smem_u32(&bars[1]), 0u};
+  uint32_t xphase = 0u;
+  const uint32_t idesc128 = make_idesc_f16(128, kHid, 0, 0), idesc16 = make_idesc_f16(128, 16, 0, 0);
+
+  auto epilogue_to_h = [&]() {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t u[16];
+      relu_pack32(tD + lane_sel + half * 64 + c * 32, u);
+      tmem_st16(tH + lane_sel + half * 32 + c * 16, u);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    consumer_sync();
+    fence_after_sync();
+  };
+  auto issue_l1 = [&](uint32_t b, int64_t t) {   // waits for tile t in X buffer b, then queues layer 1 on it
+    if (warp == kFwdIssuer) {
+      if (elect_one()) {
+        mbar_wait(xfull + 8u * b, (xphase >> b) & 1u);
+        if (xt_out) bulk_s2g(xt_out + t * static_cast<int64_t>(x_bytes), smem_u32(sXb) + b * x_bytes, x_bytes);
+        gemm_kk(tD, smem_u32(sXb) + b * x_bytes, K1, smem_u32(sW1), K1, kHid, K1, false);
+        mma_commit(chain.bar);
+        if (xt_out) bulk_s2g_wait_read();
+        mma_commit(xempty + 8u * b);       // second arrival of the same completion: the producers may refill the buffer
+      }
+      __syncwarp();
+    }
+    xphase ^= 1u << b;
+  };
+  auto epilogue_rgb = [&](int64_t s_prev) {
+    if (half == 0) {                                         // tcgen05.ld is warp-collective
       float z[16];
       tmem_ld16(tD3 + lane_sel, z);
       tmem_ld_wait();
-      if (s0 + row < count) {
+      if (s_prev + row < count) {
         const float z0 = z[0] + sB3[0], z1 = z[1] + sB3[1], z2 = z[2] + sB3[2];
-        float* __restrict__ o = rgb + (s0 + row) * 3;
-        o[0] = __frcp_rn(1.f + expf(-z0));   // correctly rounded reciprocal == 1.f / x without the division's range fix-ups
+        float* __restrict__ o = rgb + (s_prev + row) * 3;
+        o[0] = __frcp_rn(1.f + expf(-z0));
         o[1] = __frcp_rn(1.f + expf(-z1));
         o[2] = __frcp_rn(1.f + expf(-z2));
         if (!(fabsf(z0) + fabsf(z1) + fabsf(z2) < 3.0e38f)) counters[1] = counters[1] | 2;  // NaN / inf logit
       }
     }
-    stamp();
-    // L3 of the next tile is issued two CTA barriers from here, so these D3 reads are ordered before it
+  };
+
+  int64_t tile = blockIdx.x;
+  issue_l1(0u, tile);
+  uint32_t buf = 0u;
+  int64_t s_prev = -1;
+  for (; tile < n_proc; tile += step, buf ^= 1u) {
+    const bool has_next = tile + step < n_proc;
+    mma_wait(chain);                                       // L1(tile)
+    epilogue_to_h();                                       // H1
+    if (warp == kFwdIssuer) {
+      if (elect_one()) {
+        gemm_ts(tD, tH, desc_kmajor(smem_u32(sW2), kHidA), 256u, idesc128, kHidA / kMmaK, false);
+        mma_commit(chain.bar);
+      }
+      __syncwarp();
+    }
+    if (s_prev >= 0) {                                     // the previous tile's rgb, in the shadow of layer 2
+      mma_wait(out3);
+      epilogue_rgb(s_prev);
+    }
+    mma_wait(chain);                                       // L2(tile)
+    epilogue_to_h();                                       // H2
+    if (warp == kFwdIssuer) {
+      if (elect_one()) {
+        gemm_ts(tD3, tH, desc_kmajor(smem_u32(sW3), kHid), 256u, idesc16, kHid / kMmaK, false);
+        mma_commit(out3.bar);
+      }
+      __syncwarp();
+    }
+    if (has_next) issue_l1(buf ^ 1u, tile + step);
+    s_prev = tile * kTile;
+  }
+  mma_wait(out3);
+  epilogue_rgb(s_prev);
+  if (xt_out && warp == kFwdIssuer) {      // the tile copies must have landed in global memory before the CTA exits
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
   fence_before_sync();
-  __syncthreads();
+  consumer_sync();
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
@@ -1271,6 +1495,27 @@ DVGO_API int dvgo_mlp_fwd_timed(const void* xt, int C, int P, int pe_stride, int
 DVGO_API int dvgo_mlp_fwd(const void* xt, int C, int P, int pe_stride, int32_t* counters, int64_t surv_cap,
                           const void* wpack, float* rgb, dvgo_stream_t stream) {
   return dvgo_mlp_fwd_timed(xt, C, P, pe_stride, counters, surv_cap, wpack, rgb, nullptr, stream);
+}
+
+DVGO_API int dvgo_mlp_fwd_gather(const dvgo_scene_t* scene, const float* k0_cl, const float* s_pos,
+                                 const void* pe_rows16, int P, int pe_stride, int32_t* counters, int64_t surv_cap,
+                                 const void* wpack, float* rgb, void* xt_out, dvgo_stream_t stream) {
+  if (!scene || !mlp_shape_ok(scene->C, P, pe_stride) || scene->C < 1 || surv_cap < 0) return DVGO_EINVAL;
+  if (!k0_cl || !s_pos || !pe_rows16 || !counters || !wpack || !rgb) return DVGO_EINVAL;
+  if (surv_cap == 0) return 0;
+  const int K1 = mlp_k1(scene->C, pe_stride);
+  const size_t bytes = mlp_fwd_smem(K1);
+  const int64_t tiles = (surv_cap + kTile - 1) / kTile + 1;
+  const int grid = static_cast<int>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+  DVGO_DISPATCH_C(scene->C, {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_gather_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(bytes));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    mlp_fwd_gather_kernel<kC><<<grid, kFgThreads, bytes, as_stream(stream)>>>(
+        to_args(scene), k0_cl, reinterpret_cast<const float4*>(s_pos), static_cast<const uint8_t*>(pe_rows16), pe_stride,
+        counters, surv_cap, static_cast<const uint8_t*>(wpack), K1, rgb, static_cast<uint8_t*>(xt_out));
+  });
+  return launch_status();
 }
 
 DVGO_API int dvgo_mlp_bwd_timed(const void* xt, const void* dzt, int C, int P, int pe_stride, int32_t* counters,

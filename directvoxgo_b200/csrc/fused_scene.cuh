@@ -148,3 +148,16 @@ __device__ __forceinline__ Corner8 corner8(const SceneDev& sc, float px, float p
 }
 
 }  // namespace dvgo
+
+// k0 channel counts (rgbnet_dim) the fused kernels are instantiated for; any other returns DVGO_EINVAL
+#define DVGO_DISPATCH_C(Cval, ...)                       \
+  switch (Cval) {                                        \
+    case 3: { constexpr int kC = 3; __VA_ARGS__; } break;   \
+    case 4: { constexpr int kC = 4; __VA_ARGS__; } break;   \
+    case 6: { constexpr int kC = 6; __VA_ARGS__; } break;   \
+    case 8: { constexpr int kC = 8; __VA_ARGS__; } break;   \
+    case 9: { constexpr int kC = 9; __VA_ARGS__; } break;   \
+    case 12: { constexpr int kC = 12; __VA_ARGS__; } break; \
+    case 16: { constexpr int kC = 16; __VA_ARGS__; } break; \
+    default: return DVGO_EINVAL;                         \
+  }

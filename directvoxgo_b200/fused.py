@@ -20,6 +20,8 @@ rgbnet modes
              in-TMEM weight-gradient accumulation; no host sync   [fused_mlp.cu]
 """
 
+import os
+
 import torch
 
 from . import adam_upd_cuda, ext
@@ -50,10 +52,13 @@ class _Workspace:
         self.t_min = torch.empty(n_rays, **f32)
         self.n_steps = torch.empty(n_rays, **i32)
         self.ray_off = torch.empty(n_rays + 1, **i32)
-        self.slot_alpha = torch.empty(cap, **f32)
-        self.slot_T = torch.empty(cap, **f32)
-        self.slot_expd = torch.empty(cap, **f32)
-        self.slot_code = torch.empty(cap, **i32)
+        # per-slot record of the forward march, read by march_bwd only: a rendering workspace passes empty tensors and
+        # march_fwd skips those 16 B / sample of stores (and 16 B x cap of memory)
+        slots = cap if train else 0
+        self.slot_alpha = torch.empty(slots, **f32)
+        self.slot_T = torch.empty(slots, **f32)
+        self.slot_expd = torch.empty(slots, **f32)
+        self.slot_code = torch.empty(slots, **i32)
         self.feat = torch.empty(cap, C, **f32)
         self.s_ray = torch.empty(cap, **i32)
         self.s_slot = torch.empty(cap, **i32)
@@ -114,6 +119,12 @@ class _FusedBase:
             raise ImportError("tensor-core rgbnet kernels are not built")
         self.mlp_mode = mlp
         self.split_k0 = True
+        # tensor-core rgbnet: False (default) = k0_gather_tiles -> X~ tiles in HBM -> mlp_fwd (bulk copies); True = the k0
+        # gather inside the forward kernel (mlp_fwd_gather: four producer warps per CTA fill the shared-memory tile).
+        # Measured on B200 the fused form is SLOWER (dense 800x800 render 41.5 vs 28.6 ms; training forward 0.65 vs
+        # 0.33 ms): the gather is L1-wavefront bound and needs ~24 resident warps per SM to keep enough loads in flight,
+        # the forward kernel's register budget leaves room for 8.  Kept as an opt-in experiment.
+        self.fuse_gather = os.environ.get("DVGO_FUSE_GATHER", "0") == "1"
         if model.rgbnet is not None and not getattr(model, "rgbnet_direct", True):
             if mlp == "tc":
                 raise NotImplementedError("tc rgbnet implements rgbnet_direct=True (the configs' default)")
@@ -184,13 +195,24 @@ class _FusedBase:
         ext.march_fwd(self.scene, rays_o, rays_d, self.density, None if (self.split_k0 or pe is not None) else self.k0, ws.t_min,
                       ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T, ws.slot_expd, ws.slot_code, ws.feat, ws.s_ray,
                       ws.s_slot, ws.s_weight, ws.alphainv_last, ws.counters, ws.s_pos)
-        if pe is not None:
+        if pe is not None and self.fuse_gather:
+            pass      # the gather happens inside _rgb_tc (mlp_fwd_gather)
+        elif pe is not None:
             ext.k0_gather_tiles(self.scene, rays_o, rays_d, self.k0, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot,
                                 ws.counters, ws.s_pos, pe[1], pe[0].shape[1],
                                 ws.tiles(self.C, pe[0].shape[1], hasattr(ws, "d_feat")))
         elif self.split_k0:
             ext.k0_gather(self.scene, rays_o, rays_d, self.k0, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot,
                           ws.counters, ws.feat)
+
+    def _rgb_tc(self, ws, pe, train):
+        """Tensor-core rgbnet forward over the survivor stream -> ws.rgb (and, when training, the X~ tiles in ws.xt)."""
+        pe_stride = pe[0].shape[1]
+        if self.fuse_gather:
+            self._tc.forward_gather(self.scene, self.k0, ws.s_pos, pe[1], self.C, pe_stride, ws.counters, ws.cap, ws.rgb,
+                                    ws.tiles(self.C, pe_stride, True) if train else None)
+        else:
+            self._tc.forward_tiles(ws.xt, self.C, pe_stride, ws.counters, ws.cap, ws.rgb)
 
     def _rgb_torch(self, ws, viewdirs, m4, grad):
         """rgbnet through torch/cuBLAS fp32 on the first m4 survivors; returns (rgb, feat leaf)."""
@@ -249,7 +271,7 @@ class FusedRenderer(_FusedBase):
         if self.model.rgbnet is None:
             ext.rgb_direct(ws.feat, ws.counters, ws.rgb)
         elif tc:
-            self._tc.forward_tiles(ws.xt, self.C, pe[0].shape[1], ws.counters, ws.cap, ws.rgb)
+            self._rgb_tc(ws, pe, False)
         else:
             m4 = int(ws.counters[0].item())
             if m4:
@@ -531,7 +553,7 @@ class FusedTrainer(_FusedBase):
             after_rgb()
             ext.rgb_direct_bwd(ws.rgb, ws.d_rgb, ws.counters, ws.d_feat)
         elif tc:
-            self._tc.forward_tiles(ws.xt, self.C, pe[0].shape[1], ws.counters, ws.cap, ws.rgb)
+            self._rgb_tc(ws, pe, True)
             self._mark("mlp_fwd")
             after_rgb()
             self._mark("loss")

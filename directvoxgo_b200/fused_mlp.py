@@ -99,6 +99,12 @@ class TensorCoreMLP:
         wp = self.pack(C, pe_stride)
         ext.mlp_fwd_tiles(xt, C, self.d_in - C, pe_stride, counters, cap, wp, rgb)
 
+    def forward_gather(self, scene, k0_cl, s_pos, pe16, C, pe_stride, counters, cap, rgb, xt=None):
+        """k0 gather + forward in one kernel (mlp_fwd_gather_kernel): the X~ tiles are built in shared memory by
+        producer warps; xt (training) receives a copy of every tile for backward_tiles()."""
+        wp = self.pack(C, pe_stride)
+        ext.mlp_fwd_gather(scene, k0_cl, s_pos, pe16, self.d_in - C, pe_stride, counters, cap, wp, rgb, xt)
+
     def backward_tiles(self, xt, dzt, C, pe_stride, counters, cap, d_feat, n_global):
         ext.zero_(self.grad_flat)
         wp = self._wpack if getattr(self, "_wpack_key", None) == (C, pe_stride) else self.pack(C, pe_stride)

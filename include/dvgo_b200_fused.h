@@ -80,7 +80,8 @@ int dvgo_fused_ray_setup(const float* rays_o, const float* rays_d, const dvgo_sc
 /* march_fwd.  Slot arrays [slot_cap], survivor arrays [surv_cap] (feat [surv_cap, C]); per ray
  * alphainv_last [N]; counters[0] = number of survivors M4 (must be zeroed by the caller, e.g. with
  * dvgo_fused_zero), counters[1] = overflow flag (set if a capacity was too small).
- * want_k0 = 0 skips the k0 gather (render of alpha only). */
+ * k0_cl == NULL skips the k0 gather (k0_gather / k0_gather_tiles follow).  The four slot arrays are the record
+ * march_bwd reads; pass all four as NULL for a forward-only (rendering) call: nothing is written per slot. */
 int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, const dvgo_scene_t* scene,
                          const float* density, const float* k0_cl, int n_rays, const float* t_min,
                          const int32_t* n_steps, const int32_t* ray_off, int64_t slot_cap,
@@ -232,6 +233,15 @@ int dvgo_mlp_pack_dz(const float* rgb, const float* d_rgb, float grad_scale,
                      const int32_t* counters, int64_t surv_cap, void* dzt, dvgo_stream_t stream);
 int dvgo_mlp_fwd(const void* xt, int C, int P, int pe_stride, int32_t* counters, int64_t surv_cap, const void* wpack,
                  float* rgb, dvgo_stream_t stream);
+/* k0 gather + rgbnet forward in ONE kernel: four producer warps per CTA build each X~ tile (trilinear k0 features of
+ * lib/dvgo.py:509 + the ray's embedding row) straight into the shared-memory buffer the layer-1 MMA reads, in the
+ * shadow of the tensor-core chain of the previous tiles (replaces dvgo_fused_k0_gather_tiles + dvgo_mlp_fwd, i.e.
+ * F.grid_sample at lib/dvgo.py:321 + rgbnet at :536-539).  s_pos [surv_cap,4]: march_fwd's per-survivor record.
+ * xt_out: NULL (rendering: the tiles never leave shared memory) or the X~ tile buffer of dvgo_mlp_xtile_bytes bytes
+ * (training: written by one bulk copy per tile, covering whole tile pairs, for dvgo_mlp_bwd). */
+int dvgo_mlp_fwd_gather(const dvgo_scene_t* scene, const float* k0_cl, const float* s_pos, const void* pe_rows16,
+                        int P, int pe_stride, int32_t* counters, int64_t surv_cap, const void* wpack, float* rgb,
+                        void* xt_out, dvgo_stream_t stream);
 /* Same as dvgo_mlp_fwd; if `timeline` is non-NULL, CTA 0 records clock64() at every phase boundary of its
  * first tiles into timeline[0..63] (thread 0) and timeline[64..127] (thread 255) -- kernel-author tooling. */
 int dvgo_mlp_fwd_timed(const void* xt, int C, int P, int pe_stride, int32_t* counters, int64_t surv_cap,

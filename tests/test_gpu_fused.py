@@ -14,11 +14,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _fine_model(grid, seed=1, dens_scale=3.0, mask_p=0.3):
+def _fine_model(grid, seed=1, dens_scale=3.0, mask_p=0.3, **over):
     from directvoxgo_b200 import synthetic as syn
     from directvoxgo_b200.dvgo import DirectVoxGO
     lo, hi = syn.fine_bbox()
     kw = dict(syn.FINE_MODEL, num_voxels=grid ** 3, num_voxels_base=grid ** 3)
+    kw.update(over)
     torch.manual_seed(0)
     m = DirectVoxGO(lo, hi, **kw)
     syn.randomize_grids_(m, seed)
@@ -272,8 +273,12 @@ def test_fused_full_size_invariants():
     n_steps = ws.n_steps[:8192].float()
     assert torch.all((wsum + out["alphainv_last"] - 1).abs() < 1e-4 * n_steps + 1e-4)
     assert float(out["rgb_marched"].min()) >= 0 and float(out["rgb_marched"].max()) <= 1 + 1e-5
-    codes = ws.slot_code[: int(ws.ray_off[8192])]
-    assert int((codes >= 0).sum()) == m4 and int(codes.max()) == m4 - 1
+    # the per-slot record only exists in a training workspace (a rendering call keeps nothing for march_bwd)
+    assert ws.slot_code.numel() == 0
+    wt = fr._workspace(8192, True)
+    fr._march(wt, ro, rd)
+    codes = wt.slot_code[: int(wt.ray_off[8192])]
+    assert int(wt.counters[0]) == m4 and int((codes >= 0).sum()) == m4 and int(codes.max()) == m4 - 1
     np.testing.assert_allclose(to_np(out["rgb_marched"]), to_np(ref["rgb_marched"]), rtol=0, atol=2e-3)
 
 
@@ -363,6 +368,7 @@ def test_survivor_tile_producers_match_pack_kernels(rgbnet_dim, n_rays):
     rk = dict(syn.RENDER_KWARGS)
     ro, rd, vd, _ = syn.random_training_rays(n_rays, n_views=20, seed=5, device=DEV)
     fr = FusedRenderer(m, rk, mlp="tc")
+    fr.fuse_gather = False          # this test checks the stand-alone tile producer (k0_gather_tiles)
     ws = fr._workspace(n_rays, False)
     pe, pe16 = fr._tc_embed(vd)
     C, ps = rgbnet_dim, pe.shape[1]
@@ -426,3 +432,45 @@ def test_survivor_tile_producers_match_pack_kernels(rgbnet_dim, n_rays):
         off = (p // 128) * 2048 + ((p % 128) // 8) * 128 + (p % 8) * 8
         np.testing.assert_array_equal(t[off:off + 3], z[p])
         assert np.all(t[off + 3:off + 8] == 0) and np.all(t[off + 64:off + 72] == 0)
+
+
+@pytest.mark.parametrize("C", [12, 9, 4])
+def test_gather_fused_into_rgbnet_forward_matches_two_kernel_path(C):
+    """mlp_fwd_gather_kernel (producer warps build the X~ tile in shared memory) against k0_gather_tiles + mlp_fwd on
+    the SAME survivor stream (one march; the stream order differs from run to run): byte-identical tiles over the tile
+    pairs the backward kernel reads, hence bit-identical rgb, in the rendering form (no tiles out) and the training
+    form (tiles copied out); and the rendered image agrees with the two-kernel renderer (lib/dvgo.py:509, :536-539)."""
+    from directvoxgo_b200 import ext, synthetic as syn
+    from directvoxgo_b200.fused import FusedRenderer
+    m = _fine_model(48, dens_scale=1.0, mask_p=0.3, rgbnet_dim=C).to(DEV)
+    ro, rd, vd, _ = syn.random_training_rays(3000, n_views=20, seed=3, device=DEV)
+    rk = dict(syn.RENDER_KWARGS)
+    fr = FusedRenderer(m, rk)
+    assert fr.mlp_mode == "tc"
+    imgs = []
+    for fuse in (True, False):
+        fr.fuse_gather = fuse
+        imgs.append(fr.render(ro, rd, vd)["rgb_marched"].clone())
+    assert int(fr._workspace(3000, False).counters[1]) == 0
+    np.testing.assert_allclose(to_np(imgs[0]), to_np(imgs[1]), rtol=0, atol=1e-5)
+
+    pe = fr._tc_embed(vd)
+    ws = fr._workspace(3000, True)
+    fr.fuse_gather = True
+    fr._march(ws, ro, rd, pe)                      # march only: the gather is left to the forward kernel
+    m4 = int(ws.counters[0])
+    assert m4 > 1000
+    pe_stride = pe[0].shape[1]
+    xt_two = torch.zeros_like(ws.tiles(C, pe_stride, True))
+    ext.k0_gather_tiles(fr.scene, ro, rd, fr.k0, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot, ws.counters, ws.s_pos,
+                        pe[1], pe_stride, xt_two)
+    rgb_two = torch.zeros_like(ws.rgb)
+    fr._tc.forward_tiles(xt_two, C, pe_stride, ws.counters, ws.cap, rgb_two)
+    xt_fused = torch.full_like(xt_two, 0xAB)       # every byte of the pairs in use must be written by the kernel
+    rgb_train, rgb_render = torch.zeros_like(ws.rgb), torch.zeros_like(ws.rgb)
+    fr._tc.forward_gather(fr.scene, fr.k0, ws.s_pos, pe[1], C, pe_stride, ws.counters, ws.cap, rgb_train, xt_fused)
+    fr._tc.forward_gather(fr.scene, fr.k0, ws.s_pos, pe[1], C, pe_stride, ws.counters, ws.cap, rgb_render, None)
+    tile_bytes = xt_two.numel() // ((ws.cap + 127) // 128 + 1)
+    used = (m4 + 255) // 256 * 2 * tile_bytes
+    assert torch.equal(xt_fused[:used], xt_two[:used])
+    assert torch.equal(rgb_train[:m4], rgb_two[:m4]) and torch.equal(rgb_render[:m4], rgb_two[:m4])

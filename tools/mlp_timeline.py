@@ -28,7 +28,7 @@ def show(who, t, names, first_tile=2, n_show=3):
 for _ in range(2):
     tl = ext.mlp_fwd_timeline(feat, s_ray, pe_pad, 27, counters, tc.params, 128, rgb)
 torch.cuda.synchronize()
-fwd = ["wait L1 + refill X", "e1->TMEM+sync", "issue L2", "wait L2", "e2->TMEM+sync", "issue L3, L1(next) + wait L3", "e3 sigmoid+store", "loop"]
+fwd = ["wait L1 + refill X", "e1->TMEM+sync", "issue L2", "rgb epilogue of the previous tile", "wait L2", "e2->TMEM+sync", "issue L3, L1(next)", "loop"]
 t0 = tl[0:64].cpu().tolist()
 print("forward prologue (entry -> first loop top): %d cycles" % (t0[1] - t0[0]))
 show("forward, thread 0", t0[1:], fwd)
