@@ -14,6 +14,8 @@
 //
 // Arithmetic follows the reference expression trees exactly where integer / boolean results depend
 // on it (common.cuh); see include/dvgo_b200_fused.h for the data layout.
+#include <climits>
+
 #include "fused_scene.cuh"
 #include "k0_tiles.cuh"
 #include "tc_common.cuh"
@@ -433,6 +435,14 @@ __global__ void __launch_bounds__(256, 3) k0_gather_tiles_kernel(
   }
 }
 
+// Warp-aggregated reductions.  A thread owns (survivor p, 16-byte channel group q); lane + G is survivor p + 1, the
+// next sample of the same ray most of the time, and at half a voxel per step it lies in the SAME base cell about 40 %
+// of the time -- all eight of its reductions then go to the same eight addresses.  Such runs of equal base cell are
+// merged in registers before anything leaves the SM: the issuing lane pulls its (up to two) predecessors' inputs
+// (voxel coordinates + gradient group: 7 shuffles each), recomputes their corner weights and adds the products, and
+// the predecessors issue nothing.  Runs are cut into triples from their start (a run is at most 4 samples long at this
+// step size); lanes of different warps never merge.  The kernel is bound by the L2 reduction rate (one 32-byte sector
+// per slice per clock: profiles/r01_sweep_grid.txt), so fewer red.global.add.v4.f32 is what buys time.
 template <int C>
 __global__ void __launch_bounds__(256) k0_scatter_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
@@ -446,40 +456,92 @@ __global__ void __launch_bounds__(256) k0_scatter_kernel(
   int64_t n = counters[0];
   if (n > surv_cap) n = surv_cap;
   const int64_t total = n * G;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i - lane < total;   // warp-uniform
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t p = i / G;
-    const int q = static_cast<int>(i - p * G);
-    Corner8 cn;
-    if (s_pos) {         // march_fwd's per-survivor record (continuous voxel coordinates)
-      const float4 rec = __ldg(s_pos + p);
-      cn = corner8_idx(sc, rec.x, rec.y, rec.z);
-    } else {
-      const int r = s_ray[p];
-      const int step = s_slot[p] - ray_off[r];
-      const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
-      float px, py, pz;
-      sample_point(sc, g, step, px, py, pz);
-      cn = corner8(sc, px, py, pz);
+    const bool valid = i < total;
+    const int64_t p = valid ? i / G : 0;
+    const int q = static_cast<int>(i - (i / G) * G);
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (valid) {
+      if (s_pos) {         // march_fwd's per-survivor record (continuous voxel coordinates)
+        const float4 rec = __ldg(s_pos + p);
+        fx = rec.x; fy = rec.y; fz = rec.z;
+      } else {
+        const int r = s_ray[p];
+        const int step = s_slot[p] - ray_off[r];
+        const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
+        float px, py, pz;
+        sample_point(sc, g, step, px, py, pz);
+        voxel_coords(sc, px, py, pz, fx, fy, fz);
+      }
     }
+    Corner8 cn = corner8_idx(sc, fx, fy, fz);
+    if (!valid) cn.valid = 0u;
     float d[W];
-    const float* __restrict__ src = d_feat + p * C + q * W;
     if (C % 4 == 0) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) f = __ldg(reinterpret_cast<const float4*>(d_feat + p * C + q * W));
       d[0] = f.x; d[1] = f.y; d[2 % W] = f.z; d[3 % W] = f.w;
-    } else {
+      // ---- runs of equal base cell among the lanes of this channel group ----
+      constexpr unsigned kFull = 0xffffffffu;
+      const int base = valid ? cn.base : INT_MIN;       // INT_MIN never equals a real (even padded) base index
+      const int pb = __shfl_up_sync(kFull, base, G);
+      const int nb = __shfl_down_sync(kFull, base, G);
+      const bool head = !(lane >= G && pb == base);
+      const bool last = !(lane + G < 32 && nb == base);
+      const unsigned heads = __ballot_sync(kFull, head);
+      unsigned mine = 0u;                                // lanes of my channel group at or below me
+#pragma unroll
+      for (int l = 0; l < 32; ++l)
+        if (l % G == 0) mine |= 1u << l;
+      mine = (mine << (lane % G)) & (0xffffffffu >> (31 - lane));
+      const int head_lane = 31 - __clz(heads & mine);   // my own lane if I am a head
+      const int pos = (lane - head_lane) / G;
+      const int npull = pos % 3;                         // predecessors an issuing lane absorbs
+      const bool issue = valid && (last || npull == 2);
+      float acc[8][4];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float wk = cn.w(k);
+        acc[k][0] = fmul(wk, d[0]); acc[k][1] = fmul(wk, d[1]); acc[k][2] = fmul(wk, d[2 % W]); acc[k][3] = fmul(wk, d[3 % W]);
+      }
+#pragma unroll
+      for (int back = 1; back <= 2; ++back) {            // every lane shuffles; only issuing lanes with enough run use it
+        const float qx = __shfl_up_sync(kFull, fx, back * G), qy = __shfl_up_sync(kFull, fy, back * G),
+                    qz = __shfl_up_sync(kFull, fz, back * G);
+        float e[4];
+        e[0] = __shfl_up_sync(kFull, d[0], back * G); e[1] = __shfl_up_sync(kFull, d[1], back * G);
+        e[2] = __shfl_up_sync(kFull, d[2 % W], back * G); e[3] = __shfl_up_sync(kFull, d[3 % W], back * G);
+        if (issue && npull >= back) {
+          Corner8 pc = cn;                               // same base cell, same validity: only the weights differ
+          const Tri t = tri_from_index(qx, qy, qz);
+          pc.wx0 = t.wx0; pc.wx1 = t.wx1; pc.wy0 = t.wy0; pc.wy1 = t.wy1; pc.wz0 = t.wz0; pc.wz1 = t.wz1;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float wk = pc.w(k);
+            acc[k][0] = fma_(wk, e[0], acc[k][0]); acc[k][1] = fma_(wk, e[1], acc[k][1]);
+            acc[k][2] = fma_(wk, e[2], acc[k][2]); acc[k][3] = fma_(wk, e[3], acc[k][3]);
+          }
+        }
+      }
+      if (issue) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (!cn.ok(k)) continue;
+          float* __restrict__ dst = grad_k0 + static_cast<int64_t>(cn.off(k)) * C + q * W;
+          atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]));
+        }
+      }
+    } else if (valid) {
+      const float* __restrict__ src = d_feat + p * C + q * W;
 #pragma unroll
       for (int c = 0; c < W; ++c) d[c] = __ldg(src + c);
-    }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (!cn.ok(k)) continue;
-      float* __restrict__ dst = grad_k0 + static_cast<int64_t>(cn.off(k)) * C + q * W;
-      const float wk = cn.w(k);
-      if (C % 4 == 0) {
-        atomicAdd(reinterpret_cast<float4*>(dst),
-                  make_float4(fmul(wk, d[0]), fmul(wk, d[1]), fmul(wk, d[2 % W]), fmul(wk, d[3 % W])));
-      } else {
+      for (int k = 0; k < 8; ++k) {
+        if (!cn.ok(k)) continue;
+        float* __restrict__ dst = grad_k0 + static_cast<int64_t>(cn.off(k)) * C + q * W;
+        const float wk = cn.w(k);
 #pragma unroll
         for (int c = 0; c < W; ++c) atomicAdd(dst + c, fmul(wk, d[c]));
       }
