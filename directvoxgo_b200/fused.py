@@ -72,6 +72,11 @@ class _Workspace:
         self.loss_acc = self.zblock[2:4]
         self.rgb_acc = self.zblock[4:4 + 3 * n_rays].view(n_rays, 3)
         self.depth_acc = self.zblock[4 + 3 * n_rays:4 + 4 * n_rays]
+        # device-side running statistics of the calls made on this workspace, folded in by step_begin at the START of
+        # the next call (no host sync): [sum survivors, calls, status bits (1 = a capacity was too small, 2 = non-finite
+        # rgbnet value), max survivors of a call]; `pending`: the last call's counters are not folded in yet
+        self.stats = torch.zeros(4, dtype=torch.int64, device=device)
+        self.pending = False
         if train:
             self.G = torch.empty(n_rays, 3, **f32)
             self.g_last = torch.empty(n_rays, **f32)
@@ -131,10 +136,6 @@ class _FusedBase:
         self.density = model.density.detach().reshape(self.X, self.Y, self.Z).contiguous().clone()
         self.k0 = ext.ncdhw_to_cl(model.k0.detach().contiguous())
         self._ws = {}
-        # device-side running statistics, folded in by step_begin (no host sync): [sum survivors, calls,
-        # status bits (1 = a capacity was too small, 2 = non-finite rgbnet value), max survivors of a call]
-        self.stats = torch.zeros(4, dtype=torch.int64, device=self.device)
-        self._last_ws = None
 
     def _viewfreq(self):
         vf = getattr(self.model, "viewfreq", None)     # DirectMPIGO with viewbase_pe=0 has an empty table
@@ -146,24 +147,28 @@ class _FusedBase:
         return (len(lin) == 3 and lin[0].out_features <= 128 and lin[1].out_features == lin[0].out_features and
                 getattr(model, "rgbnet_direct", True) and getattr(model, "posbase_pe", 0) == 0)
 
-    def _workspace(self, n_rays, train):
-        key = (n_rays, train)
+    def _workspace(self, n_rays, train, slot=0):
+        """slot: independent workspaces of the same shape (render_view pipelines its chunks over two streams)."""
+        key = (n_rays, train, slot)
         if key not in self._ws:
             self._ws[key] = _Workspace(self.scene, n_rays, self.C, self.device, train)
         return self._ws[key]
 
     def stats_snapshot(self, reset=False):
-        """(survivors summed over the completed calls, number of calls, status bits, max survivors) -- one host read.
-        Includes the call whose counters have not been folded in yet.  Raises on a non-zero status."""
-        st = [int(v) for v in self.stats.tolist()]
-        if self._last_ws is not None:
-            c = [int(v) for v in self._last_ws.counters.tolist()]
-            st = [st[0] + c[0], st[1] + 1, st[2] | c[1], max(st[3], c[0])]
+        """(survivors summed over the completed calls, number of calls, status bits, max survivors) over all workspaces
+        -- one host read per workspace.  Includes calls whose counters have not been folded in yet.  Raises on a
+        non-zero status."""
+        st = [0, 0, 0, 0]
+        for ws in self._ws.values():
+            w = [int(v) for v in ws.stats.tolist()]
+            if ws.pending:
+                c = [int(v) for v in ws.counters.tolist()]
+                w = [w[0] + c[0], w[1] + 1, w[2] | c[1], max(w[3], c[0])]
+            st = [st[0] + w[0], st[1] + w[1], st[2] | w[2], max(st[3], w[3])]
             if reset:
-                self._last_ws.counters.zero_()
-                self._last_ws = None
-        if reset:
-            self.stats.zero_()
+                ws.counters.zero_()
+                ws.stats.zero_()
+                ws.pending = False
         self._raise_on_status(st[2])
         return tuple(st)
 
@@ -183,13 +188,8 @@ class _FusedBase:
     def _march(self, ws, rays_o, rays_d, pe=None):
         """pe (tensor-core rgbnet): (padded view-embedding table, its fp16 row form) as TensorCoreMLP.embed(.., C) returns
         them; the k0 gather then writes the rgbnet's X~ tiles (ws.xt) instead of the fp32 feature stream ws.feat."""
-        ext.step_begin(ws.zblock, self.stats if self._last_ws is ws else None)
-        if self._last_ws is not None and self._last_ws is not ws:   # switching workspaces: fold the other one in now
-            c = self._last_ws.counters
-            self.stats[0] += c[0]; self.stats[1] += 1; self.stats[2] |= c[1].long()
-            self.stats[3] = torch.maximum(self.stats[3], c[0].long())
-            c.zero_()
-        self._last_ws = ws
+        ext.step_begin(ws.zblock, ws.stats if ws.pending else None)   # folds the previous call's counters, then zeroes
+        ws.pending = True
         ext.ray_setup(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off)
         # density march (scan-bound, per ray) then the k0 gather over the compacted stream (fully parallel)
         ext.march_fwd(self.scene, rays_o, rays_d, self.density, None if (self.split_k0 or pe is not None) else self.k0, ws.t_min,
@@ -205,14 +205,15 @@ class _FusedBase:
             ext.k0_gather(self.scene, rays_o, rays_d, self.k0, ws.t_min, ws.ray_off, ws.s_ray, ws.s_slot,
                           ws.counters, ws.feat)
 
-    def _rgb_tc(self, ws, pe, train):
-        """Tensor-core rgbnet forward over the survivor stream -> ws.rgb (and, when training, the X~ tiles in ws.xt)."""
+    def _rgb_tc(self, ws, pe, train, wp=None):
+        """Tensor-core rgbnet forward over the survivor stream -> ws.rgb (and, when training, the X~ tiles in ws.xt).
+        wp: weight tiles already packed for this (C, pe_stride) (render_view packs once per view)."""
         pe_stride = pe[0].shape[1]
         if self.fuse_gather:
             self._tc.forward_gather(self.scene, self.k0, ws.s_pos, pe[1], self.C, pe_stride, ws.counters, ws.cap, ws.rgb,
-                                    ws.tiles(self.C, pe_stride, True) if train else None)
+                                    ws.tiles(self.C, pe_stride, True) if train else None, wp)
         else:
-            self._tc.forward_tiles(ws.xt, self.C, pe_stride, ws.counters, ws.cap, ws.rgb)
+            self._tc.forward_tiles(ws.xt, self.C, pe_stride, ws.counters, ws.cap, ws.rgb, wp)
 
     def _rgb_torch(self, ws, viewdirs, m4, grad):
         """rgbnet through torch/cuBLAS fp32 on the first m4 survivors; returns (rgb, feat leaf)."""
@@ -262,16 +263,18 @@ class FusedRenderer(_FusedBase):
     (the keys run.py:89,98-99 keeps)."""
 
     @torch.no_grad()
-    def render(self, rays_o, rays_d, viewdirs, render_depth=True):
+    def render(self, rays_o, rays_d, viewdirs, render_depth=True, slot=0, out=None):
+        """out: optional (rgb [n,3], alphainv_last [n], depth [n] or None) views to write the results into (render_view
+        hands in slices of the frame buffers); default: fresh tensors."""
         n = rays_o.shape[0]
-        ws = self._workspace(n, False)
+        ws = self._workspace(n, False, slot)
         tc = self.model.rgbnet is not None and self.mlp_mode == "tc"
-        pe = self._tc_embed(viewdirs) if tc else None
+        pe = self._tc_embed(viewdirs, slot) if tc else None
         self._march(ws, rays_o.contiguous(), rays_d.contiguous(), pe)
         if self.model.rgbnet is None:
             ext.rgb_direct(ws.feat, ws.counters, ws.rgb)
         elif tc:
-            self._rgb_tc(ws, pe, False)
+            self._rgb_tc(ws, pe, False, getattr(self, "_view_wp", None))
         else:
             m4 = int(ws.counters[0].item())
             if m4:
@@ -282,41 +285,68 @@ class FusedRenderer(_FusedBase):
         ext.ray_finish(ws.rgb_acc, ws.alphainv_last, None, float(self.rk["bg"]), n, n, 1.0, 0.0, None, None, None)
         if getattr(self, "check_every_call", False):
             self.check_status()
-        out = {"rgb_marched": ws.rgb_acc.clone(), "alphainv_last": ws.alphainv_last.clone()}
+        if out is not None:
+            out[0].copy_(ws.rgb_acc)
+            out[1].copy_(ws.alphainv_last)
+            if render_depth:
+                out[2].copy_(ws.depth_acc)
+            return None
+        res = {"rgb_marched": ws.rgb_acc.clone(), "alphainv_last": ws.alphainv_last.clone()}
         if render_depth:
-            out["depth"] = ws.depth_acc.clone()
-        return out
+            res["depth"] = ws.depth_acc.clone()
+        return res
 
     @torch.no_grad()
     def render_view(self, H, W, K, c2w, ndc=False, inverse_y=False, flip_x=False, flip_y=False, chunk=65536,
-                    render_depth=True):
+                    render_depth=True, streams=2):
         """One full view (run.py:82-99): the rays of each chunk of pixels are generated on the device straight
         into a reusable [chunk,3] workspace (`dvgo_rays_of_view`, lib/ray_utils.py:80-85) instead of three
-        [H*W,3] tensors per view, then rendered.  Returns [H,W,3] rgb, [H,W] depth / alphainv_last."""
+        [H*W,3] tensors per view, then rendered.  Returns [H,W,3] rgb, [H,W] depth / alphainv_last.
+
+        streams = 2: consecutive chunks run on two CUDA streams with a workspace each, so the kernels of chunk i + 1
+        (march: L1 / latency bound; k0 gather: L1-wavefront bound) fill the SM resources the tensor-core rgbnet kernel
+        of chunk i leaves idle (its two 256-thread CTAs hold 41 K of the 64 K registers and little L1 bandwidth)
+        instead of queueing behind it; streams = 1 is the serial order."""
         from .ray_utils import make_view
         view = make_view(H, W, K, c2w, ndc, inverse_y, flip_x, flip_y)
         n = H * W
         chunk = min(chunk, n)
-        if getattr(self, "_view_rays", None) is None or self._view_rays[0].shape[0] != chunk:
-            self._view_rays = [torch.empty(chunk, 3, device=self.device) for _ in range(3)]
-        ro, rd, vd = self._view_rays
+        n_slots = max(1, min(int(streams), (n + chunk - 1) // chunk))
+        if getattr(self, "_view_rays", None) is None or self._view_rays[0][0].shape[0] != chunk or \
+                len(self._view_rays) < n_slots:
+            self._view_rays = [[torch.empty(chunk, 3, device=self.device) for _ in range(3)] for _ in range(n_slots)]
         rgb = torch.empty(n, 3, device=self.device)
         last = torch.empty(n, device=self.device)
         depth = torch.empty(n, device=self.device) if render_depth else None
-        for p0 in range(0, n, chunk):
+        cur = torch.cuda.current_stream(self.device)
+        if self.model.rgbnet is not None and self.mlp_mode == "tc":
+            # the weights do not change during a view: pack the fp16 tiles once, before the streams fork
+            self._tc_embed(torch.zeros(1, 3, device=self.device))           # creates self._tc on first use
+            P = 3 + 6 * int(self._viewfreq().numel())
+            self._view_wp = self._tc.pack(self.C, (P + 1 + 3) // 4 * 4)
+        if n_slots > 1:
+            if len(getattr(self, "_side_streams", [])) < n_slots:
+                self._side_streams = [torch.cuda.Stream(self.device) for _ in range(n_slots)]
+            for st in self._side_streams[:n_slots]:
+                st.wait_stream(cur)
+        for ci, p0 in enumerate(range(0, n, chunk)):
             m = min(chunk, n - p0)
-            ext.rays_of_view(view, p0, m, ro, rd, vd)
-            out = self.render(ro[:m], rd[:m], vd[:m], render_depth)
-            rgb[p0:p0 + m] = out["rgb_marched"]
-            last[p0:p0 + m] = out["alphainv_last"]
-            if render_depth:
-                depth[p0:p0 + m] = out["depth"]
+            slot = ci % n_slots
+            ro, rd, vd = self._view_rays[slot]
+            with torch.cuda.stream(self._side_streams[slot] if n_slots > 1 else cur):
+                ext.rays_of_view(view, p0, m, ro, rd, vd)
+                self.render(ro[:m], rd[:m], vd[:m], render_depth, slot,
+                            (rgb[p0:p0 + m], last[p0:p0 + m], depth[p0:p0 + m] if render_depth else None))
+        if n_slots > 1:
+            for st in self._side_streams[:n_slots]:
+                cur.wait_stream(st)
+        self._view_wp = None
         res = {"rgb_marched": rgb.reshape(H, W, 3), "alphainv_last": last.reshape(H, W)}
         if render_depth:
             res["depth"] = depth.reshape(H, W)
         return res
 
-    def _tc_embed(self, viewdirs):
+    def _tc_embed(self, viewdirs, slot=0):
         from .fused_mlp import TensorCoreMLP
         if not hasattr(self, "_tc"):
             self._tc = TensorCoreMLP(self.model.rgbnet, self.device)

@@ -95,14 +95,17 @@ class TensorCoreMLP:
                     self.grad_scale(n_global), d_feat, self.grad_flat, wp)
 
     # the fused step's calls: survivor tiles written by their producers (k0_gather_tiles / sample_grad)
-    def forward_tiles(self, xt, C, pe_stride, counters, cap, rgb):
-        wp = self.pack(C, pe_stride)
+    def forward_tiles(self, xt, C, pe_stride, counters, cap, rgb, wp=None):
+        """wp: weight tiles packed earlier by pack() (a renderer packs once per view); default: pack now."""
+        if wp is None:
+            wp = self.pack(C, pe_stride)
         ext.mlp_fwd_tiles(xt, C, self.d_in - C, pe_stride, counters, cap, wp, rgb)
 
-    def forward_gather(self, scene, k0_cl, s_pos, pe16, C, pe_stride, counters, cap, rgb, xt=None):
+    def forward_gather(self, scene, k0_cl, s_pos, pe16, C, pe_stride, counters, cap, rgb, xt=None, wp=None):
         """k0 gather + forward in one kernel (mlp_fwd_gather_kernel): the X~ tiles are built in shared memory by
         producer warps; xt (training) receives a copy of every tile for backward_tiles()."""
-        wp = self.pack(C, pe_stride)
+        if wp is None:
+            wp = self.pack(C, pe_stride)
         ext.mlp_fwd_gather(scene, k0_cl, s_pos, pe16, self.d_in - C, pe_stride, counters, cap, wp, rgb, xt)
 
     def backward_tiles(self, xt, dzt, C, pe_stride, counters, cap, d_feat, n_global):
