@@ -48,6 +48,9 @@ class _Workspace:
         f32 = dict(dtype=torch.float32, device=device)
         i32 = dict(dtype=torch.int32, device=device)
         cap = n_rays * scene.max_steps()
+        if cap >= 2 ** 31:      # slot offsets (ray_off) and survivor indices are int32 on the device
+            raise ValueError("fused path: %d rays x %d steps per ray exceeds the int32 slot index range; render / train "
+                             "in smaller ray chunks, or check near / far / stepsize" % (n_rays, scene.max_steps()))
         self.n_rays, self.cap = n_rays, cap
         self.t_min = torch.empty(n_rays, **f32)
         self.n_steps = torch.empty(n_rays, **i32)
@@ -136,6 +139,7 @@ class _FusedBase:
         self.density = model.density.detach().reshape(self.X, self.Y, self.Z).contiguous().clone()
         self.k0 = ext.ncdhw_to_cl(model.k0.detach().contiguous())
         self._ws = {}
+        self._density_swept = False
 
     def _viewfreq(self):
         vf = getattr(self.model, "viewfreq", None)     # DirectMPIGO with viewbase_pe=0 has an empty table
@@ -568,6 +572,13 @@ class FusedTrainer(_FusedBase):
                 ext.march_bwd(self.scene, rays_o, rays_d, ws.t_min, ws.n_steps, ws.ray_off, ws.slot_alpha, ws.slot_T,
                               ws.slot_expd, ws.slot_code, ws.d_feat, ws.d_w, ws.alphainv_last, ws.g_last, self.g_density,
                               None)
+                if self.world_size == 1:
+                    # single GPU: the density gradient is final here, so its TV + Adam sweep (27 us at 160^3) follows on
+                    # the side stream, under the rgbnet backward / k0 scatter, instead of after them.  (Ray-sharded runs
+                    # exchange gradients first: their sweeps stay behind the barrier in _optimise.)
+                    tv_on, tv_dense = self._tv_now()
+                    self._density_swept = self._sweep_grid("density", 1, n_global, self.opt_step + 1, tv_on, tv_dense,
+                                                           False, 0, self.X) or self.lr["density"] <= 0
                 self._dens_done.record()
             return True
 
@@ -680,6 +691,43 @@ class FusedTrainer(_FusedBase):
         else:
             dist.all_reduce(self._bar, group=self.dist_group)
 
+    def _sweep_grid(self, name, C, n_global, opt_step, tv_on, tv_dense, peer, x0, x1):
+        """TV + (masked) Adam + gradient re-zero of one grid's x-slab [x0, x1) in one kernel; swaps the ping-pong
+        buffers when TV is on.  Returns False when the grid is frozen (lr <= 0)."""
+        cfg = self.cfg
+        lr = self.lr[name]
+        if lr <= 0:
+            return False
+        b1, b2 = self.betas
+        wt = float(cfg.get("weight_tv_" + name, 0.0))
+        tv = tv_on and wt > 0
+        if self.ndc:  # lib/dmpigo.py:147-157 anisotropic weights
+            wx = wy = wt / n_global * float(max(self.X, self.Y)) / 128
+            wz = wt / n_global * float(self.Z) / 128
+        else:
+            wx = wy = wz = wt / n_global * float(max(self.X, self.Y, self.Z)) / 128  # lib/dvgo.py:297-305, run.py:392
+        cur = getattr(self, name)
+        nxt = getattr(self, name + "_next") if tv else cur
+        per_lr = self.per_lr if (name == "density" and self.per_lr is not None) else None
+        masked = self.masked[name] and per_lr is None  # dispatch of lib/masked_adam.py:60-71
+        if peer:
+            out = name + "_next" if tv else name
+            ext.sweep_peer(cur, self._pp[out], self._pp["g_" + name], self._mc[out], self._mc["g_" + name], self.rank,
+                           getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
+                           per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, opt_step,
+                           b1, b2, lr, self.eps, x0, x1)
+        else:
+            ext.sweep(cur, nxt, getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
+                      per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, opt_step,
+                      b1, b2, lr, self.eps, x0, x1)
+        if tv:
+            setattr(self, name, nxt)
+            setattr(self, name + "_next", cur)
+            if peer:
+                for tab in (self._pp, self._mc):
+                    tab[name], tab[name + "_next"] = tab[name + "_next"], tab[name]
+        return True
+
     def _optimise(self, n_global):
         cfg = self.cfg
         peer = self.exchange == "peer"
@@ -703,41 +751,13 @@ class FusedTrainer(_FusedBase):
         self.opt_step += 1
         b1, b2 = self.betas
         tv_on, tv_dense = self._tv_now()
-        wmax = float(max(self.X, self.Y, self.Z))
-        if self.ndc:  # lib/dmpigo.py:147-157 anisotropic weights
-            wxy_s, wz_s = float(max(self.X, self.Y)) / 128, float(self.Z) / 128
         for name, C in (("density", 1), ("k0", self.C)):
-            lr = self.lr[name]
-            if lr <= 0:
+            if name == "density" and self._density_swept:
+                self._density_swept = False      # done on the side stream right behind march_bwd (step())
+                updated.append(name)
                 continue
-            wt = float(cfg.get("weight_tv_" + name, 0.0))
-            tv = tv_on and wt > 0
-            if self.ndc:
-                wx = wy = wt / n_global * wxy_s
-                wz = wt / n_global * wz_s
-            else:
-                wx = wy = wz = wt / n_global * wmax / 128  # lib/dvgo.py:297-305, run.py:392
-            cur = getattr(self, name)
-            nxt = getattr(self, name + "_next") if tv else cur
-            per_lr = self.per_lr if (name == "density" and self.per_lr is not None) else None
-            masked = self.masked[name] and per_lr is None  # dispatch of lib/masked_adam.py:60-71
-            if peer:
-                out = name + "_next" if tv else name
-                ext.sweep_peer(cur, self._pp[out], self._pp["g_" + name], self._mc[out], self._mc["g_" + name], self.rank,
-                               getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
-                               per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, self.opt_step,
-                               b1, b2, lr, self.eps, x0, x1)
-            else:
-                ext.sweep(cur, nxt, getattr(self, "g_" + name), getattr(self, "m_" + name), getattr(self, "v_" + name),
-                          per_lr, self.X, self.Y, self.Z, C, tv, tv_dense, wx, wy, wz, masked, self.opt_step,
-                          b1, b2, lr, self.eps, x0, x1)
-            if tv:
-                setattr(self, name, nxt)
-                setattr(self, name + "_next", cur)
-                if peer:
-                    for tab in (self._pp, self._mc):
-                        tab[name], tab[name + "_next"] = tab[name + "_next"], tab[name]
-            updated.append(name)
+            if self._sweep_grid(name, C, n_global, self.opt_step, tv_on, tv_dense, peer, x0, x1):
+                updated.append(name)
         rgbnet_done = False
         if flags and self.model.rgbnet is not None and self.lr["rgbnet"] > 0:
             # rgbnet Adam on the gradient summed over ranks, read from the peers' flat buffers inside the kernel
