@@ -126,7 +126,7 @@ __device__ __forceinline__ void gather_k0(const float* __restrict__ k0, const Co
 }
 
 template <int C>
-__global__ void __launch_bounds__(256, 3) march_fwd_kernel(
+__global__ void __launch_bounds__(256, 4) march_fwd_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
     const float* __restrict__ density, const float* __restrict__ k0, int n_rays,
     const float* __restrict__ t_min, const int32_t* __restrict__ n_steps,
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(256) k0_gather_kernel(
 // G = 3).  The fused step / renderer use mlp_fwd_gather_kernel (fused_mlp.cu) instead, which builds the same rows
 // straight into the shared-memory tile; this kernel serves callers that want the tiles in global memory.
 template <int C>
-__global__ void __launch_bounds__(256, 3) k0_gather_tiles_kernel(
+__global__ void __launch_bounds__(256, 4) k0_gather_tiles_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
     const float* __restrict__ k0, const float* __restrict__ t_min, const int32_t* __restrict__ ray_off,
     const int32_t* __restrict__ s_ray, const int32_t* __restrict__ s_slot,

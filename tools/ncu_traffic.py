@@ -12,7 +12,7 @@ import json
 import subprocess
 import sys
 
-STAGE_OF = {"march_fwd_kernel": "march_fwd", "k0_gather_kernel": "march_fwd", "mlp_fwd_kernel": "mlp_fwd",
+STAGE_OF = {"march_fwd_kernel": "march_fwd", "k0_gather_kernel": "march_fwd", "k0_gather_tiles_kernel": "march_fwd", "mlp_fwd_kernel": "mlp_fwd",
             "mlp_bwd_kernel": "mlp_bwd", "k0_scatter_kernel": "march_bwd", "march_bwd_kernel": "march_bwd",
             "sweep_kernel": "sweep"}
 COLS = {"gpu__time_duration.sum": "time_us", "dram__bytes_read.sum": "dram_rd", "dram__bytes_write.sum": "dram_wr",
@@ -22,7 +22,11 @@ COLS = {"gpu__time_duration.sum": "time_us", "dram__bytes_read.sum": "dram_rd", 
         "launch__registers_per_thread": "regs", "launch__grid_size": "grid", "launch__block_size": "block",
         "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
         "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
-        "lts__t_sector_hit_rate.pct": "l2_hit_pct", "smsp__inst_executed.sum": "warp_insts"}
+        "lts__t_sector_hit_rate.pct": "l2_hit_pct", "smsp__inst_executed.sum": "warp_insts",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed": "l1_lsu_wavefront_pct",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_lsu_wavefronts",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum": "smem_tc_wavefronts",
+        "sm__cycles_elapsed.max": "sm_cycles"}
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}
 
 
@@ -57,13 +61,15 @@ def main(rep, out_json, out_md):
                "kernels": stages, "per_kernel": per}, open(out_json, "w"), indent=1)
     with open(out_md, "w") as f:
         f.write("# ncu --set full, per-kernel averages (%s, commit %s)\n\n" % (rep, commit))
-        f.write("| kernel | launches | time us | dram rd MB | dram wr MB | dram % | sm % | tensor pipe % | issue active % | warps active % | L2 hit % | regs | grid x block |\n")
-        f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        f.write("| kernel | launches | time us | dram rd MB | dram wr MB | dram % | sm % | tensor pipe % | issue active % | warps active % | L2 hit % | regs | grid x block | L1 LSU wavefronts % | smem wavefronts / SM / cycle (LSU + tensor) |\n")
+        f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         for k, r in sorted(per.items(), key=lambda kv: -kv[1].get("time_us", 0)):
-            f.write("| `%s` | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %d | %d x %d |\n" % (
+            cyc = max(r.get("sm_cycles", 0), 1.0) * 148
+            f.write("| `%s` | %d | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %d | %d x %d | %.1f | %.2f + %.2f |\n" % (
                 k, r["launches"], r.get("time_us", 0), r.get("dram_rd", 0) / 1e6, r.get("dram_wr", 0) / 1e6, r.get("dram_pct", 0),
                 r.get("sm_pct", 0), r.get("tensor_pct", 0), r.get("issue_active_pct", 0), r.get("warps_active_pct", 0),
-                r.get("l2_hit_pct", 0), r.get("regs", 0), r.get("grid", 0), r.get("block", 0)))
+                r.get("l2_hit_pct", 0), r.get("regs", 0), r.get("grid", 0), r.get("block", 0),
+                r.get("l1_lsu_wavefront_pct", 0), r.get("smem_lsu_wavefronts", 0) / cyc, r.get("smem_tc_wavefronts", 0) / cyc))
     print(json.dumps(stages))
 
 
