@@ -299,8 +299,9 @@ __global__ void __launch_bounds__(kRowConsumers + 32, 1) sweep_rows_kernel(
   const uint32_t row_bytes = static_cast<uint32_t>(row_f4) * 16u;
   const int G = C / 4;                                 // float4 per voxel
   const int64_t n_rows = static_cast<int64_t>(x_end - x_begin) * Y;
-  const int64_t per_cta = (n_rows + gridDim.x - 1) / gridDim.x;
-  const int64_t r0 = blockIdx.x * per_cta, r1 = min(n_rows, r0 + per_cta);
+  // rows are dealt round-robin: at any time the CTAs work on ~gridDim consecutive rows, a compact window of each array
+  // (one contiguous run per CTA -- 148 x 8 streams 1.3 MB apart -- measured slower: DRAM page locality)
+  const int64_t r0 = blockIdx.x, r1 = n_rows, r_step = gridDim.x;
   if (r0 >= r1) return;
   const int64_t sy = static_cast<int64_t>(Z) * C, sx = sy * Y;
   using namespace tc;
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(kRowConsumers + 32, 1) sweep_rows_kernel(
     if (elect_one()) {
       uint32_t ephase = 0u;
       int64_t j = 0;
-      for (int64_t r = r0; r < r1; ++r, ++j) {
+      for (int64_t r = r0; r < r1; r += r_step, ++j) {
         const int s = static_cast<int>(j % kRowStages);
         if (j >= kRowStages) {             // the consumers have finished with the row that used this stage
           mbar_wait(smem_u32(&bars[kRowStages + s]), (ephase >> s) & 1u);
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(kRowConsumers + 32, 1) sweep_rows_kernel(
   // ---- consumers ----
   uint32_t fphase = 0u;
   int64_t j = 0;
-  for (int64_t r = r0; r < r1; ++r, ++j) {
+  for (int64_t r = r0; r < r1; r += r_step, ++j) {
     const int s = static_cast<int>(j % kRowStages);
     mbar_wait(smem_u32(&bars[s]), (fphase >> s) & 1u);
     fphase ^= 1u << s;
