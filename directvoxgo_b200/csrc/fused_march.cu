@@ -409,17 +409,23 @@ __global__ void __launch_bounds__(256, 4) k0_gather_tiles_kernel(
   const int q = lane % G, sub = lane / G;
   const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  // the per-survivor record of the NEXT grid-stride iteration is requested one iteration ahead: record -> corner
+  // addresses -> corner loads is a chain of two dependent memory round trips per iteration otherwise
+  float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s_pos && sub < SPW && warp0 * SPW + sub < n) rec_next = __ldg(s_pos + warp0 * SPW + sub);
   for (int64_t base = warp0 * SPW; base < rows; base += n_warps * SPW) {   // warp-uniform trip count
     const int64_t p = base + sub;
     const bool active = sub < SPW && p < rows;
     const bool live = active && p < n;
     uint8_t* __restrict__ trow = xt + (p >> 7) * xb + tc::tile_off(static_cast<int>(p & 127), 0, K1);
+    const float4 rec = rec_next;
+    const int64_t p_next = p + n_warps * SPW;
+    if (s_pos && sub < SPW && p_next < n) rec_next = __ldg(s_pos + p_next);
     int r = 0;
     Corner8 cn;
     cn.valid = 0u;
     if (live) {
       if (s_pos) {       // march_fwd's record: continuous voxel coordinates + ray index, one 16-byte load
-        const float4 rec = __ldg(s_pos + p);
         r = __float_as_int(rec.w);
         cn = corner8_idx(sc, rec.x, rec.y, rec.z);
       } else {
