@@ -364,8 +364,7 @@ __global__ void __launch_bounds__(kRowConsumers + 32, 1) sweep_rows_kernel(
     const float4* __restrict__ sm = reinterpret_cast<const float4*>(stage(s, 6));
     const float4* __restrict__ sv = reinterpret_cast<const float4*>(stage(s, 7));
     for (int i = tid; i < row_f4; i += kRowConsumers) {
-      const int z = i / G;
-      const bool ozm = z > 0, ozp = z < Z - 1;
+      const bool ozm = i >= G, ozp = i < row_f4 - G;     // z > 0, z < Z - 1 (no integer division: G is a run-time value)
       const float4 p4 = sp[i], g4 = sg[i], m4 = sm[i], v4 = sv[i];
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 nzm = ozm ? sp[i - G] : zero4, nzp = ozp ? sp[i + G] : zero4;

@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 STAGE_OF = {"march_fwd_kernel": "march_fwd", "k0_gather_kernel": "march_fwd", "k0_gather_tiles_kernel": "march_fwd", "mlp_fwd_kernel": "mlp_fwd",
-            "mlp_bwd_kernel": "mlp_bwd", "k0_scatter_kernel": "march_bwd", "march_bwd_kernel": "march_bwd",
+            "mlp_bwd_kernel": "mlp_bwd", "k0_scatter_kernel": "march_bwd", "march_bwd_kernel": "march_bwd", "sweep_rows_kernel": "sweep",
             "sweep_kernel": "sweep"}
 COLS = {"gpu__time_duration.sum": "time_us", "dram__bytes_read.sum": "dram_rd", "dram__bytes_write.sum": "dram_wr",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
