@@ -16,7 +16,8 @@ One JSON line on stdout (rank 0).  What is measured, and from which state:
     (FusedTrainer.snapshot / restore), so neither trains the model that is timed;
   * `value`    K steps, inputs resident in HBM, CUDA events around the loop, max over ranks;
   * `e2e`      the same K steps through step() with pinned-host rays copied H2D and the loss read back every step;
-  * `roofline` a third pass of the same K steps with CUDA events between the stages; the survivor count M4 of exactly
+  * `roofline` a third pass of the same K steps with CUDA events between the stages (per-stage MEDIAN over the steps:
+    a host-side launch hiccup otherwise lands in whichever stage was waiting); the survivor count M4 of exactly
     those steps is accumulated on the device (dvgo_fused_step_begin) and printed (`survivors_per_step`), and the MLP
     FLOPs / gather-scatter bytes are computed from it -- every `frac` can be recomputed from the line;
   * `cpu_baseline` / `--impl reference`: oracle/model_ref.py (the reference's algorithm restated on torch-CPU + the C
@@ -603,7 +604,10 @@ def run_ours(args):
                 "peak_kind": peak_kind + (" (bf16 sustained; fp16 runs at the same rate)" if kind == "tensor" else ""),
                 "kernel_ms": stages_main[dom], "algorithmic_work_per_launch": work,
                 "survivors_per_step": M4, "work_term": "M4 = survivors_per_step counted on the device over the same %d steps "
-                                                       "whose stage events give kernel_ms" % args.steps,
+                                                       "whose stage events give kernel_ms (median over the steps)" % args.steps,
+                "limiter_observed": ("ncu, profiles/r02c_ncu_kernels.md: mlp_bwd_kernel moves 0.85 shared-memory wavefronts per "
+                                     "SM per cycle (0.49 tensor-core operand fetch + 0.36 LSU) -- shared-memory bandwidth, not "
+                                     "the tensor pipe (39 % busy), bounds it") if dom == "mlp_bwd" else None,
                 "all_stages": {k: {"ms": stages_main[k], "bound": alg[k][0], "work": alg[k][1],
                                    "frac": (alg[k][1] / (stages_main[k] * 1e-3) / (1e9 * hbm_peak if alg[k][0] == "hbm" else 1e12 * tensor_peak))}
                                for k in stages_main if k in alg},

@@ -282,27 +282,30 @@ __global__ void __launch_bounds__(256, kPeer ? DVGO_PEER_MINB : 1) sweep_kernel(
 // ten 16-byte loads per thread in 114 registers at 25 % occupancy and runs at 0.71 of the HBM rate against 0.96
 // without TV), and 3 x 61 KB are in flight per SM.  Same arithmetic, same term order (bit-identical results).
 // Used for every TV sweep (dense or sparse) of a vectorisable grid on one GPU (or an NCCL slab): measured on B200, k0
-// 160^3 x 12: dense TV 0.330 -> 0.308 ms, sparse TV (10 % of the cells touched) 0.48 -> 0.31 ms.  Rows that do not fit
-// (Z*C*4 > 9 KB), the peer / per-lr variants and the sweeps without TV (in place, lazy: most elements stop after
-// reading g) stay with sweep_kernel.
+// 160^3 x 12: dense TV 0.332 -> 0.278 ms (5.67 TB/s), sparse TV (10 % of the cells touched) 0.48 -> 0.28 ms.  The peer /
+// per-lr variants and the sweeps without TV (in place, lazy: most elements stop after reading g) stay with sweep_kernel.
 constexpr int kRowStages = 3;
 constexpr int kRowConsumers = 512;   // + one producer warp (measured: 256 -> 0.365 ms, 512 -> 0.308 ms, 768 -> 0.308 ms)
 
+// A row longer than the stage budget is processed as `nseg` equal SEGMENTS (voxel-aligned); the centre copy of a
+// segment carries one voxel of z-halo on each side (clipped at the row ends), the seven other copies are the segment.
 __global__ void __launch_bounds__(kRowConsumers + 32, 1) sweep_rows_kernel(
     const float* __restrict__ pin, float* __restrict__ pout, float* __restrict__ grad, float* __restrict__ m_,
-    float* __restrict__ v_, int X, int Y, int Z, int C, int x_begin, int x_end, int tv_dense, float wy, float wz,
-    int masked, float step_size, float beta1, float beta2, float eps) {
+    float* __restrict__ v_, int X, int Y, int Z, int C, int x_begin, int x_end, int nseg, int tv_dense, float wy,
+    float wz, int masked, float step_size, float beta1, float beta2, float eps) {
   extern __shared__ __align__(128) uint8_t srow[];
   __shared__ __align__(8) uint64_t bars[2 * kRowStages];   // full[s], empty[s]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row_f4 = Z * C / 4;                        // float4 per row
-  const uint32_t row_bytes = static_cast<uint32_t>(row_f4) * 16u;
+  const int seg_f4 = row_f4 / nseg;                    // float4 per segment (a multiple of G)
   const int G = C / 4;                                 // float4 per voxel
-  const int64_t n_rows = static_cast<int64_t>(x_end - x_begin) * Y;
-  // rows are dealt round-robin: at any time the CTAs work on ~gridDim consecutive rows, a compact window of each array
-  // (one contiguous run per CTA -- 148 x 8 streams 1.3 MB apart -- measured slower: DRAM page locality)
-  const int64_t r0 = blockIdx.x, r1 = n_rows, r_step = gridDim.x;
-  if (r0 >= r1) return;
+  const uint32_t seg_bytes = static_cast<uint32_t>(seg_f4) * 16u;
+  const uint32_t ctr_bytes = (static_cast<uint32_t>(seg_f4 + 2 * G) * 16u + 127u) & ~127u;   // centre buffer: + halo
+  const int64_t n_units = static_cast<int64_t>(x_end - x_begin) * Y * nseg;
+  // units are dealt round-robin: at any time the CTAs work on ~gridDim consecutive segments, a compact window of each
+  // array (one contiguous run per CTA -- 148 x 8 streams 1.3 MB apart -- measured slower: DRAM page locality)
+  const int64_t u0 = blockIdx.x, u1 = n_units, u_step = gridDim.x;
+  if (u0 >= u1) return;
   const int64_t sy = static_cast<int64_t>(Z) * C, sx = sy * Y;
   using namespace tc;
   if (tid == 0) {
@@ -313,33 +316,42 @@ __global__ void __launch_bounds__(kRowConsumers + 32, 1) sweep_rows_kernel(
     mbar_init_fence();
   }
   __syncthreads();
-  // stage layout: [p | p(y-1) | p(y+1) | p(x-1) | p(x+1) | g | m | v], each row_bytes
-  auto stage = [&](int s, int which) { return srow + (static_cast<size_t>(s) * 8 + which) * row_bytes; };
+  // stage layout: [p with halo | p(y-1) | p(y+1) | p(x-1) | p(x+1) | g | m | v]
+  const size_t stage_bytes = ctr_bytes + 7u * static_cast<size_t>(seg_bytes);
+  auto stage = [&](int s, int which) {
+    return srow + static_cast<size_t>(s) * stage_bytes + (which == 0 ? 0u : ctr_bytes + (which - 1) * static_cast<size_t>(seg_bytes));
+  };
 
   if (warp == kRowConsumers / 32) {
     // ---- producer ----
     if (elect_one()) {
       uint32_t ephase = 0u;
       int64_t j = 0;
-      for (int64_t r = r0; r < r1; r += r_step, ++j) {
+      for (int64_t u = u0; u < u1; u += u_step, ++j) {
         const int s = static_cast<int>(j % kRowStages);
-        if (j >= kRowStages) {             // the consumers have finished with the row that used this stage
+        if (j >= kRowStages) {             // the consumers have finished with the unit that used this stage
           mbar_wait(smem_u32(&bars[kRowStages + s]), (ephase >> s) & 1u);
           ephase ^= 1u << s;
         }
+        const int64_t r = u / nseg;
+        const int seg = static_cast<int>(u - r * nseg);
         const int x = x_begin + static_cast<int>(r / Y), y = static_cast<int>(r % Y);
-        const int64_t e0 = (static_cast<int64_t>(x) * Y + y) * sy;
+        const int f0 = seg * seg_f4;                                    // first float4 of the segment in its row
+        const int64_t e0 = (static_cast<int64_t>(x) * Y + y) * sy + static_cast<int64_t>(f0) * 4;
+        const int lo = f0 >= G ? G : 0, hi = f0 + seg_f4 + G <= row_f4 ? G : 0;   // halo float4 present on each side
         const uint32_t full = smem_u32(&bars[s]);
-        const int n_copies = 4 + (y > 0) + (y < Y - 1) + (x > 0) + (x < X - 1);
-        mbar_expect_tx(full, n_copies * row_bytes);
-        bulk_g2s(smem_u32(stage(s, 0)), pin + e0, row_bytes, full);
-        if (y > 0) bulk_g2s(smem_u32(stage(s, 1)), pin + e0 - sy, row_bytes, full);
-        if (y < Y - 1) bulk_g2s(smem_u32(stage(s, 2)), pin + e0 + sy, row_bytes, full);
-        if (x > 0) bulk_g2s(smem_u32(stage(s, 3)), pin + e0 - sx, row_bytes, full);
-        if (x < X - 1) bulk_g2s(smem_u32(stage(s, 4)), pin + e0 + sx, row_bytes, full);
-        bulk_g2s(smem_u32(stage(s, 5)), grad + e0, row_bytes, full);
-        bulk_g2s(smem_u32(stage(s, 6)), m_ + e0, row_bytes, full);
-        bulk_g2s(smem_u32(stage(s, 7)), v_ + e0, row_bytes, full);
+        const int n_other = 3 + (y > 0) + (y < Y - 1) + (x > 0) + (x < X - 1);
+        mbar_expect_tx(full, static_cast<uint32_t>(seg_f4 + lo + hi) * 16u + n_other * seg_bytes);
+        // element f0 + i of the row sits at float4 index G + i of the centre buffer
+        bulk_g2s(smem_u32(stage(s, 0)) + static_cast<uint32_t>(G - lo) * 16u, pin + e0 - lo * 4,
+                 static_cast<uint32_t>(seg_f4 + lo + hi) * 16u, full);
+        if (y > 0) bulk_g2s(smem_u32(stage(s, 1)), pin + e0 - sy, seg_bytes, full);
+        if (y < Y - 1) bulk_g2s(smem_u32(stage(s, 2)), pin + e0 + sy, seg_bytes, full);
+        if (x > 0) bulk_g2s(smem_u32(stage(s, 3)), pin + e0 - sx, seg_bytes, full);
+        if (x < X - 1) bulk_g2s(smem_u32(stage(s, 4)), pin + e0 + sx, seg_bytes, full);
+        bulk_g2s(smem_u32(stage(s, 5)), grad + e0, seg_bytes, full);
+        bulk_g2s(smem_u32(stage(s, 6)), m_ + e0, seg_bytes, full);
+        bulk_g2s(smem_u32(stage(s, 7)), v_ + e0, seg_bytes, full);
       }
     }
     return;
@@ -348,14 +360,17 @@ __global__ void __launch_bounds__(kRowConsumers + 32, 1) sweep_rows_kernel(
   // ---- consumers ----
   uint32_t fphase = 0u;
   int64_t j = 0;
-  for (int64_t r = r0; r < r1; r += r_step, ++j) {
+  for (int64_t u = u0; u < u1; u += u_step, ++j) {
     const int s = static_cast<int>(j % kRowStages);
     mbar_wait(smem_u32(&bars[s]), (fphase >> s) & 1u);
     fphase ^= 1u << s;
+    const int64_t r = u / nseg;
+    const int seg = static_cast<int>(u - r * nseg);
     const int x = x_begin + static_cast<int>(r / Y), y = static_cast<int>(r % Y);
-    const int64_t e0 = (static_cast<int64_t>(x) * Y + y) * sy;
+    const int f0 = seg * seg_f4;
+    const int64_t e0 = (static_cast<int64_t>(x) * Y + y) * sy + static_cast<int64_t>(f0) * 4;
     const bool oym = y > 0, oyp = y < Y - 1, oxm = x > 0, oxp = x < X - 1;
-    const float4* __restrict__ sp = reinterpret_cast<const float4*>(stage(s, 0));
+    const float4* __restrict__ sp = reinterpret_cast<const float4*>(stage(s, 0)) + G;   // sp[i]: element f0 + i
     const float4* __restrict__ sym = reinterpret_cast<const float4*>(stage(s, 1));
     const float4* __restrict__ syp = reinterpret_cast<const float4*>(stage(s, 2));
     const float4* __restrict__ sxm = reinterpret_cast<const float4*>(stage(s, 3));
@@ -363,8 +378,8 @@ __global__ void __launch_bounds__(kRowConsumers + 32, 1) sweep_rows_kernel(
     const float4* __restrict__ sg = reinterpret_cast<const float4*>(stage(s, 5));
     const float4* __restrict__ sm = reinterpret_cast<const float4*>(stage(s, 6));
     const float4* __restrict__ sv = reinterpret_cast<const float4*>(stage(s, 7));
-    for (int i = tid; i < row_f4; i += kRowConsumers) {
-      const bool ozm = i >= G, ozp = i < row_f4 - G;     // z > 0, z < Z - 1 (no integer division: G is a run-time value)
+    for (int i = tid; i < seg_f4; i += kRowConsumers) {
+      const bool ozm = f0 + i >= G, ozp = f0 + i < row_f4 - G;   // z > 0, z < Z - 1 (no integer division by the run-time G)
       const float4 p4 = sp[i], g4 = sg[i], m4 = sm[i], v4 = sv[i];
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 nzm = ozm ? sp[i - G] : zero4, nzp = ozp ? sp[i + G] : zero4;
@@ -547,18 +562,28 @@ static int sweep_launch(const float* param_in, float* param_out, float* grad, fl
     else SWEEP_ONE(V, false, false, KZ, N);                                                           \
   } while (0)
   static const int bulk_env = [] { const char* e = getenv("DVGO_SWEEP_BULK"); return e ? atoi(e) : 1; }();
-  const size_t row_bytes = static_cast<size_t>(Z) * C * 4;
-  const size_t rows_smem = kRowStages * 8 * row_bytes;
-  if (bulk_env && vec && tv && peers.n == 0 && !perlr && rows_smem <= 220 * 1024) {
-    // row-staged sweep: one persistent CTA per SM, whole rows through shared memory by bulk copies
+  // row segments: the fewest equal, voxel-aligned pieces of a z-row whose three stages fit 220 KB of shared memory
+  const int row_f4 = Z * C / 4, G4 = C / 4;
+  int nseg = 0;
+  size_t rows_smem = 0;
+  if (bulk_env && vec && tv && peers.n == 0 && !perlr) {
+    for (int k = 1; k <= 8 && !nseg; ++k) {
+      if (row_f4 % k || (row_f4 / k) % G4) continue;
+      const size_t ctr = ((static_cast<size_t>(row_f4 / k + 2 * G4) * 16) + 127) & ~static_cast<size_t>(127);
+      const size_t need = kRowStages * (ctr + 7 * static_cast<size_t>(row_f4 / k) * 16);
+      if (need <= 220 * 1024) { nseg = k; rows_smem = need; }
+    }
+  }
+  if (nseg) {
+    // row-staged sweep: one persistent CTA per SM, whole rows (or row segments) through shared memory by bulk copies
     cudaError_t e = cudaFuncSetAttribute(sweep_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(rows_smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    const int64_t n_rows = static_cast<int64_t>(x_end - x_begin) * Y;
-    const int blocks = static_cast<int>(n_rows < kNumSMs ? n_rows : kNumSMs);
+    const int64_t n_units = static_cast<int64_t>(x_end - x_begin) * Y * nseg;
+    const int blocks = static_cast<int>(n_units < kNumSMs ? n_units : kNumSMs);
     sweep_rows_kernel<<<blocks, kRowConsumers + 32, rows_smem, s>>>(param_in, param_out, grad, exp_avg, exp_avg_sq, X, Y, Z,
-                                                                    C, x_begin, x_end, tv_dense, wy, wz, masked, step_size,
-                                                                    beta1, beta2, eps);
+                                                                    C, x_begin, x_end, nseg, tv_dense, wy, wz, masked,
+                                                                    step_size, beta1, beta2, eps);
   } else if (vec) SWEEP_LAUNCH(4, false, n / 4);
   else if (zvec) SWEEP_LAUNCH(4, true, n / 4);
   else SWEEP_LAUNCH(1, false, n);
