@@ -39,16 +39,21 @@ def test_layout_converters_roundtrip():
     assert torch.equal(ext.cl_to_ncdhw(cl), g)
 
 
-@pytest.mark.parametrize("C,tv,tv_dense,masked,perlr", [
-    (12, True, True, True, False), (12, True, False, True, False), (12, False, False, True, False),
-    (12, False, False, False, False), (1, True, True, True, False), (1, False, False, False, True),
-    (3, True, True, False, False), (9, True, False, True, False)])
-def test_sweep_matches_oracle_tv_plus_adam(C, tv, tv_dense, masked, perlr):
+@pytest.mark.parametrize("C,tv,tv_dense,masked,perlr,shape", [
+    (12, True, True, True, False, (11, 9, 13)), (12, True, False, True, False, (11, 9, 13)),
+    (12, False, False, True, False, (11, 9, 13)), (12, False, False, False, False, (11, 9, 13)),
+    (1, True, True, True, False, (11, 9, 13)), (1, False, False, False, True, (11, 9, 13)),
+    (3, True, True, False, False, (11, 9, 13)), (9, True, False, True, False, (11, 9, 13)),
+    # the row-staged (bulk-copy) sweep: more rows than CTAs x stages (stage reuse), a row that is split into two
+    # segments with a z-halo (200 x 12 floats = 9.6 KB), 16 channels, and unmasked Adam
+    (12, True, True, True, False, (23, 31, 16)), (12, True, False, True, False, (5, 4, 200)),
+    (16, True, True, False, False, (7, 5, 150)), (4, True, True, True, False, (3, 2, 8))])
+def test_sweep_matches_oracle_tv_plus_adam(C, tv, tv_dense, masked, perlr, shape):
     """The fused TV+Adam sweep on channel-last buffers == total_variation_add_grad followed by the
     matching Adam kernel on the reference's [1,C,X,Y,Z] layout (oracle), 3 consecutive steps."""
     from directvoxgo_b200 import ext
     from oracle import oracle as orc
-    X, Y, Z = 11, 9, 13
+    X, Y, Z = shape
     g = torch.Generator().manual_seed(C * 7 + tv)
     p = torch.randn(1, C, X, Y, Z, generator=g) * 1.5
     m = torch.zeros_like(p)
