@@ -15,7 +15,8 @@ One JSON line on stdout (rank 0).  What is measured, and from which state:
     trainer, then its parameters / Adam state are restored from a snapshot taken at construction
     (FusedTrainer.snapshot / restore), so neither trains the model that is timed;
   * `value`    K steps, inputs resident in HBM, CUDA events around the loop, max over ranks;
-  * `e2e`      the same K steps through step() with pinned-host rays copied H2D and the loss read back every step;
+  * `e2e`      the same K steps through the public host-fed loop (trainer.HostFedLoop): pinned-host rays copied H2D and
+    the loss read back for every step; `serialised_ms_per_step` = the same with copy -> step -> read strictly in turn;
   * `roofline` a third pass of the same K steps with CUDA events between the stages (per-stage MEDIAN over the steps:
     a host-side launch hiccup otherwise lands in whichever stage was waiting); the survivor count M4 of exactly
     those steps is accumulated on the device (dvgo_fused_step_begin) and printed (`survivors_per_step`), and the MLP
@@ -490,8 +491,25 @@ def run_ours(args):
                 loss_host = float(trainer.step(*stage).item())
             ev1.record()
             barrier()
+            res["e2e_sync_ms"] = max_over_ranks(ev0.elapsed_time(ev1)) / steps     # copy -> step -> read, serialised
+            # the public host-fed loop (directvoxgo_b200.trainer.HostFedLoop): the same K copies, K steps and K loss
+            # reads, but step i's copy runs under step i-1 and its loss is read after step i+1 was enqueued
+            from directvoxgo_b200.trainer import HostFedLoop
+            restore()
+            loop = HostFedLoop(trainer, host_batches[0], device)
+            losses = []
+            torch.cuda.synchronize()
+            ev0.record()
+            for i in range(steps):
+                prev = loop.step(host_batches[(warm + i) % nb])
+                if prev is not None:
+                    losses.append(prev)
+            losses.append(loop.drain())
+            ev1.record()
+            barrier()
+            assert len(losses) == steps and abs(losses[-1] - loss_host) <= 1e-3 * max(1.0, abs(loss_host)), (losses[-1], loss_host)
             res["e2e_ms"] = max_over_ranks(ev0.elapsed_time(ev1)) / steps
-            res["e2e_loss"] = loss_host
+            res["e2e_loss"] = losses[-1]
             res["h2d"] = sum(x.numel() * x.element_size() for x in host_batches[0])
         # ---- pass 3: the same K steps with CUDA events between the stages, survivors counted on the device ----------
         if with_stages and path == "fused":
@@ -550,6 +568,7 @@ def run_ours(args):
     surv = main.get("survivors_per_step")
     launches = main["launches"]
     main_e2e_ms, main_h2d, main_e2e_loss = main["e2e_ms"], main["h2d"], main["e2e_loss"]
+    main_e2e_sync_ms = main.get("e2e_sync_ms")
     exchange_used = getattr(trainer, "exchange", "nccl all-reduce" if world > 1 else "none") + \
         (" + NVLS multicast" if getattr(trainer, "multicast", False) else "")
     surv_value_pass = main.get("survivors_value_pass")
@@ -647,7 +666,10 @@ def run_ours(args):
                                 "%d distinct ray batches cycled" % (G * 13 * 16 / 1e9, N_BATCHES),
                    "algorithmic_bytes_per_step": balg, "clock_ramp_s": args.ramp_s},
         "e2e": {"value": n_global / (main_e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": main_e2e_ms,
-                "h2d_bytes_per_step": main_h2d, "d2h_bytes_per_step": 4, "last_loss": main_e2e_loss},
+                "h2d_bytes_per_step": main_h2d, "d2h_bytes_per_step": 4, "last_loss": main_e2e_loss,
+                "api": "directvoxgo_b200.trainer.HostFedLoop(trainer).step(pinned host batch): every step copies its own "
+                       "rays H2D (copy stream, under the previous step) and its own loss D2H (read one call later)",
+                "serialised_ms_per_step": main_e2e_sync_ms},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,

@@ -76,3 +76,63 @@ class ModuleTrainer:
         for group in self.opt.param_groups:     # run.py:401-406: per-iteration exponential lr decay
             group["lr"] = group["lr"] * self.decay
         return loss.detach()
+
+
+class HostFedLoop:
+    """Drives a trainer from HOST batches (pinned memory) without idling the GPU between steps.
+
+    The reference keeps its training rays on the device and reads the loss only at its logging cadence
+    (run.py:353-370, :409-417); a caller that streams ray batches from the host and wants every step's loss would
+    otherwise serialise copy -> step -> read.  Here the host -> device copy of step i runs on a copy stream under the
+    kernels of step i - 1 (two staging sets), and the loss of step i is read one call later, through a pinned buffer
+    and an event, after step i + 1 has been enqueued:
+
+        loop = HostFedLoop(trainer, example_batch)
+        for batch in host_batches:            # tuples of pinned CPU tensors (rays_o, rays_d, viewdirs, target)
+            prev = loop.step(batch)           # loss of the PREVIOUS step (None on the first call)
+        last = loop.drain()                   # loss of the final step
+
+    Every step still pays its own H2D copy and its own 4-byte D2H read; only the order of the waits changes.
+    """
+
+    def __init__(self, trainer, example_batch, device=None):
+        self.trainer = trainer
+        self.device = torch.device(device) if device is not None else trainer.device
+        self.staging = [[torch.empty_like(x, device=self.device) for x in example_batch] for _ in range(2)]
+        self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.done = [None, None]
+        self.loss_ready = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+
+    def step(self, host_batch):
+        b = self.i % 2
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.done[b] is not None:          # step i - 2 has finished reading this staging set
+                self.copy_stream.wait_event(self.done[b])
+            for d, h in zip(self.staging[b], host_batch):
+                d.copy_(h, non_blocking=True)
+            self.copied[b].record(self.copy_stream)
+        cur.wait_event(self.copied[b])
+        loss = self.trainer.step(*self.staging[b])
+        if self.done[b] is None:
+            self.done[b] = torch.cuda.Event()
+        self.done[b].record(cur)
+        self.loss_host[b].copy_(loss.reshape(()), non_blocking=True)
+        self.loss_ready[b].record(cur)
+        prev = None
+        if self.i > 0:
+            self.loss_ready[1 - b].synchronize()
+            prev = float(self.loss_host[1 - b])
+        self.i += 1
+        return prev
+
+    def drain(self):
+        """Loss of the last step enqueued (waits for it)."""
+        if self.i == 0:
+            return None
+        b = (self.i - 1) % 2
+        self.loss_ready[b].synchronize()
+        return float(self.loss_host[b])

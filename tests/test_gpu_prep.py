@@ -213,3 +213,25 @@ def test_full_size_properties_800x800():
                        for s in range(0, H * W, 65536)])
     # compositing accumulates with fp32 atomics (free order): stated tolerance 1e-5 abs on rgb in [0,1]
     np.testing.assert_allclose(to_np(a["rgb_marched"].reshape(-1, 3)), to_np(b_rgb), rtol=0, atol=1e-5)
+
+
+def test_render_view_chunk_streams_agree():
+    """render_view with its chunks pipelined over two streams (a workspace each) == the serial order, and the device
+    statistics count every chunk once."""
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedRenderer
+    from tests.test_gpu_fused import _fine_model
+    m = _fine_model(48, dens_scale=2.0, mask_p=0.2).to(DEV)
+    rk = dict(syn.RENDER_KWARGS)
+    H = W = 96
+    K = syn.intrinsics(H, W, focal=syn.blender_focal(W))
+    c2w = syn.random_poses(1, seed=11)[0]
+    outs, stats = [], []
+    for streams in (1, 2, 3):
+        fr = FusedRenderer(m, rk)
+        outs.append(fr.render_view(H, W, K, c2w, chunk=2048, streams=streams))
+        stats.append(fr.stats_snapshot())
+    for o in outs[1:]:
+        for k in ("rgb_marched", "depth", "alphainv_last"):
+            np.testing.assert_allclose(to_np(o[k]), to_np(outs[0][k]), rtol=0, atol=2e-5)
+    assert stats[0][0] == stats[1][0] == stats[2][0] and stats[0][1] == stats[1][1] == stats[2][1] == 5
