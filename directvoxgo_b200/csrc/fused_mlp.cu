@@ -2,12 +2,17 @@
 // tensor cores: tcgen05.mma kind::f16 (FP16 operands, fp32 accumulators in TMEM), operands staged in
 // shared memory in the canonical no-swizzle core-matrix layout (tc_common.cuh).
 //
-// Numerics: fp32 master weights / features / outputs; GEMM operands rounded to FP16 (10-bit mantissa,
-// the same as TF32 -- what the reference's nn.Linear uses on any tensor-core GPU under its pinned
-// PyTorch 1.8.1, where allow_tf32 defaulted to True; README.md:32) on the way into shared memory;
-// products accumulated in fp32.  Backward operands are scaled by a power of two so that small
-// gradients stay in FP16's normal range, and unscaled exactly in the fp32 epilogue.
-// Stated tolerance vs the exact-fp32 path: 2e-3 abs on rgb (tests/test_gpu_mlp.py).
+// Numerics: fp32 master weights / features / outputs; GEMM operands rounded to FP16 on the way into shared memory /
+// tensor memory; products accumulated in fp32.  FP16 shares TF32's 10-bit MANTISSA (the rounding error of what the
+// reference's nn.Linear does on any tensor-core GPU under its pinned PyTorch 1.8.1, where allow_tf32 defaulted to True;
+// README.md:32) but NOT its range: 5 exponent bits, largest finite value 65504, subnormal below 6e-5.  Hence
+//   * every conversion saturates (cvt.rn.satfinite: a value beyond +-65504 clamps instead of becoming inf) and a NaN /
+//     inf reaching an output sets bit 1 of the device status word, which check_status() / sync_to_model() /
+//     checkpointing raise on (the reference's fp32 path has no such range limit: mlp="torch" is the exact mode);
+//   * backward operands are scaled by a power of two (grad_scale) so that small gradients stay in FP16's normal
+//     range, and unscaled exactly in the fp32 epilogue.
+// Stated tolerance vs the exact-fp32 path: 2e-3 abs on rgb, 5e-2 relative L2 on gradients (tests/test_gpu_mlp.py,
+// incl. a 300-step convergence comparison against the fp32 mode).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "fused_scene.cuh"
@@ -24,9 +29,10 @@ using namespace tc;
 // One tile = 128 survivors of the sample stream.  256 threads: thread (row = 32*(warp%4)+lane,
 // half = warp/4) owns one sample row of the tile and half of the 128 hidden columns (a warp can only
 // read its own 32-lane quarter of TMEM, so warps w and w+4 split the columns of the same rows).
-//   layers 1, 2 : tcgen05.mma, A = activations [sample][feature] (K-major), B = weights [out][in]
-//   layer 3     : fp32 SIMT dot products fused into the layer-2 epilogue (3 outputs: cheaper than an N=16 MMA)
-//   b1 is folded into W1 as column d_in of the augmented input (the constant-1 feature).
+//   layer 1     : tcgen05.mma, A = X~ tile [sample][feature] (K-major, shared memory), B = weights [out][in]
+//   layers 2, 3 : tcgen05.mma with the A operand (the previous layer's activations, packed fp16) in TENSOR MEMORY;
+//                 layer 3 is an N = 16 MMA (3 outputs used)
+//   b1 is folded into W1 as column d_in of the augmented input (the constant-1 feature), b2 into W2 as column 128.
 // ----------------------------------------------------------------------------------------------------
 constexpr int kHid = 128;
 constexpr int kHidA = kHid + 16;  // hidden width augmented with the constant-1 column (carries b2 / db2 in bwd)
