@@ -197,16 +197,19 @@ void ray_finish(Tensor rgb_acc, Tensor alphainv_last, c10::optional<Tensor> targ
 }
 
 void sample_grad(Tensor rgb, Tensor s_weight, Tensor s_ray, Tensor G, Tensor target, Tensor counters, int n_global,
-                 double weight_rgbper, Tensor d_rgb, Tensor d_w, Tensor loss_acc, c10::optional<Tensor> dzt,
+                 double weight_rgbper, c10::optional<Tensor> d_rgb, Tensor d_w, Tensor loss_acc, c10::optional<Tensor> dzt,
                  double grad_scale) {
-  F32(rgb); F32(s_weight); I32(s_ray); F32(G); F32(target); I32(counters); F32(d_rgb); F32(d_w); F32(loss_acc);
+  F32(rgb); F32(s_weight); I32(s_ray); F32(G); F32(target); I32(counters); F32(d_w); F32(loss_acc);
+  if (d_rgb.has_value()) F32((*d_rgb));
+  TORCH_CHECK(d_rgb.has_value() || dzt.has_value(), "sample_grad: d_rgb may only be omitted when dzt is given");
   if (dzt.has_value())
     TORCH_CHECK(dzt->is_cuda() && dzt->is_contiguous() && dzt->scalar_type() == torch::kUInt8 &&
                 dzt->numel() >= dvgo_mlp_dztile_bytes(rgb.numel() / 3) &&
                 reinterpret_cast<uintptr_t>(dzt->data_ptr()) % 16 == 0, "dzt: uint8 CUDA tensor of mlp_dztile_bytes bytes");
   const c10::cuda::CUDAGuard guard(rgb.device());
   rc_check(dvgo_fused_sample_grad(fp(rgb), fp(s_weight), ipm(s_ray), fp(G), fp(target), ipm(counters),
-                                  rgb.numel() / 3, n_global, static_cast<float>(weight_rgbper), fpm(d_rgb), fpm(d_w),
+                                  rgb.numel() / 3, n_global, static_cast<float>(weight_rgbper),
+                                  d_rgb.has_value() ? d_rgb->data_ptr<float>() : nullptr, fpm(d_w),
                                   fpm(loss_acc), dzt.has_value() ? dzt->data_ptr() : nullptr,
                                   static_cast<float>(grad_scale), cur_stream()),
            "sample_grad");

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) sample_grad_kernel(
         dr += w_per * 2.f * w * d * inv_n;        // run.py:384-386 (weights detached)
         loss += w_per * w * d * d * inv_n;
       }
-      d_rgb[3 * p + c] = dr;
+      if (d_rgb) d_rgb[3 * p + c] = dr;
       z[c] = dr * x * (1.f - x);                  // through the sigmoid: what the rgbnet backward starts from
       dw += g * x;
     }
@@ -304,9 +304,9 @@ DVGO_API int dvgo_fused_sample_grad(const float* rgb, const float* s_weight, con
                                     int64_t surv_cap, int n_global, float weight_rgbper, float* d_rgb,
                                     float* d_w, float* loss_acc, void* dzt, float grad_scale,
                                     dvgo_stream_t stream) {
-  if (surv_cap < 0 || n_global <= 0 || !rgb || !s_weight || !s_ray || !G || !counters || !d_rgb ||
+  if (surv_cap < 0 || n_global <= 0 || !rgb || !s_weight || !s_ray || !G || !counters || (!d_rgb && !dzt) ||
       !d_w || (weight_rgbper > 0.f && !target) || (dzt && !(grad_scale > 0.f)))
-    return DVGO_EINVAL;
+    return DVGO_EINVAL;   // (d_rgb may be NULL when the dZ3 tiles are the only consumer: the tensor-core rgbnet)
   sample_grad_kernel<<<stream_grid(surv_cap, 256), 256, 0, as_stream(stream)>>>(
       rgb, s_weight, s_ray, G, target, counters, surv_cap, n_global, weight_rgbper, d_rgb, d_w,
       loss_acc, static_cast<uint8_t*>(dzt), grad_scale);

@@ -590,8 +590,10 @@ class FusedTrainer(_FusedBase):
             ext.composite(ws.rgb, ws.s_weight, ws.s_ray, ws.s_slot, ws.ray_off, ws.counters, ws.rgb_acc, None)
             ext.ray_finish(ws.rgb_acc, ws.alphainv_last, target, bg, n, n_global, w_main, w_ent, ws.G, ws.g_last,
                            ws.loss_acc)
-            ext.sample_grad(ws.rgb, ws.s_weight, ws.s_ray, ws.G, target, ws.counters, n_global, w_per, ws.d_rgb,
-                            ws.d_w, ws.loss_acc, ws.dzt if tc else None, self._tc.grad_scale(n_global) if tc else 1.0)
+            # tensor-core rgbnet: the dZ3 tiles are the only consumer of dL/d(rgb): the fp32 stream is not written
+            ext.sample_grad(ws.rgb, ws.s_weight, ws.s_ray, ws.G, target, ws.counters, n_global, w_per,
+                            None if tc else ws.d_rgb, ws.d_w, ws.loss_acc, ws.dzt if tc else None,
+                            self._tc.grad_scale(n_global) if tc else 1.0)
 
         if model.rgbnet is None:
             ext.rgb_direct(ws.feat, ws.counters, ws.rgb)

@@ -146,7 +146,7 @@ int dvgo_fused_ray_finish(float* rgb_acc, const float* alphainv_last, const floa
  *   loss_acc[0] += weight_rgbper * w_i * |rgb_i - target[r]|^2 / n_global
  * dzt (optional, dvgo_mlp_dztile_bytes(surv_cap) bytes): the rgbnet backward's dZ3 tiles, grad_scale * d_rgb[i] *
  * rgb_i * (1 - rgb_i) (the gradient through the sigmoid of lib/dvgo.py:539) as saturated fp16 in the operand layout,
- * rows up to the next multiple of 256 zeroed -- the input of dvgo_mlp_bwd. */
+ * rows up to the next multiple of 256 zeroed -- the input of dvgo_mlp_bwd; d_rgb may then be NULL (not written). */
 int dvgo_fused_sample_grad(const float* rgb, const float* s_weight, const int32_t* s_ray,
                            const float* G, const float* target, const int32_t* counters,
                            int64_t surv_cap, int n_global, float weight_rgbper, float* d_rgb,
