@@ -6,6 +6,7 @@
 // 2 launches (setup+scan, warp-per-ray fill); every store of the [M,...] outputs is coalesced
 // because a warp owns a contiguous run of samples of one ray.
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace dvgo {
 
@@ -59,57 +60,7 @@ __global__ void __launch_bounds__(256) ray_count_kernel(
   N_steps[r] = n_samples_of(t.t_min, t.t_max, stepdist);
 }
 
-// Single-CTA inclusive scan of int64 counts.  n_rays is 8192 per training step (64 Ki at most in
-// the configs), i.e. 2-16 trips of a 1024-thread CTA: cheaper than a multi-kernel device scan.
-constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 4;
-__global__ void __launch_bounds__(kScanThreads) inclusive_scan_i64_kernel(
-    const int64_t* __restrict__ in, int n, int64_t* __restrict__ out) {
-  __shared__ int64_t warp_sums[kScanThreads / kWarp];
-  __shared__ int64_t carry_s;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += kScanThreads * kScanItems) {
-    int64_t v[kScanItems];
-    int64_t local = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-      const int i = base + tid * kScanItems + k;
-      v[k] = (i < n) ? in[i] : 0;
-      local += v[k];
-    }
-    int64_t incl = local;  // warp inclusive scan of the per-thread sums
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int64_t up = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += up;
-    }
-    if (lane == 31) warp_sums[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-      int64_t ws = warp_sums[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int64_t up = __shfl_up_sync(0xffffffffu, ws, off);
-        if (lane >= off) ws += up;
-      }
-      warp_sums[lane] = ws;  // inclusive over warps
-    }
-    __syncthreads();
-    const int64_t carry = carry_s;
-    int64_t run = carry + (wid ? warp_sums[wid - 1] : 0) + (incl - local);
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-      const int i = base + tid * kScanItems + k;
-      run += v[k];
-      if (i < n) out[i] = run;
-    }
-    __syncthreads();
-    if (tid == kScanThreads - 1) carry_s = run;
-    __syncthreads();
-  }
-}
+// (the single-CTA inclusive scan of the int64 counts lives in scan.cuh, shared with f64_ops.cu)
 
 // ---- a4 phase 2: one warp per ray writes that ray's contiguous run of samples -----------------------
 __global__ void __launch_bounds__(256) sample_pts_fill_kernel(

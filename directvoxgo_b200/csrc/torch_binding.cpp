@@ -11,6 +11,11 @@
 // RuntimeError, shape asserts), guard the device, allocate outputs with torch, and pass raw
 // pointers + the current CUDA stream to include/dvgo_b200.h.  There is NO CPU path: a non-CUDA
 // tensor is an error, exactly as in the reference (render_utils.cpp:40).
+//
+// The three reference modules dispatch on the tensor dtype (AT_DISPATCH_FLOATING_TYPES, e.g.
+// lib/cuda/render_utils_kernel.cu:86): float32 goes to include/dvgo_b200.h, float64 to the
+// double instantiation in include/dvgo_b200_f64.h.  Any other dtype, or tensors of mixed
+// floating dtypes, is an error (the reference's data<scalar_t>() throws there too).
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
@@ -18,6 +23,7 @@
 #include <vector>
 
 #include "../../include/dvgo_b200.h"
+#include "../../include/dvgo_b200_f64.h"
 
 namespace {
 
@@ -29,6 +35,12 @@ using torch::Tensor;
   CHECK_CUDA(x);       \
   CHECK_CONTIGUOUS(x)
 #define CHECK_F32(x) TORCH_CHECK((x).scalar_type() == torch::kFloat32, #x " must be float32")
+// float32 or float64, and every further floating tensor of the call has the dtype of the first
+#define CHECK_FLT(x)                                                                              \
+  TORCH_CHECK((x).scalar_type() == torch::kFloat32 || (x).scalar_type() == torch::kFloat64, #x    \
+              " must be float32 or float64")
+#define CHECK_SAME(x, ref) \
+  TORCH_CHECK((x).scalar_type() == (ref).scalar_type(), #x " must have the dtype of " #ref)
 #define CHECK_I64(x) TORCH_CHECK((x).scalar_type() == torch::kInt64, #x " must be int64")
 #define CHECK_BOOL(x) TORCH_CHECK((x).scalar_type() == torch::kBool, #x " must be bool")
 
@@ -44,6 +56,9 @@ inline void check_rc(int rc, const char* what) {
 
 inline const float* fp(const Tensor& t) { return t.data_ptr<float>(); }
 inline float* fpm(Tensor& t) { return t.data_ptr<float>(); }
+inline bool is_f64(const Tensor& t) { return t.scalar_type() == torch::kFloat64; }
+inline const double* dp(const Tensor& t) { return t.data_ptr<double>(); }
+inline double* dpm(Tensor& t) { return t.data_ptr<double>(); }
 inline const int64_t* ip(const Tensor& t) { return t.data_ptr<int64_t>(); }
 inline const uint8_t* bp(const Tensor& t) { return reinterpret_cast<const uint8_t*>(t.data_ptr<bool>()); }
 inline uint8_t* bpm(Tensor& t) { return reinterpret_cast<uint8_t*>(t.data_ptr<bool>()); }
@@ -54,11 +69,17 @@ inline uint8_t* bpm(Tensor& t) { return reinterpret_cast<uint8_t*>(t.data_ptr<bo
 std::vector<Tensor> infer_t_minmax(Tensor rays_o, Tensor rays_d, Tensor xyz_min, Tensor xyz_max,
                                    const float near, const float far) {
   CHECK_INPUT(rays_o); CHECK_INPUT(rays_d); CHECK_INPUT(xyz_min); CHECK_INPUT(xyz_max);
-  CHECK_F32(rays_o); CHECK_F32(rays_d); CHECK_F32(xyz_min); CHECK_F32(xyz_max);
+  CHECK_FLT(rays_o); CHECK_SAME(rays_d, rays_o); CHECK_SAME(xyz_min, rays_o); CHECK_SAME(xyz_max, rays_o);
   const c10::cuda::CUDAGuard guard(rays_o.device());
   const int n_rays = rays_o.size(0);
   auto t_min = torch::empty({n_rays}, rays_o.options());
   auto t_max = torch::empty({n_rays}, rays_o.options());
+  if (is_f64(rays_o)) {
+    check_rc(dvgo_infer_t_minmax_f64(dp(rays_o), dp(rays_d), dp(xyz_min), dp(xyz_max), near, far, n_rays,
+                                     dpm(t_min), dpm(t_max), cur_stream()),
+             "infer_t_minmax<double>");
+    return {t_min, t_max};
+  }
   check_rc(dvgo_infer_t_minmax(fp(rays_o), fp(rays_d), fp(xyz_min), fp(xyz_max), near, far, n_rays,
                                fpm(t_min), fpm(t_max), cur_stream()),
            "infer_t_minmax");
@@ -66,10 +87,16 @@ std::vector<Tensor> infer_t_minmax(Tensor rays_o, Tensor rays_d, Tensor xyz_min,
 }
 
 Tensor infer_n_samples(Tensor t_min, Tensor t_max, const float stepdist) {
-  CHECK_INPUT(t_min); CHECK_INPUT(t_max); CHECK_F32(t_min); CHECK_F32(t_max);
+  CHECK_INPUT(t_min); CHECK_INPUT(t_max); CHECK_FLT(t_min); CHECK_SAME(t_max, t_min);
   const c10::cuda::CUDAGuard guard(t_min.device());
   const int n_rays = t_min.size(0);
   auto n_samples = torch::empty({n_rays}, t_min.options().dtype(torch::kInt64));
+  if (is_f64(t_min)) {
+    check_rc(dvgo_infer_n_samples_f64(dp(t_min), dp(t_max), stepdist, n_rays, n_samples.data_ptr<int64_t>(),
+                                      cur_stream()),
+             "infer_n_samples<double>");
+    return n_samples;
+  }
   check_rc(dvgo_infer_n_samples(fp(t_min), fp(t_max), stepdist, n_rays,
                                 n_samples.data_ptr<int64_t>(), cur_stream()),
            "infer_n_samples");
@@ -78,11 +105,17 @@ Tensor infer_n_samples(Tensor t_min, Tensor t_max, const float stepdist) {
 
 std::vector<Tensor> infer_ray_start_dir(Tensor rays_o, Tensor rays_d, Tensor t_min) {
   CHECK_INPUT(rays_o); CHECK_INPUT(rays_d); CHECK_INPUT(t_min);
-  CHECK_F32(rays_o); CHECK_F32(rays_d); CHECK_F32(t_min);
+  CHECK_FLT(rays_o); CHECK_SAME(rays_d, rays_o); CHECK_SAME(t_min, rays_o);
   const c10::cuda::CUDAGuard guard(rays_o.device());
   const int n_rays = rays_o.size(0);
   auto rays_start = torch::empty_like(rays_o);
   auto rays_dir = torch::empty_like(rays_o);
+  if (is_f64(rays_o)) {
+    check_rc(dvgo_infer_ray_start_dir_f64(dp(rays_o), dp(rays_d), dp(t_min), n_rays, dpm(rays_start),
+                                          dpm(rays_dir), cur_stream()),
+             "infer_ray_start_dir<double>");
+    return {rays_start, rays_dir};
+  }
   check_rc(dvgo_infer_ray_start_dir(fp(rays_o), fp(rays_d), fp(t_min), n_rays, fpm(rays_start),
                                     fpm(rays_dir), cur_stream()),
            "infer_ray_start_dir");
@@ -92,7 +125,7 @@ std::vector<Tensor> infer_ray_start_dir(Tensor rays_o, Tensor rays_d, Tensor t_m
 std::vector<Tensor> sample_pts_on_rays(Tensor rays_o, Tensor rays_d, Tensor xyz_min, Tensor xyz_max,
                                        const float near, const float far, const float stepdist) {
   CHECK_INPUT(rays_o); CHECK_INPUT(rays_d); CHECK_INPUT(xyz_min); CHECK_INPUT(xyz_max);
-  CHECK_F32(rays_o); CHECK_F32(rays_d); CHECK_F32(xyz_min); CHECK_F32(xyz_max);
+  CHECK_FLT(rays_o); CHECK_SAME(rays_d, rays_o); CHECK_SAME(xyz_min, rays_o); CHECK_SAME(xyz_max, rays_o);
   TORCH_CHECK(rays_o.dim() == 2 && rays_o.size(1) == 3, "rays_o must be [N,3]");
   TORCH_CHECK(rays_d.sizes() == rays_o.sizes(), "rays_d must match rays_o");
   const c10::cuda::CUDAGuard guard(rays_o.device());
@@ -104,6 +137,21 @@ std::vector<Tensor> sample_pts_on_rays(Tensor rays_o, Tensor rays_d, Tensor xyz_
   auto N_steps = torch::empty({n_rays}, iopt);
   auto cumsum = torch::empty({n_rays}, iopt);
   int64_t total = 0;
+  if (is_f64(rays_o)) {
+    check_rc(dvgo_sample_pts_count_f64(dp(rays_o), dp(rays_d), dp(xyz_min), dp(xyz_max), near, far, stepdist,
+                                       n_rays, dpm(t_min), dpm(t_max), N_steps.data_ptr<int64_t>(),
+                                       cumsum.data_ptr<int64_t>(), &total, cur_stream()),
+             "sample_pts_count<double>");
+    auto rays_pts = torch::empty({total, 3}, fopt);
+    auto mask_outbbox = torch::empty({total}, fopt.dtype(torch::kBool));
+    auto ray_id = torch::empty({total}, iopt);
+    auto step_id = torch::empty({total}, iopt);
+    check_rc(dvgo_sample_pts_fill_f64(dp(rays_o), dp(rays_d), dp(xyz_min), dp(xyz_max), dp(t_min), ip(cumsum),
+                                      stepdist, n_rays, total, dpm(rays_pts), bpm(mask_outbbox),
+                                      ray_id.data_ptr<int64_t>(), step_id.data_ptr<int64_t>(), cur_stream()),
+             "sample_pts_fill<double>");
+    return {rays_pts, mask_outbbox, ray_id, step_id, N_steps, t_min, t_max};
+  }
   check_rc(dvgo_sample_pts_count(fp(rays_o), fp(rays_d), fp(xyz_min), fp(xyz_max), near, far,
                                  stepdist, n_rays, fpm(t_min), fpm(t_max),
                                  N_steps.data_ptr<int64_t>(), cumsum.data_ptr<int64_t>(), &total,
@@ -124,12 +172,18 @@ std::vector<Tensor> sample_pts_on_rays(Tensor rays_o, Tensor rays_d, Tensor xyz_
 std::vector<Tensor> sample_ndc_pts_on_rays(Tensor rays_o, Tensor rays_d, Tensor xyz_min,
                                            Tensor xyz_max, const int N_samples) {
   CHECK_INPUT(rays_o); CHECK_INPUT(rays_d); CHECK_INPUT(xyz_min); CHECK_INPUT(xyz_max);
-  CHECK_F32(rays_o); CHECK_F32(rays_d); CHECK_F32(xyz_min); CHECK_F32(xyz_max);
+  CHECK_FLT(rays_o); CHECK_SAME(rays_d, rays_o); CHECK_SAME(xyz_min, rays_o); CHECK_SAME(xyz_max, rays_o);
   TORCH_CHECK(rays_o.dim() == 2 && rays_o.size(1) == 3, "rays_o must be [N,3]");
   const c10::cuda::CUDAGuard guard(rays_o.device());
   const int n_rays = rays_o.size(0);
   auto rays_pts = torch::empty({n_rays, N_samples, 3}, rays_o.options());
   auto mask_outbbox = torch::empty({n_rays, N_samples}, rays_o.options().dtype(torch::kBool));
+  if (is_f64(rays_o)) {
+    check_rc(dvgo_sample_ndc_pts_on_rays_f64(dp(rays_o), dp(rays_d), dp(xyz_min), dp(xyz_max), N_samples, n_rays,
+                                             dpm(rays_pts), bpm(mask_outbbox), cur_stream()),
+             "sample_ndc_pts_on_rays<double>");
+    return {rays_pts, mask_outbbox};
+  }
   check_rc(dvgo_sample_ndc_pts_on_rays(fp(rays_o), fp(rays_d), fp(xyz_min), fp(xyz_max), N_samples,
                                        n_rays, fpm(rays_pts), bpm(mask_outbbox), cur_stream()),
            "sample_ndc_pts_on_rays");
@@ -138,12 +192,18 @@ std::vector<Tensor> sample_ndc_pts_on_rays(Tensor rays_o, Tensor rays_d, Tensor 
 
 Tensor maskcache_lookup(Tensor world, Tensor xyz, Tensor xyz2ijk_scale, Tensor xyz2ijk_shift) {
   CHECK_INPUT(world); CHECK_INPUT(xyz); CHECK_INPUT(xyz2ijk_scale); CHECK_INPUT(xyz2ijk_shift);
-  CHECK_BOOL(world); CHECK_F32(xyz); CHECK_F32(xyz2ijk_scale); CHECK_F32(xyz2ijk_shift);
+  CHECK_BOOL(world); CHECK_FLT(xyz); CHECK_SAME(xyz2ijk_scale, xyz); CHECK_SAME(xyz2ijk_shift, xyz);
   TORCH_CHECK(world.dim() == 3, "world must be [X,Y,Z]");
   TORCH_CHECK(xyz.dim() == 2 && xyz.size(1) == 3, "xyz must be [P,3]");
   const c10::cuda::CUDAGuard guard(xyz.device());
   const int64_t n_pts = xyz.size(0);
   auto out = torch::empty({n_pts}, xyz.options().dtype(torch::kBool));
+  if (is_f64(xyz)) {
+    check_rc(dvgo_maskcache_lookup_f64(bp(world), dp(xyz), dp(xyz2ijk_scale), dp(xyz2ijk_shift), world.size(0),
+                                       world.size(1), world.size(2), n_pts, bpm(out), cur_stream()),
+             "maskcache_lookup<double>");
+    return out;
+  }
   check_rc(dvgo_maskcache_lookup(bp(world), fp(xyz), fp(xyz2ijk_scale), fp(xyz2ijk_shift),
                                  world.size(0), world.size(1), world.size(2), n_pts, bpm(out),
                                  cur_stream()),
@@ -152,11 +212,17 @@ Tensor maskcache_lookup(Tensor world, Tensor xyz, Tensor xyz2ijk_scale, Tensor x
 }
 
 std::vector<Tensor> raw2alpha(Tensor density, const float shift, const float interval) {
-  CHECK_INPUT(density); CHECK_F32(density);
+  CHECK_INPUT(density); CHECK_FLT(density);
   TORCH_CHECK(density.dim() == 1, "density must be 1-D");
   const c10::cuda::CUDAGuard guard(density.device());
   auto exp_d = torch::empty_like(density);
   auto alpha = torch::empty_like(density);
+  if (is_f64(density)) {
+    check_rc(dvgo_raw2alpha_f64(dp(density), shift, interval, density.size(0), dpm(exp_d), dpm(alpha),
+                                cur_stream()),
+             "raw2alpha<double>");
+    return {exp_d, alpha};
+  }
   check_rc(dvgo_raw2alpha(fp(density), shift, interval, density.size(0), fpm(exp_d), fpm(alpha),
                           cur_stream()),
            "raw2alpha");
@@ -164,10 +230,15 @@ std::vector<Tensor> raw2alpha(Tensor density, const float shift, const float int
 }
 
 Tensor raw2alpha_backward(Tensor exp, Tensor grad_back, const float interval) {
-  CHECK_INPUT(exp); CHECK_INPUT(grad_back); CHECK_F32(exp); CHECK_F32(grad_back);
+  CHECK_INPUT(exp); CHECK_INPUT(grad_back); CHECK_FLT(exp); CHECK_SAME(grad_back, exp);
   TORCH_CHECK(exp.numel() == grad_back.numel(), "exp and grad_back must have the same numel");
   const c10::cuda::CUDAGuard guard(exp.device());
   auto grad = torch::empty_like(exp);
+  if (is_f64(exp)) {
+    check_rc(dvgo_raw2alpha_backward_f64(dp(exp), dp(grad_back), interval, exp.numel(), dpm(grad), cur_stream()),
+             "raw2alpha_backward<double>");
+    return grad;
+  }
   check_rc(dvgo_raw2alpha_backward(fp(exp), fp(grad_back), interval, exp.numel(), fpm(grad),
                                    cur_stream()),
            "raw2alpha_backward");
@@ -175,7 +246,7 @@ Tensor raw2alpha_backward(Tensor exp, Tensor grad_back, const float interval) {
 }
 
 std::vector<Tensor> alpha2weight(Tensor alpha, Tensor ray_id, const int n_rays) {
-  CHECK_INPUT(alpha); CHECK_INPUT(ray_id); CHECK_F32(alpha); CHECK_I64(ray_id);
+  CHECK_INPUT(alpha); CHECK_INPUT(ray_id); CHECK_FLT(alpha); CHECK_I64(ray_id);
   TORCH_CHECK(alpha.dim() == 1 && ray_id.dim() == 1 && alpha.sizes() == ray_id.sizes(),
               "alpha and ray_id must be 1-D of equal length");
   const c10::cuda::CUDAGuard guard(alpha.device());
@@ -185,6 +256,12 @@ std::vector<Tensor> alpha2weight(Tensor alpha, Tensor ray_id, const int n_rays) 
   auto alphainv_last = torch::empty({n_rays}, alpha.options());
   auto i_start = torch::empty({n_rays}, alpha.options().dtype(torch::kInt64));
   auto i_end = torch::empty({n_rays}, alpha.options().dtype(torch::kInt64));
+  if (is_f64(alpha)) {
+    check_rc(dvgo_alpha2weight_f64(dp(alpha), ip(ray_id), n_rays, n_pts, dpm(weight), dpm(T), dpm(alphainv_last),
+                                   i_start.data_ptr<int64_t>(), i_end.data_ptr<int64_t>(), cur_stream()),
+             "alpha2weight<double>");
+    return {weight, T, alphainv_last, i_start, i_end};
+  }
   check_rc(dvgo_alpha2weight(fp(alpha), ip(ray_id), n_rays, n_pts, fpm(weight), fpm(T),
                              fpm(alphainv_last), i_start.data_ptr<int64_t>(),
                              i_end.data_ptr<int64_t>(), cur_stream()),
@@ -197,10 +274,17 @@ Tensor alpha2weight_backward(Tensor alpha, Tensor weight, Tensor T, Tensor alpha
                              Tensor grad_last) {
   CHECK_INPUT(alpha); CHECK_INPUT(weight); CHECK_INPUT(T); CHECK_INPUT(alphainv_last);
   CHECK_INPUT(i_start); CHECK_INPUT(i_end); CHECK_INPUT(grad_weights); CHECK_INPUT(grad_last);
-  CHECK_F32(alpha); CHECK_F32(weight); CHECK_F32(T); CHECK_F32(alphainv_last);
-  CHECK_I64(i_start); CHECK_I64(i_end); CHECK_F32(grad_weights); CHECK_F32(grad_last);
+  CHECK_FLT(alpha); CHECK_SAME(weight, alpha); CHECK_SAME(T, alpha); CHECK_SAME(alphainv_last, alpha);
+  CHECK_I64(i_start); CHECK_I64(i_end); CHECK_SAME(grad_weights, alpha); CHECK_SAME(grad_last, alpha);
   const c10::cuda::CUDAGuard guard(alpha.device());
   auto grad = torch::empty_like(alpha);
+  if (is_f64(alpha)) {
+    check_rc(dvgo_alpha2weight_backward_f64(dp(alpha), dp(weight), dp(T), dp(alphainv_last), ip(i_start),
+                                            ip(i_end), n_rays, alpha.numel(), dp(grad_weights), dp(grad_last),
+                                            dpm(grad), cur_stream()),
+             "alpha2weight_backward<double>");
+    return grad;
+  }
   check_rc(dvgo_alpha2weight_backward(fp(alpha), fp(weight), fp(T), fp(alphainv_last), ip(i_start),
                                       ip(i_end), n_rays, alpha.numel(), fp(grad_weights),
                                       fp(grad_last), fpm(grad), cur_stream()),
@@ -213,10 +297,16 @@ Tensor alpha2weight_backward(Tensor alpha, Tensor weight, Tensor T, Tensor alpha
 // ------------------------------------------------------------------------------------------------
 void total_variation_add_grad(Tensor param, Tensor grad, float wx, float wy, float wz,
                               bool dense_mode) {
-  CHECK_INPUT(param); CHECK_INPUT(grad); CHECK_F32(param); CHECK_F32(grad);
+  CHECK_INPUT(param); CHECK_INPUT(grad); CHECK_FLT(param); CHECK_SAME(grad, param);
   TORCH_CHECK(param.dim() == 5, "param must be [1,C,X,Y,Z]");
   TORCH_CHECK(param.sizes() == grad.sizes(), "param and grad must have the same shape");
   const c10::cuda::CUDAGuard guard(param.device());
+  if (is_f64(param)) {
+    check_rc(dvgo_total_variation_add_grad_f64(dp(param), dpm(grad), wx, wy, wz, dense_mode ? 1 : 0, param.numel(),
+                                               param.size(2), param.size(3), param.size(4), cur_stream()),
+             "total_variation_add_grad<double>");
+    return;
+  }
   check_rc(dvgo_total_variation_add_grad(fp(param), fpm(grad), wx, wy, wz, dense_mode ? 1 : 0,
                                          param.numel(), param.size(2), param.size(3), param.size(4),
                                          cur_stream()),
@@ -225,7 +315,7 @@ void total_variation_add_grad(Tensor param, Tensor grad, float wx, float wy, flo
 
 #define ADAM_CHECKS()                                                                       \
   CHECK_INPUT(param); CHECK_INPUT(grad); CHECK_INPUT(exp_avg); CHECK_INPUT(exp_avg_sq);     \
-  CHECK_F32(param); CHECK_F32(grad); CHECK_F32(exp_avg); CHECK_F32(exp_avg_sq);             \
+  CHECK_FLT(param); CHECK_SAME(grad, param); CHECK_SAME(exp_avg, param); CHECK_SAME(exp_avg_sq, param); \
   TORCH_CHECK(param.numel() == grad.numel() && param.numel() == exp_avg.numel() &&          \
                   param.numel() == exp_avg_sq.numel(),                                      \
               "param, grad, exp_avg, exp_avg_sq must have the same numel");                 \
@@ -234,6 +324,12 @@ void total_variation_add_grad(Tensor param, Tensor grad, float wx, float wy, flo
 void adam_upd(Tensor param, Tensor grad, Tensor exp_avg, Tensor exp_avg_sq, int step, float beta1,
               float beta2, float lr, float eps) {
   ADAM_CHECKS();
+  if (is_f64(param)) {
+    check_rc(dvgo_adam_upd_f64(dpm(param), dp(grad), dpm(exp_avg), dpm(exp_avg_sq), param.numel(), step, beta1,
+                               beta2, lr, eps, cur_stream()),
+             "adam_upd<double>");
+    return;
+  }
   check_rc(dvgo_adam_upd(fpm(param), fp(grad), fpm(exp_avg), fpm(exp_avg_sq), param.numel(), step,
                          beta1, beta2, lr, eps, cur_stream()),
            "adam_upd");
@@ -242,6 +338,12 @@ void adam_upd(Tensor param, Tensor grad, Tensor exp_avg, Tensor exp_avg_sq, int 
 void masked_adam_upd(Tensor param, Tensor grad, Tensor exp_avg, Tensor exp_avg_sq, int step,
                      float beta1, float beta2, float lr, float eps) {
   ADAM_CHECKS();
+  if (is_f64(param)) {
+    check_rc(dvgo_masked_adam_upd_f64(dpm(param), dp(grad), dpm(exp_avg), dpm(exp_avg_sq), param.numel(), step,
+                                      beta1, beta2, lr, eps, cur_stream()),
+             "masked_adam_upd<double>");
+    return;
+  }
   check_rc(dvgo_masked_adam_upd(fpm(param), fp(grad), fpm(exp_avg), fpm(exp_avg_sq), param.numel(),
                                 step, beta1, beta2, lr, eps, cur_stream()),
            "masked_adam_upd");
@@ -250,8 +352,14 @@ void masked_adam_upd(Tensor param, Tensor grad, Tensor exp_avg, Tensor exp_avg_s
 void adam_upd_with_perlr(Tensor param, Tensor grad, Tensor exp_avg, Tensor exp_avg_sq, Tensor perlr,
                          int step, float beta1, float beta2, float lr, float eps) {
   ADAM_CHECKS();
-  CHECK_INPUT(perlr); CHECK_F32(perlr);
+  CHECK_INPUT(perlr); CHECK_SAME(perlr, param);
   TORCH_CHECK(perlr.numel() == param.numel(), "perlr must match param");
+  if (is_f64(param)) {
+    check_rc(dvgo_adam_upd_with_perlr_f64(dpm(param), dp(grad), dpm(exp_avg), dpm(exp_avg_sq), dp(perlr),
+                                          param.numel(), step, beta1, beta2, lr, eps, cur_stream()),
+             "adam_upd_with_perlr<double>");
+    return;
+  }
   check_rc(dvgo_adam_upd_with_perlr(fpm(param), fp(grad), fpm(exp_avg), fpm(exp_avg_sq), fp(perlr),
                                     param.numel(), step, beta1, beta2, lr, eps, cur_stream()),
            "adam_upd_with_perlr");

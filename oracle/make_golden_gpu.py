@@ -3,9 +3,12 @@ from the unmodified /root/reference/lib/cuda sources) on a B200, as golden vecto
 oracle and the product.  Run on the GPU box:
 
     python -m oracle.make_golden_gpu gpurun_out/golden/ref_gpu_ops.npz
+    python -m oracle.make_golden_gpu gpurun_out/golden/ref_gpu_ops_f64.npz f64
 
-then copy the file to tests/golden/.  Inputs are seeded and stored in the file, so the fixture is
-self-contained.  Sizes are small (a few hundred rays) to keep the fixture < 1 MB.
+then copy the files to tests/golden/.  The second form records the reference's DOUBLE instantiation
+(AT_DISPATCH_FLOATING_TYPES with float64 tensors) on the same seeded inputs, widened to float64 and scaled
+by (1 + 2^-30) so that they are not float32-representable; it pins oracle/dvgo_oracle_f64.c.
+Inputs are seeded and stored in the file, so the fixture is self-contained.  Sizes are small (a few hundred rays) to keep the fixture < 1 MB.
 """
 import os
 import sys
@@ -18,7 +21,7 @@ sys.path.insert(0, os.path.join(HERE, "_ref"))
 sys.path.insert(0, os.path.join(HERE, ".."))
 
 
-def main(out_path):
+def main(out_path, f64=False):
     import ref_adam_upd_cuda as ad
     import ref_render_utils_cuda as ru
     import ref_total_variation_cuda as tv
@@ -27,6 +30,14 @@ def main(out_path):
     dev = "cuda"
     c = lambda t: t.detach().cpu().numpy()
     save = {}
+    if f64:
+        # every floating input of the run below goes through Tensor.to(dev): widen it there
+        _to = torch.Tensor.to
+
+        def widen(t, *a, **k):
+            t = _to(t, *a, **k)
+            return _to(t, torch.float64) * (1.0 + 2.0 ** -30) if t.dtype == torch.float32 else t
+        torch.Tensor.to = widen
 
     lo = torch.tensor([-1.0, -0.9, -0.8]).to(dev)
     hi = torch.tensor([1.0, 0.9, 0.8]).to(dev)
@@ -87,14 +98,18 @@ def main(out_path):
     gr = torch.randn(N, generator=g)
     gr[torch.rand(N, generator=g) < 0.4] = 0
     perlr = torch.rand(N, generator=g)
+    p0, m0, v0, gr, perlr = (t.to(dev) for t in (p0, m0, v0, gr, perlr))   # (widened here in the f64 run)
     save.update(adam_p=c(p0), adam_m=c(m0), adam_v=c(v0), adam_g=c(gr), adam_perlr=c(perlr))
     for name in ("adam_upd", "masked_adam_upd", "adam_upd_with_perlr"):
-        p, m, v = p0.clone().to(dev), m0.clone().to(dev), v0.clone().to(dev)
+        p, m, v = p0.clone(), m0.clone(), v0.clone()
         for step in (1, 2, 3):
-            args = (p, gr.to(dev), m, v) + ((perlr.to(dev),) if name == "adam_upd_with_perlr" else ())
+            args = (p, gr, m, v) + ((perlr,) if name == "adam_upd_with_perlr" else ())
             getattr(ad, name)(*args, step, 0.9, 0.99, 0.1, 1e-8)
         save["adam_out_p_" + name], save["adam_out_m_" + name], save["adam_out_v_" + name] = c(p), c(m), c(v)
 
+    if f64:
+        torch.Tensor.to = _to
+        assert save["rays_pts"].dtype == np.float64 and save["adam_out_p_adam_upd"].dtype == np.float64
     torch.cuda.synchronize()
     os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
     np.savez_compressed(out_path, **save)
@@ -102,4 +117,4 @@ def main(out_path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden/ref_gpu_ops.npz")
+    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden/ref_gpu_ops.npz", f64="f64" in sys.argv[2:])

@@ -20,10 +20,10 @@ _LIB_PATH = os.path.join(_HERE, "libdvgo_oracle.so")
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "dvgo_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(src) > os.path.getmtime(_LIB_PATH):
+    srcs = [os.path.join(_HERE, f) for f in ("dvgo_oracle.c", "dvgo_oracle_f64.c")]
+    if force or not os.path.exists(_LIB_PATH) or max(map(os.path.getmtime, srcs)) > os.path.getmtime(_LIB_PATH):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off",
-                               "-fno-fast-math", "-o", _LIB_PATH, src, "-lm"])
+                               "-fno-fast-math", "-o", _LIB_PATH] + srcs + ["-lm"])
     return _LIB_PATH
 
 
@@ -36,6 +36,7 @@ def lib():
         build()
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.orc_sample_pts_count.restype = ctypes.c_int64
+        _lib.orc64_sample_pts_count.restype = ctypes.c_int64
         _lib.orc_adam_step_size.restype = ctypes.c_float
     return _lib
 
