@@ -3,9 +3,10 @@
 //
 // The reference's alpha2weight runs ONE THREAD PER RAY through a serial loop of dependent
 // float*double multiplies (:447-455), with stride-M uncoalesced accesses across the warp.
-// Here one WARP owns a ray: 32 consecutive samples are loaded coalesced, the per-sample factors
-// (1 - alpha + 1e-10) are combined by a shuffle-based inclusive product scan in double (the
-// reference forms each factor in double, :450, but re-rounds its running product to float per sample), and the early stop (T < 1e-3) is found with a ballot.
+// Here one WARP owns a ray: 32 consecutive samples are loaded coalesced and the warp replays the
+// reference's per-sample recurrence (float T_cum re-rounded after every double multiply) in
+// lock-step from shuffled factors, so T, the weights and the early-stop index are bit-exact.
+// (The fused trainer's march kernels keep a double product scan instead: tolerance class)
 #include "common.cuh"
 
 namespace dvgo {
@@ -61,12 +62,16 @@ __global__ void __launch_bounds__(256) a2w_bounds_kernel(const int64_t* __restri
   if (i == n_pts - 1) i_end[r] = n_pts;
 }
 
-__device__ __forceinline__ double shfl_up_f64(double v, int off) {
-  return __shfl_up_sync(0xffffffffu, v, off);
-}
-
 // One warp per ray.  Writes weight/T for EVERY sample of the ray's segment (fills 0 / 1 after the
 // early stop, :478-479), the stop index into i_end (:456) and alphainv_last (:457).
+//
+// The reference re-rounds its running transmittance to float after every sample (float T_cum, :447:
+// T_cum = (float)((double)T_cum * (1. - alpha + 1e-10))), so the recurrence is inherently serial and
+// a product scan cannot reproduce its roundings.  Here 32 consecutive alphas are loaded coalesced
+// and all lanes then replay the 32 dependent updates TOGETHER from shuffled factors: every lane
+// holds the same T_cum and lane j keeps the value it saw at its own sample.  Bit-exact with the
+// reference (T, weights, alphainv_last and the stop index), coalesced loads / stores, and the
+// serial chain is 32 steps per chunk instead of one thread walking the whole ray.
 __global__ void __launch_bounds__(256) alpha2weight_kernel(const float* __restrict__ alpha,
                                                            int n_rays, float* __restrict__ weight,
                                                            float* __restrict__ T,
@@ -79,62 +84,50 @@ __global__ void __launch_bounds__(256) alpha2weight_kernel(const float* __restri
     const int64_t i_s = i_start[r];
     const int64_t i_e_max = i_end[r];
     if (i_e_max <= i_s) continue;  // no samples: keeps alphainv_last = 1, i_end = i_start (= 0)
-    double carry = 1.0;            // product of all factors before this chunk (T_cum at chunk start)
+    float T_cum = 1.f;             // :447
     int64_t stop = -1;             // index of the sample whose update drove T below 1e-3
-    float last_T = 1.f;
-    for (int64_t base = i_s; base < i_e_max; base += 32) {
+    for (int64_t base = i_s; base < i_e_max && stop < 0; base += 32) {
       const int64_t i = base + lane;
       const bool valid = i < i_e_max;
       const float a = valid ? alpha[i] : 0.f;
-      // :450  T_cum *= (1. - alpha + 1e-10): the reference forms the factor in double but re-rounds T_cum to float after
-      // every sample; here the running product itself stays in double and is rounded once per output (rel. 5e-6 on T /
-      // weights, stop index equal except at ties T ~ 1e-3: the tolerance class stated in DESIGN.md section 4)
-      const double f = valid ? ((1.0 - static_cast<double>(a)) + 1e-10) : 1.0;
-      double incl = f;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const double up = shfl_up_f64(incl, off);
-        if (lane >= off) incl *= up;
+      // :450  (1. - alpha + 1e-10) in double
+      const double f = __dadd_rn(__dsub_rn(1.0, static_cast<double>(a)), 1e-10);
+      const int n_valid = static_cast<int>(min(static_cast<int64_t>(32), i_e_max - base));
+      float T_mine = 1.f;
+      int first = 32;  // lane whose update drove T below 1e-3
+      for (int j = 0; j < n_valid; ++j) {
+        const double fj = __shfl_sync(0xffffffffu, f, j);
+        if (lane == j) T_mine = T_cum;
+        T_cum = __double2float_rn(__dmul_rn(static_cast<double>(T_cum), fj));  // :450
+        if (static_cast<double>(T_cum) < 1e-3) { first = j; break; }           // :451 (uniform across the warp)
       }
-      double excl = shfl_up_f64(incl, 1);
-      if (lane == 0) excl = 1.0;
-      const float T_before = static_cast<float>(carry * excl);  // T_cum when sample i is visited
-      const float T_after = static_cast<float>(carry * incl);   // T_cum after its update
-      // :451  if (T_cum < 1e-3) -> stop after this sample (comparison in double of the float value)
-      const bool hit = valid && (static_cast<double>(T_after) < 1e-3);
-      const unsigned hits = __ballot_sync(0xffffffffu, hit);
-      const int first = hits ? (__ffs(hits) - 1) : 32;
       if (valid) {
         if (lane <= first) {
-          T[i] = T_before;                 // :448
-          weight[i] = fmul(T_before, a);   // :449
+          T[i] = T_mine;                // :448
+          weight[i] = fmul(T_mine, a);  // :449
         } else {
-          T[i] = 1.f;                      // fills of :478-479
+          T[i] = 1.f;                   // fills of :478-479
           weight[i] = 0.f;
         }
       }
-      if (hits) {
+      if (first < 32) {
         stop = base + first;
-        last_T = __shfl_sync(0xffffffffu, T_after, first);
         // every later sample of the segment keeps the fills
         for (int64_t j = base + 32 + lane; j < i_e_max; j += 32) { T[j] = 1.f; weight[j] = 0.f; }
-        break;
       }
-      const int n_valid = static_cast<int>(min(static_cast<int64_t>(32), i_e_max - base));
-      carry = carry * __shfl_sync(0xffffffffu, incl, n_valid - 1);
-      last_T = static_cast<float>(carry);
     }
     if (lane == 0) {
       i_end[r] = (stop >= 0) ? stop + 1 : i_e_max;  // :452-456
-      alphainv_last[r] = last_T;                    // :457
+      alphainv_last[r] = T_cum;                     // :457
     }
   }
 }
 
 // ---- a9 backward ---------------------------------------------------------------------------------
-// grad[i] = gw[i]*T[i] - back_i / (1 - alpha[i] + 1e-10),  back_i = g_last*alphainv_last +
-// sum_{j>i} gw[j]*w[j]  (:525-529).  One warp per ray walks [i_start, i_end) from the far end in
-// chunks of 32 with a shuffle suffix sum.
+// grad[i] = gw[i]*T[i] - back_i / (1 - alpha[i] + 1e-10), back_i = float accumulator started at
+// g_last*alphainv_last and advanced by back = fma(gw[j], w[j], back) from the far end (:522-529; the
+// FFMA is what the reference's SASS shows).  Same replay scheme as the forward: one warp per ray walks
+// [i_start, i_end) from the far end in chunks of 32; bit-exact with the reference.
 __global__ void __launch_bounds__(256) alpha2weight_backward_kernel(
     const float* __restrict__ alpha, const float* __restrict__ weight, const float* __restrict__ T,
     const float* __restrict__ alphainv_last, const int64_t* __restrict__ i_start,
@@ -146,30 +139,27 @@ __global__ void __launch_bounds__(256) alpha2weight_backward_kernel(
     const int64_t i_s = i_start[r];
     const int64_t i_e = i_end[r];
     if (i_e <= i_s) continue;
-    float back = fmul(grad_last[r], alphainv_last[r]);  // :525
+    float back = fmul(grad_last[r], alphainv_last[r]);  // :522
     for (int64_t hi = i_e; hi > i_s; hi -= 32) {
-      // lane 0 takes the farthest sample of the chunk so that shfl_up gives "everything farther"
-      const int64_t i = hi - 1 - lane;
+      const int64_t i = hi - 1 - lane;  // lane 0 = the farthest sample of the chunk
       const bool valid = i >= i_s;
       const float gw = valid ? grad_weights[i] : 0.f;
-      const float term = valid ? fmul(gw, weight[i]) : 0.f;  // :528
-      float incl = term;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const float up = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += up;
+      const float w = valid ? weight[i] : 0.f;
+      const int n_valid = static_cast<int>(min(static_cast<int64_t>(32), hi - i_s));
+      float back_mine = 0.f;
+      for (int j = 0; j < n_valid; ++j) {
+        const float gwj = __shfl_sync(0xffffffffu, gw, j);
+        const float wj = __shfl_sync(0xffffffffu, w, j);
+        if (lane == j) back_mine = back;
+        back = fma_(gwj, wj, back);  // :525
       }
-      float excl = __shfl_up_sync(0xffffffffu, incl, 1);  // sum over samples farther than i
-      if (lane == 0) excl = 0.f;
-      const float back_i = back + excl;
       if (valid) {
         const float gwT = fmul(gw, T[i]);
         const float one_m_a = fsub(1.f, alpha[i]);
-        grad[i] = static_cast<float>(static_cast<double>(gwT) -
-                                     static_cast<double>(back_i) /
-                                         (static_cast<double>(one_m_a) + 1e-10));  // :527
+        grad[i] = __double2float_rn(__dsub_rn(static_cast<double>(gwT),
+                                              __ddiv_rn(static_cast<double>(back_mine),
+                                                        __dadd_rn(static_cast<double>(one_m_a), 1e-10))));  // :524
       }
-      back += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
 }

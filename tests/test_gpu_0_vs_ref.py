@@ -69,19 +69,17 @@ def test_alpha_ops_vs_reference_kernels(pkg, ref_gpu):
         alpha = (torch.rand(n_pts, generator=g) * amax).to(DEV)
         w_r, T_r, l_r, s_r, e_r2 = ref_gpu.render_utils_cuda.alpha2weight(alpha, rid, n_rays)
         w, T, l, s, e2 = pkg.render_utils_cuda.alpha2weight(alpha, rid, n_rays)
-        assert torch.equal(s, s_r)
-        same = (e2 == e_r2)
-        assert same.float().mean() > 0.995         # i_end equal except ties at T ~ 1e-3
-        keep = same[rid]
-        # stated tolerance: rel 5e-6 (the reference rounds T to fp32 at each of up to ~400 steps)
-        np.testing.assert_allclose(to_np(T[keep]), to_np(T_r[keep]), rtol=5e-6, atol=1e-9)
-        np.testing.assert_allclose(to_np(w[keep]), to_np(w_r[keep]), rtol=5e-6, atol=1e-9)
-        np.testing.assert_allclose(to_np(l[same]), to_np(l_r[same]), rtol=5e-6, atol=1e-9)
+        # bit-exact incl. the early-stop index: the warp replays the reference's float T_cum recurrence sample by sample
+        for name, x, y in (("i_start", s, s_r), ("i_end", e2, e_r2), ("T", T, T_r), ("weights", w, w_r),
+                           ("alphainv_last", l, l_r)):
+            assert torch.equal(x, y), (amax, name)
+        if amax > 0.1:      # the inputs must exercise the early stop
+            assert int(((e_r2 - s_r) < torch.bincount(rid, minlength=n_rays)).sum()) > 100
         gw = torch.randn(n_pts, generator=g).to(DEV)
         gl = torch.randn(n_rays, generator=g).to(DEV)
         g_r = ref_gpu.render_utils_cuda.alpha2weight_backward(alpha, w_r, T_r, l_r, s_r, e_r2, n_rays, gw, gl)
         g_g = pkg.render_utils_cuda.alpha2weight_backward(alpha, w_r, T_r, l_r, s_r, e_r2, n_rays, gw, gl)
-        assert rel_to_max(g_g, g_r) < 2e-5
+        assert torch.equal(g_g, g_r), amax
 
 
 def test_tv_and_adam_vs_reference_kernels(pkg, ref_gpu):

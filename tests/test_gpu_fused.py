@@ -272,7 +272,10 @@ def test_fused_full_size_invariants():
     assert int(ws.counters[1]) == 0 and 2_000_000 < m4 < 3_000_000
     with torch.no_grad():
         ref = m(ro, rd, vd, global_step=0, **rk)
-    assert m4 == ref["ray_id"].numel()
+    # The op-by-op path's alpha2weight is bit-exact with the reference (float T_cum re-rounded per sample); the fused
+    # march keeps a double product scan (T rel 5e-6), so a sample whose weight sits within that
+    # rounding of the 1e-4 threshold may fall on the other side: a handful out of 2.4 M at most.
+    assert abs(m4 - ref["ray_id"].numel()) <= 4
     wsum = torch.zeros(8192, device=DEV).index_add_(0, ws.s_ray[:m4].long(), ws.s_weight[:m4])
     # samples below the weight threshold (1e-4) are dropped from the stream: allow their mass
     n_steps = ws.n_steps[:8192].float()
