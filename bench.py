@@ -383,6 +383,26 @@ def ncu_traffic():
                                   "workload": d.get("workload")}
 
 
+def sampling_hbm(hbm_peak):
+    """BASELINE metric (iii): achieved HBM GB/s of the sampling (gather) kernels, taken from ncu as SURVEY.md section
+    8(d) defines it -- (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration per launch, from the newest
+    committed capture of this command (never from a run under a profiler of THIS process: the table is read, not
+    measured here)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None
+    d = json.load(open(files[-1]))
+    out = {"unit": "GB/s", "source": {"file": os.path.relpath(files[-1], ROOT), "commit": d.get("commit")},
+           "definition": "ncu dram bytes (read + write) per launch / ncu gpu__time_duration, cold-cache serialised launches"}
+    for name, k in d.get("per_kernel", {}).items():
+        if name.startswith(("k0_gather", "march_fwd")) and k.get("time_us"):
+            gbs = (k["dram_rd"] + k["dram_wr"]) / (k["time_us"] * 1e-6) / 1e9
+            out[name] = {"achieved": gbs, "frac_of_measured_hbm_peak": gbs / hbm_peak, "dram_bytes_per_launch": k["dram_rd"] + k["dram_wr"],
+                         "time_us": k["time_us"], "l1_lsu_wavefront_pct": k.get("l1_lsu_wavefront_pct"),
+                         "l2_hit_pct": k.get("l2_hit_pct")}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -679,6 +699,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
         "step_hbm_frac": (balg / (ms_per_step * 1e-3) / 1e9 / hbm_peak) if balg else None,
+        "sampling_hbm": sampling_hbm(hbm_peak) if (grid == 160 and world == 1 and args.workload == "cfg2") else None,
         "cpu_baseline": cpu,
         "ref_gpu_baseline": refgpu,
         "train_sphere_extra": sphere_extra,
