@@ -42,7 +42,8 @@ struct Scene {
   Tensor xyz_min, xyz_max, mask, mask_scale, mask_shift;
   Scene(int X, int Y, int Z, int C, Tensor xyz_min_, Tensor xyz_max_, c10::optional<Tensor> mask_,
         c10::optional<Tensor> mask_scale_, c10::optional<Tensor> mask_shift_, double near, double far,
-        double stepdist, double act_shift, double interval, double thres, bool ndc, int ndc_samples)
+        double stepdist, double act_shift, double interval, double thres, bool ndc, int ndc_samples,
+        bool exact_transmittance)
       : xyz_min(xyz_min_), xyz_max(xyz_max_) {
     F32(xyz_min); F32(xyz_max);
     s.X = X; s.Y = Y; s.Z = Z; s.C = C;
@@ -60,6 +61,7 @@ struct Scene {
     s.stepdist = static_cast<float>(stepdist); s.act_shift = static_cast<float>(act_shift);
     s.interval = static_cast<float>(interval); s.fast_color_thres = static_cast<float>(thres);
     s.ndc = ndc ? 1 : 0; s.ndc_samples = ndc_samples;
+    s.exact_transmittance = exact_transmittance ? 1 : 0;
   }
   int max_steps() const { return dvgo_fused_max_steps(&s); }
 };
@@ -453,7 +455,12 @@ void dvgo_bind_mlp(pybind11::module_& m);  // mlp_binding.cpp
 void dvgo_bind_fused(pybind11::module_& m) {
   pybind11::class_<Scene>(m, "Scene")
       .def(pybind11::init<int, int, int, int, Tensor, Tensor, c10::optional<Tensor>, c10::optional<Tensor>,
-                          c10::optional<Tensor>, double, double, double, double, double, double, bool, int>())
+                          c10::optional<Tensor>, double, double, double, double, double, double, bool, int, bool>(),
+           pybind11::arg("X"), pybind11::arg("Y"), pybind11::arg("Z"), pybind11::arg("C"), pybind11::arg("xyz_min"),
+           pybind11::arg("xyz_max"), pybind11::arg("mask"), pybind11::arg("mask_scale"), pybind11::arg("mask_shift"),
+           pybind11::arg("near"), pybind11::arg("far"), pybind11::arg("stepdist"), pybind11::arg("act_shift"),
+           pybind11::arg("interval"), pybind11::arg("thres"), pybind11::arg("ndc"), pybind11::arg("ndc_samples"),
+           pybind11::arg("exact_transmittance") = false)
       .def("max_steps", &Scene::max_steps);
   m.def("ray_setup", &ray_setup);
   m.def("march_fwd", &march_fwd, pybind11::arg("scene"), pybind11::arg("rays_o"), pybind11::arg("rays_d"), pybind11::arg("density"), pybind11::arg("k0_cl"), pybind11::arg("t_min"), pybind11::arg("n_steps"), pybind11::arg("ray_off"), pybind11::arg("slot_alpha"), pybind11::arg("slot_T"), pybind11::arg("slot_expd"), pybind11::arg("slot_code"), pybind11::arg("feat"), pybind11::arg("s_ray"), pybind11::arg("s_slot"), pybind11::arg("s_weight"), pybind11::arg("alphainv_last"), pybind11::arg("counters"), pybind11::arg("s_pos") = pybind11::none());

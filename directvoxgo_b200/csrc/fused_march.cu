@@ -125,7 +125,13 @@ __device__ __forceinline__ void gather_k0(const float* __restrict__ k0, const Co
   }
 }
 
-template <int C>
+// kExactT = false (default): the transmittance of a 32-sample chunk is a shuffle product scan in double, rounded to
+// float once per output (T / weights rel 5e-6 vs the reference, whose `float T_cum` is re-rounded after EVERY sample,
+// render_utils_kernel.cu:447-451).  kExactT = true (scene.exact_transmittance): the warp replays that per-sample
+// recurrence in lock-step over the live lanes of the chunk (all lanes hold the same T_cum; lane j keeps the value it
+// saw at its own sample) -> T, weights, alphainv_last, the early-stop index and hence the survivor SET are bit-exact
+// with the reference kernels, at one dependent cvt-DMUL-cvt step per live sample.
+template <int C, bool kExactT>
 __global__ void __launch_bounds__(256, 4) march_fwd_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, SceneArgs a,
     const float* __restrict__ density, const float* __restrict__ k0, int n_rays,
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(256, 4) march_fwd_kernel(
     const int64_t off = ray_off[r];
     const RayGeom g = ray_geom(sc, rays_o, rays_d, r, t_min[r]);
     double carry = 1.0;
-    float last_T = 1.f;
+    float last_T = 1.f;   // kExactT: the running float T_cum itself
     bool stopped = false;
     for (int base = 0; base < n; base += 32) {
       const int i = base + lane;
@@ -173,19 +179,36 @@ __global__ void __launch_bounds__(256, 4) march_fwd_kernel(
       }
       // transmittance: exclusive product of (1 - alpha + 1e-10) over the samples still alive
       const double f = live ? ((1.0 - static_cast<double>(alpha)) + 1e-10) : 1.0;
-      double incl = f;
+      float T_before, T_after = 0.f;
+      unsigned hits;
+      int first;
+      [[maybe_unused]] double incl = 1.0;
+      if constexpr (kExactT) {
+        T_before = last_T;
+        first = 32;
+        for (unsigned m = __ballot_sync(0xffffffffu, live); m; m &= m - 1) {   // live lanes, near to far (warp-uniform)
+          const int j = __ffs(m) - 1;
+          const double fj = __shfl_sync(0xffffffffu, f, j);
+          if (lane == j) T_before = last_T;                                            // render_utils_kernel.cu:448
+          last_T = __double2float_rn(__dmul_rn(static_cast<double>(last_T), fj));      // :450
+          if (static_cast<double>(last_T) < 1e-3) { first = j; break; }                // :451
+        }
+        hits = first < 32 ? 1u : 0u;
+      } else {
+        incl = f;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl *= up;
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl *= up;
+        }
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.0;
+        T_before = static_cast<float>(carry * excl);
+        T_after = static_cast<float>(carry * incl);
+        const bool hit = live && (static_cast<double>(T_after) < 1e-3);  // render_utils_kernel.cu:451
+        hits = __ballot_sync(0xffffffffu, hit);
+        first = hits ? (__ffs(hits) - 1) : 32;
       }
-      double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-      if (lane == 0) excl = 1.0;
-      const float T_before = static_cast<float>(carry * excl);
-      const float T_after = static_cast<float>(carry * incl);
-      const bool hit = live && (static_cast<double>(T_after) < 1e-3);  // render_utils_kernel.cu:451
-      const unsigned hits = __ballot_sync(0xffffffffu, hit);
-      const int first = hits ? (__ffs(hits) - 1) : 32;
       const bool in_scan = live && lane <= first;            // inside [i_start, i_end)
       const float w = fmul(T_before, alpha);                  // :449
       const bool surv = in_scan && (!use_thres || w > sc.thres);  // lib/dvgo.py:488-494
@@ -216,7 +239,9 @@ __global__ void __launch_bounds__(256, 4) march_fwd_kernel(
           counters[1] = 1;
         }
       }
-      if (hits) {
+      if constexpr (kExactT) {
+        if (hits) stopped = true;  // later chunks have no live lane: last_T stays the reference's final T_cum
+      } else if (hits) {
         stopped = true;  // later chunks only mark their slots as culled
         last_T = __shfl_sync(0xffffffffu, T_after, first);
       } else if (!stopped) {
@@ -603,8 +628,16 @@ DVGO_API int dvgo_fused_march_fwd(const float* rays_o, const float* rays_d, cons
   // 2 rays (warps) per CTA: a CTA holds its slot until its longest ray ends, so small CTAs pack the SMs better
   // (measured on B200, 8192 rays: 8 warps/CTA 0.205 + 0.243 ms for the two march stages, 2 warps/CTA 0.198 + 0.231 ms)
   const int wpb = 2;
-  DVGO_DISPATCH_C(scene->C, (march_fwd_kernel<kC><<<ray_blocks(n_rays, wpb), wpb * 32, 0,
-                                                    as_stream(stream)>>>(
+  if (scene->exact_transmittance) {
+    DVGO_DISPATCH_C(scene->C, (march_fwd_kernel<kC, true><<<ray_blocks(n_rays, wpb), wpb * 32, 0,
+                                                            as_stream(stream)>>>(
+        rays_o, rays_d, to_args(scene), density, k0_cl, n_rays, t_min, n_steps, ray_off, slot_cap,
+        surv_cap, slot_alpha, slot_T, slot_expd, slot_code, feat, s_ray, s_slot, s_weight,
+        alphainv_last, counters, reinterpret_cast<float4*>(s_pos))));
+    return launch_status();
+  }
+  DVGO_DISPATCH_C(scene->C, (march_fwd_kernel<kC, false><<<ray_blocks(n_rays, wpb), wpb * 32, 0,
+                                                             as_stream(stream)>>>(
       rays_o, rays_d, to_args(scene), density, k0_cl, n_rays, t_min, n_steps, ray_off, slot_cap,
       surv_cap, slot_alpha, slot_T, slot_expd, slot_code, feat, s_ray, s_slot, s_weight,
       alphainv_last, counters, reinterpret_cast<float4*>(s_pos))));

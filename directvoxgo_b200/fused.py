@@ -27,7 +27,7 @@ import torch
 from . import adam_upd_cuda, ext
 
 
-def _scene_of(model, rk, ndc=False, ndc_samples=0):
+def _scene_of(model, rk, ndc=False, ndc_samples=0, exact_transmittance=False):
     X, Y, Z = (int(s) for s in model.density.shape[2:])
     C = int(model.k0.shape[1])
     mc = model.mask_cache
@@ -38,7 +38,7 @@ def _scene_of(model, rk, ndc=False, ndc_samples=0):
                      mc.xyz2ijk_shift if mc is not None else None,
                      float(rk["near"]), float(rk["far"]), stepdist, float(model.act_shift),
                      float(rk["stepsize"] * model.voxel_size_ratio), float(model.fast_color_thres),
-                     bool(ndc), int(ndc_samples))
+                     bool(ndc), int(ndc_samples), bool(exact_transmittance))
 
 
 class _Workspace:
@@ -108,13 +108,17 @@ SUPPORTED_C = (3, 4, 6, 8, 9, 12, 16)   # k0 channel counts the fused kernels ar
 
 
 class _FusedBase:
-    def __init__(self, model, render_kwargs, mlp="auto"):
+    def __init__(self, model, render_kwargs, mlp="auto", exact_transmittance=False):
+        """exact_transmittance: the forward march replays the reference's per-sample `float T_cum` recurrence
+        (render_utils_kernel.cu:447-451) instead of its double product scan -- T, weights, alphainv_last, the early-stop
+        index and the survivor set are then bit-exact with the reference kernels (default: scan, T / weights rel 5e-6)."""
         self.model = model
         self.rk = dict(render_kwargs)
         self.device = model.density.device
         self.ndc = hasattr(model, "mpi_depth")
         ndc_samples = int((model.mpi_depth - 1) / self.rk["stepsize"]) + 1 if self.ndc else 0
-        self.scene = _scene_of(model, self.rk, self.ndc, ndc_samples)
+        self.exact_transmittance = bool(exact_transmittance)
+        self.scene = _scene_of(model, self.rk, self.ndc, ndc_samples, self.exact_transmittance)
         self.X, self.Y, self.Z = (int(s) for s in model.density.shape[2:])
         self.C = int(model.k0.shape[1])
         if self.C not in SUPPORTED_C:
@@ -359,8 +363,9 @@ class FusedRenderer(_FusedBase):
 
 class FusedTrainer(_FusedBase):
     def __init__(self, model, cfg_train, render_kwargs, world_size=1, dist_group=None, mlp="auto",
-                 betas=(0.9, 0.99), eps=1e-8, rank=None, shard_sweep=True, global_step=0, exchange="auto"):
-        super().__init__(model, render_kwargs, mlp)
+                 betas=(0.9, 0.99), eps=1e-8, rank=None, shard_sweep=True, global_step=0, exchange="auto",
+                 exact_transmittance=False):
+        super().__init__(model, render_kwargs, mlp, exact_transmittance)
         self.cfg = dict(cfg_train)
         self.world_size = world_size
         self.dist_group = dist_group

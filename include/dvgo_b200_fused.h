@@ -64,6 +64,9 @@ typedef struct dvgo_scene {
   float fast_color_thres;    /* alpha / weight threshold (lib/dvgo.py:478,488); 0 disables both masks */
   int ndc;                   /* 0: sample_pts_on_rays sampler; 1: NDC fixed-count sampler (dmpigo) */
   int ndc_samples;           /* N_samples of the NDC sampler (lib/dmpigo.py:188) */
+  int exact_transmittance;   /* march_fwd: 0 = double product scan, rounded once per output (T / weights rel 5e-6 vs the
+                              * reference); 1 = replay the reference's `float T_cum` recurrence sample by sample
+                              * (render_utils_kernel.cu:447-451): T, weights, stop index and survivor set bit-exact */
 } dvgo_scene_t;
 
 /* Upper bound of samples per ray: ceil((far-near)/stepdist), at least 1 (t is clamped to [near,far],

@@ -290,6 +290,81 @@ def test_fused_full_size_invariants():
     np.testing.assert_allclose(to_np(out["rgb_marched"]), to_np(ref["rgb_marched"]), rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("dens,maskp", [(1.0, 0.0), (6.0, 0.4)])
+def test_exact_transmittance_mode_is_bit_exact_at_full_size(dens, maskp):
+    """scene.exact_transmittance: the fused march replays the reference's per-sample `float T_cum` recurrence
+    (render_utils_kernel.cu:447-451) instead of its double product scan.  At BASELINE size (160^3, 8192 rays) the
+    survivor SET, the weights and alphainv_last must then EQUAL those of the op-by-op path, whose alpha2weight is
+    itself bit-exact with the reference kernel (test_gpu_0_vs_ref.py::test_alpha_ops_vs_reference_kernels) -- no
+    tolerance.  Also times both march variants (reported in gpurun_out/exact_T_cost.json, not asserted)."""
+    import json
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedRenderer
+    m = _fine_model(160, dens_scale=dens, mask_p=maskp).to(DEV)
+    ro, rd, vd, _ = syn.random_training_rays(8192, n_views=100, seed=1000, device=DEV)
+    rk = dict(syn.RENDER_KWARGS)
+    with torch.no_grad():
+        ref = m(ro, rd, vd, global_step=0, **rk)
+    times = {}
+    for exact in (False, True):
+        fr = FusedRenderer(m, rk, mlp="torch", exact_transmittance=exact)
+        out = fr.render(ro, rd, vd)
+        ws = fr._workspace(8192, False)
+        m4 = int(ws.counters[0])
+        assert int(ws.counters[1]) == 0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        wt = fr._workspace(8192, True)
+        for _ in range(3):
+            fr._march(wt, ro, rd)
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(10):
+            fr._march(wt, ro, rd)
+        ev[1].record()
+        torch.cuda.synchronize()
+        times["exact" if exact else "scan"] = ev[0].elapsed_time(ev[1]) / 10
+        if not exact:
+            assert abs(m4 - ref["ray_id"].numel()) <= 4
+            continue
+        assert m4 == ref["ray_id"].numel() and m4 > 100000
+        ray = ws.s_ray[:m4].long()
+        step = ws.s_slot[:m4].long() - ws.ray_off[:-1].long()[ray]
+        order = torch.argsort(ray * 100000 + step)
+        assert torch.equal(ray[order], ref["ray_id"])                        # the same sample set
+        assert torch.equal(ws.s_weight[:m4][order], ref["weights"])          # the same weights, bit for bit
+        assert torch.equal(out["alphainv_last"], ref["alphainv_last"])
+    times.update(survivors=m4, what="ray_setup + march_fwd + k0_gather of one 8192-ray training batch at 160^3, ms")
+    try:
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "exact_T_cost.json")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        old = json.load(open(path)) if os.path.exists(path) else {}
+        old["dens%g_mask%g" % (dens, maskp)] = times
+        json.dump(old, open(path, "w"), indent=1)
+    except OSError:
+        pass
+    print("march stage ms:", times)
+
+
+def test_exact_transmittance_trainer_tracks_the_module_path():
+    """FusedTrainer(exact_transmittance=True): three training steps against the op-by-op ModuleTrainer from the same
+    state -- same tolerances as the default mode (the gradients still go through atomics)."""
+    from directvoxgo_b200 import synthetic as syn
+    from directvoxgo_b200.fused import FusedTrainer
+    from directvoxgo_b200.trainer import ModuleTrainer
+    m1 = _fine_model(40, dens_scale=3.0, mask_p=0.3).to(DEV)
+    m2 = copy.deepcopy(m1)
+    cfg, rk = dict(syn.FINE_TRAIN), dict(syn.RENDER_KWARGS)
+    t1, t2 = ModuleTrainer(m1, cfg, rk), FusedTrainer(m2, cfg, rk, mlp="torch", exact_transmittance=True)
+    for it in range(3):
+        ro, rd, vd, tgt = syn.random_training_rays(2048, n_views=20, seed=50 + it, device=DEV)
+        la, lb = float(t1.step(ro, rd, vd, tgt)), float(t2.step(ro, rd, vd, tgt))
+        assert abs(la - lb) < 1e-5 * max(1.0, abs(la)), (it, la, lb)
+    t2.sync_to_model()
+    for a, b in ((m1.density, m2.density), (m1.k0, m2.k0)):
+        d = np.abs(to_np(a) - to_np(b))
+        assert np.median(d) < 1e-4 and np.quantile(d, 0.999) < 5e-3
+
+
 def _composite_check(keys, n_rays, seed):
     """composite_kernel on a crafted survivor stream vs index_add_ (lib/dvgo.py:554-559, 569-576)."""
     from directvoxgo_b200 import ext
