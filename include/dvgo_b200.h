@@ -28,7 +28,8 @@ extern "C" {
 #endif
 
 #define DVGO_EINVAL (-1)
-#define DVGO_ABI_VERSION 1
+/* 2: dvgo_scene_t (dvgo_b200_fused.h) gained `exact_transmittance`; the float64 entry points (dvgo_b200_f64.h) were added */
+#define DVGO_ABI_VERSION 2
 
 typedef void* dvgo_stream_t; /* cudaStream_t */
 

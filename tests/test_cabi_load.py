@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in declared_symbols() if not hasattr(lib, n)]
     assert not missing, "declared in include/*.h but not exported: %s" % missing
     lib.dvgo_abi_version.restype = ctypes.c_int
-    assert lib.dvgo_abi_version() == 1
+    assert lib.dvgo_abi_version() == 2      # DVGO_ABI_VERSION of include/dvgo_b200.h
     lib.dvgo_build_arch.restype = ctypes.c_char_p
     assert lib.dvgo_build_arch() == b"sm_100a"
 
