@@ -192,6 +192,85 @@ def test_adam_variants(pkg, N):
             assert np.array_equal(to_np(pg)[z], p0.numpy()[z]) and np.array_equal(to_np(mg)[z], m0.numpy()[z])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_alpha2weight_chunk_boundaries_and_early_stops(pkg, dtype):
+    """Crafted rays around the 32-sample chunk boundary of the warp-per-ray kernels: segment lengths 1, 31, 32, 33, 64,
+    65, 200 x constant alphas whose transmittance crosses 1e-3 after 6, 31, 32, 33, 34, 65 samples or never -- the early-stop
+    index, the fills after it (T = 1, weight = 0) and the backward must equal the oracle's serial loop exactly
+    (render_utils_kernel.cu:431-561), in the float32 and in the float64 instantiation."""
+    from oracle import oracle_f64 as orc64
+    o = orc if dtype == torch.float32 else orc64
+    lengths = [1, 31, 32, 33, 64, 65, 200]
+    # T after k samples = (1 - a)^k: first k with (1-a)^k < 1e-3 is ceil(ln 1e-3 / ln(1-a))
+    alphas = [0.7, 0.2056, 0.1995, 0.1941, 0.1886, 0.1023, 0.0]     # kept samples: 6, 31, 32, 33, 34, 65, all
+    ray_id, alpha = [], []
+    r = 0
+    for n in lengths:
+        for a in alphas:
+            ray_id += [r] * n
+            alpha += [a] * n
+            r += 2                      # odd ray ids stay empty
+    n_rays = r
+    ray_id = torch.tensor(ray_id, dtype=torch.int64)
+    alpha = torch.tensor(alpha, dtype=dtype)
+    g = torch.Generator().manual_seed(4)
+    gw = torch.randn(alpha.numel(), generator=g, dtype=dtype)
+    gl = torch.randn(n_rays, generator=g, dtype=dtype)
+    ref = o.alpha2weight(alpha, ray_id, n_rays)
+    got = pkg.render_utils_cuda.alpha2weight(alpha.to(DEV), ray_id.to(DEV), n_rays)
+    stops = (ref[4] - ref[3])[::2].reshape(len(lengths), len(alphas))
+    assert stops[-1].tolist() == [6, 31, 32, 33, 34, 65, 200], stops[-1].tolist()     # the crafted stops are really hit
+    for name, x, y in zip(("weight", "T", "alphainv_last", "i_start", "i_end"), got, ref):
+        assert x.dtype == y.dtype and np.array_equal(to_np(x), to_np(y)), name
+    g_ref = o.alpha2weight_backward(alpha, *ref, n_rays, gw, gl)
+    g_got = pkg.render_utils_cuda.alpha2weight_backward(alpha.to(DEV), *got, n_rays, gw.to(DEV), gl.to(DEV))
+    assert np.array_equal(to_np(g_got), to_np(g_ref))
+    seg_end = (ref[3] + torch.bincount(ray_id, minlength=n_rays)).tolist()
+    past = torch.cat([torch.arange(int(s), int(e)) for s, e in zip(ref[4].tolist(), seg_end) if e > s])
+    assert past.numel() > 100 and float(g_ref[past].abs().max()) == 0.0           # no gradient past the stop (:538)
+
+
+def test_degenerate_shapes(pkg):
+    """Empty ray batch, a ray that misses the box (>= 1 sample, render_utils_kernel.cu:46-47), a grid with size-1
+    axes, Adam on a 4-byte-offset (not 16-byte aligned) view with N % 4 != 0 -- all against the oracle."""
+    ru, tv, ad = pkg.render_utils_cuda, pkg.total_variation_cuda, pkg.adam_upd_cuda
+    lo, hi = _box()
+    e3 = torch.zeros(0, 3, device=DEV)
+    out = ru.sample_pts_on_rays(e3, e3, lo.to(DEV), hi.to(DEV), 0.2, 6.0, 0.05)
+    assert [tuple(t.shape) for t in out] == [(0, 3), (0,), (0,), (0,), (0,), (0,), (0,)]
+    assert out[1].dtype == torch.bool and out[2].dtype == torch.int64 and out[4].dtype == torch.int64
+    ro = torch.tensor([[5.0, 5.0, 5.0], [0.0, 0.0, -3.0]])
+    rd = torch.tensor([[1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])       # ray 0 misses the box; ray 1 has two zero components
+    ref = orc.sample_pts_on_rays(ro, rd, lo, hi, 0.2, 6.0, 0.05)
+    got = ru.sample_pts_on_rays(ro.to(DEV), rd.to(DEV), lo.to(DEV), hi.to(DEV), 0.2, 6.0, 0.05)
+    assert int(ref[4][0]) == 1 and bool(ref[1][0])               # one sample, outside the box
+    for a, b in zip(got, ref):
+        assert np.array_equal(to_np(a), to_np(b))
+    g = torch.Generator().manual_seed(8)
+    for shape in [(1, 2, 1, 5, 1), (1, 1, 1, 1, 1), (1, 3, 4, 1, 6)]:
+        param = torch.randn(shape, generator=g)
+        grad = torch.randn(shape, generator=g)
+        grad.view(-1)[::2] = 0
+        for dense in (False, True):
+            r = grad.clone()
+            orc.total_variation_add_grad(param, r, 0.3, 0.7, 1.3, dense)
+            x = grad.clone().to(DEV)
+            tv.total_variation_add_grad(param.to(DEV), x, 0.3, 0.7, 1.3, dense)
+            assert ulp_diff(to_np(x), to_np(r)).max() <= 1, (shape, dense)
+    N = 1027
+    base = [torch.randn(N + 1, generator=g), torch.randn(N + 1, generator=g), torch.randn(N + 1, generator=g) * 0.01,
+            torch.rand(N + 1, generator=g) * 1e-3]
+    base[1][torch.rand(N + 1, generator=g) < 0.4] = 0
+    cpu = [t.clone()[1:].contiguous() for t in base]
+    dev = [t.clone().to(DEV)[1:] for t in base]                   # storage offset 4 bytes: the scalar path
+    assert all(t.data_ptr() % 16 == 4 and t.is_contiguous() for t in dev)
+    for step in (1, 2):
+        orc.masked_adam_upd(cpu[0], cpu[1], cpu[2], cpu[3], step, 0.9, 0.99, 0.1, 1e-8)
+        ad.masked_adam_upd(dev[0], dev[1], dev[2], dev[3], step, 0.9, 0.99, 0.1, 1e-8)
+    for a, b in zip(dev, cpu):
+        assert ulp_diff(to_np(a), to_np(b)).max() <= 1
+
+
 def test_raw_c_abi_call(pkg):
     """Call the shared library directly (ctypes, raw device pointers, explicit stream) -- the path a
     non-torch host would take."""
