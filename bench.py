@@ -224,6 +224,21 @@ def train_sphere_metric(model, rk, cfg, dev_batches, device, steps=100):
     return out
 
 
+def exact_transmittance_metric(grid, device, dev_batches, steps, warm):
+    """Extra (not the headline): the same cfg-2 step from the same random-init state with
+    FusedTrainer(exact_transmittance=True), i.e. the forward march replaying the reference's per-sample float T_cum
+    recurrence (survivor set / weights bit-identical to the reference kernels) instead of the double product scan."""
+    from directvoxgo_b200.fused import FusedTrainer
+    fresh, rk2, cfg2 = build_problem(grid, device)
+    tr = FusedTrainer(fresh, cfg2, rk2, exact_transmittance=True)
+    snap = tr.snapshot()
+    k = warm % len(dev_batches)            # the headline pass times its step i on batch (warm + i) mod nb: same order here
+    ms, surv, loss = time_trainer(tr, dev_batches[k:] + dev_batches[:k], steps, max(warm, 3), snap)
+    n = dev_batches[0][0].shape[0]
+    return {"ms_per_step": ms, "rays_per_s": n / ms * 1e3, "survivors_per_step": surv, "steps": steps, "last_loss": loss,
+            "what": "cfg2 step with the bit-exact transmittance instantiation of march_fwd (opt-in; default = double scan)"}
+
+
 def render_metric(model, rk, device, n_frames=2, chunk=65536, label="", rank=0, world=1):
     """Secondary metric of BASELINE.json: ms per rendered 800x800 frame (run.py:57-110: rays of a view ->
     chunks -> forward, render_depth=True), device-timed with CUDA events, rays generated on the device."""
@@ -565,7 +580,7 @@ def run_ours(args):
     value = n_global / (ms_per_step * 1e-3)
 
     # ---- secondary measurements (never inside the timed regions) -------------------------------------------------
-    render, sphere_extra, cfg5_extra = None, None, None
+    render, sphere_extra, cfg5_extra, exact_extra = None, None, None, None
     if not args.no_render and args.workload == "cfg2":      # every rank renders its share of the views
         try:
             fresh, rk2, _ = build_problem(grid, device)      # random-init N(0,1): what BASELINE configs[2] names
@@ -588,6 +603,10 @@ def run_ours(args):
             del fresh
         except Exception as e:
             sphere_extra = {"error": repr(e)[:300]}
+        try:
+            exact_extra = exact_transmittance_metric(grid, device, dev_batches, args.steps, args.warmup)
+        except Exception as e:
+            exact_extra = {"error": repr(e)[:300]}
     stages_main, U, M0 = main.get("stages"), main.get("U"), main.get("M0")
     surv = main.get("survivors_per_step")
     launches = main["launches"]
@@ -704,6 +723,7 @@ def run_ours(args):
         "ref_gpu_baseline": refgpu,
         "train_sphere_extra": sphere_extra,
         "cfg5_extra": cfg5_extra,
+        "exact_transmittance_extra": exact_extra,
         "render_800x800": render,
     }
     print(json.dumps(line), flush=True)
