@@ -5,7 +5,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host;
  *   - tensors are dense, row-major, fp32 / int64 / uint8(bool) exactly as the reference's torch
- *     tensors are (lib/cuda/render_utils.cpp:40-42 CHECK_CUDA + CHECK_CONTIGUOUS);
+ *     tensors are (lib/cuda/render_utils.cpp:40-42 CHECK_CUDA + CHECK_CONTIGUOUS); the float64
+ *     instantiation the reference's AT_DISPATCH_FLOATING_TYPES also provides is declared in
+ *     dvgo_b200_f64.h (same entry points with an _f64 suffix and double* tensors);
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream, what the reference
  *     uses, lib/cuda/render_utils_kernel.cu:87); all work is enqueued asynchronously on it, no
  *     entry point synchronises the device or allocates memory unless it says so;
