@@ -40,3 +40,41 @@ def test_f64_oracle_agrees_with_f32_oracle_on_float_inputs():
     assert np.array_equal(t32.astype(np.float64), b[5].numpy())               # t_min is a float value in a double tensor
     assert ulp_diff(a[5].numpy(), t32).max() <= 1                             # ... within one float ulp of the f32 clip
     assert (a[4] - b[4]).abs().max() <= 1 and (a[4] == b[4]).float().mean() > 0.98
+
+
+def test_f64_oracle_invariants():
+    """Size-independent properties of the restated double instantiation (render_utils_kernel.cu:431-505): the weights
+    of a ray telescope to 1 - alphainv_last up to the float rounding of T_cum; T is non-increasing inside the kept
+    range; samples past the early stop keep the fills (T = 1, weight = 0); the backward equals the analytic gradient
+    of sum_i gw_i w_i + gl * alphainv_last to float precision on rays without an early stop."""
+    from tests.util import sorted_ray_ids
+    n_rays, n_pts = 200, 30000
+    rid = sorted_ray_ids(n_rays, n_pts, 21)
+    g = torch.Generator().manual_seed(22)
+    alpha = (torch.rand(n_pts, generator=g, dtype=torch.float64) ** 3 * 0.5)
+    w, T, last, i_s, i_e = o.alpha2weight(alpha, rid, n_rays)
+    seg = torch.bincount(rid, minlength=n_rays)
+    wsum = torch.zeros(n_rays, dtype=torch.float64).index_add_(0, rid, w)
+    assert float((wsum + last - 1).abs().max()) < 5e-5          # float T_cum, up to ~600 samples per ray
+    for r in range(n_rays):
+        s, e, end = int(i_s[r]), int(i_e[r]), int(i_s[r]) + int(seg[r])
+        if seg[r] == 0:
+            assert s == 0 and e == 0 and float(last[r]) == 1.0
+            continue
+        assert torch.all(T[s:e][1:] <= T[s:e][:-1]) and float(T[s]) == 1.0
+        assert torch.all(T[e:end] == 1.0) and torch.all(w[e:end] == 0.0)
+        assert e == end or float(last[r]) < 1e-3
+    # analytic gradient in double on a stop-free problem (small alphas): d/d alpha_k of sum gw_i T_i alpha_i + gl T_end
+    n_rays, per = 50, 20
+    rid = torch.arange(n_rays).repeat_interleave(per)
+    alpha = (0.01 + 0.1 * torch.rand(n_rays * per, generator=g, dtype=torch.float64)).requires_grad_(True)
+    gw = torch.randn(n_rays * per, generator=g, dtype=torch.float64)
+    gl = torch.randn(n_rays, generator=g, dtype=torch.float64)
+    f = (1 - alpha + 1e-10).view(n_rays, per)
+    Tt = torch.cat([torch.ones(n_rays, 1, dtype=torch.float64), torch.cumprod(f, 1)], 1)
+    loss = (gw.view(n_rays, per) * Tt[:, :-1] * alpha.view(n_rays, per)).sum() + (gl * Tt[:, -1]).sum()
+    loss.backward()
+    a = alpha.detach()
+    w, T, last, i_s, i_e = o.alpha2weight(a, rid, n_rays)
+    got = o.alpha2weight_backward(a, w, T, last, i_s, i_e, n_rays, gw, gl)
+    assert float((got - alpha.grad).abs().max()) < 2e-6 * float(alpha.grad.abs().max())
